@@ -1,0 +1,21 @@
+"""depth-lidar-nerf_b200 — B200 (sm_100a) implementation of the ray-rendering training hot path of
+mertkiray/depth-lidar-nerf behind the reference's own Python call signatures.
+
+The directory name carries a hyphen, so import it as ``import dlnerf_b200`` (alias module at the repo
+root) or ``importlib.import_module("depth-lidar-nerf_b200")``.
+
+Layout:  csrc/ (CUDA kernels + C ABI, include/dlnerf_b200.h)  ·  _lib.py (loader)  ·  plan.py (static MLP
+plans)  ·  ops.py (torch wrappers)  ·  run_nerf_helpers.py / run_nerf.py (mirrors of the reference modules)
+·  train.py (fused train step, ray-sharded data parallel).
+"""
+from . import _lib
+from ._lib import build, lib
+from . import ops
+from .run_nerf_helpers import (Embedder, NeRF, get_embedder, img2mse, mse2psnr, ndc_rays, raw2outputs,
+                               sample_pdf, to8b)
+from .run_nerf import (FusedQuery, batchify, batchify_rays, create_nerf, get_rays, render, render_rays,
+                       run_network)
+
+__all__ = ["build", "lib", "ops", "Embedder", "NeRF", "get_embedder", "img2mse", "mse2psnr", "ndc_rays",
+           "raw2outputs", "sample_pdf", "to8b", "FusedQuery", "batchify", "batchify_rays", "create_nerf",
+           "get_rays", "render", "render_rays", "run_network"]

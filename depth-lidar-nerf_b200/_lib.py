@@ -1,0 +1,132 @@
+"""Loader for the C-ABI library (include/dlnerf_b200.h) and ctypes mirrors of its structs.
+
+There is NO CPU fallback: if ``libdlnerf_b200.so`` has not been built
+(``python -c "import __graft_entry__ as g; g.build()"``) every op raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(_HERE)
+CSRC = os.path.join(_HERE, "csrc")
+SO_PATH = os.path.join(_HERE, "libdlnerf_b200.so")
+SOURCES = ["render_kernels.cu", "mlp_kernels.cu"]
+
+MAX_STEPS = 12
+MAX_KSLABS = 6
+SLAB_BYTES = 16384
+TILE_ROWS = 128
+
+EPI_RELU, EPI_RELU_SIGMA, EPI_LINEAR, EPI_RELU_RGB, EPI_RELU_OUT = 0, 1, 2, 3, 4
+EPI_BWD_COPY, EPI_BWD_MASK, EPI_BWD_MASK_SIGMA = 8, 9, 10
+
+
+class ChainStep(C.Structure):
+    _fields_ = [("w_off", C.c_uint32), ("bias_off", C.c_uint32), ("head_off", C.c_uint32),
+                ("head_bias_off", C.c_uint32), ("n_out", C.c_uint16), ("nk", C.c_uint8), ("epi", C.c_uint8),
+                ("kslab", C.c_uint8 * MAX_KSLABS), ("kcnt", C.c_uint8 * MAX_KSLABS),
+                ("stash_slot", C.c_int16), ("mask_slot", C.c_int16), ("n_heads", C.c_uint8),
+                ("pad_", C.c_uint8 * 3)]
+
+
+class ChainProgram(C.Structure):
+    _fields_ = [("n_steps", C.c_int32), ("backward", C.c_int32), ("use_viewdirs", C.c_int32),
+                ("out_ch", C.c_int32), ("L_pts", C.c_int32), ("L_dir", C.c_int32), ("stash_slots", C.c_int32),
+                ("mask_slots", C.c_int32), ("pro_head_off", C.c_int32), ("pro_mask_slot", C.c_int32),
+                ("pro_slot", C.c_int32), ("pad_", C.c_int32), ("steps", ChainStep * MAX_STEPS)]
+
+
+class ChainArgs(C.Structure):
+    _fields_ = [("P", C.c_longlong), ("rays", C.c_void_p), ("ray_stride", C.c_int32), ("vd_col", C.c_int32),
+                ("z", C.c_void_p), ("S", C.c_int32), ("x", C.c_void_p), ("x_ld", C.c_int32),
+                ("wblob", C.c_void_p), ("fblob", C.c_void_p), ("out", C.c_void_p), ("d_out", C.c_void_p),
+                ("stash", C.c_void_p), ("masks", C.c_void_p)]
+
+
+class WgradItem(C.Structure):
+    _fields_ = [("a_bwd_stash", C.c_int32), ("a_slot", C.c_int32), ("a_nslab", C.c_int32),
+                ("b_from_bwd", C.c_int32), ("b_slot", C.c_int32), ("b_nslab", C.c_int32),
+                ("dw_off", C.c_int64), ("ld", C.c_int32), ("col_off", C.c_int32), ("n_cols", C.c_int32),
+                ("row_off", C.c_int32), ("n_rows", C.c_int32), ("db_off", C.c_int64),
+                ("db_col_off", C.c_int32), ("db_n", C.c_int32)]
+
+
+class PackJob(C.Structure):
+    _fields_ = [("src_off", C.c_int64), ("ld", C.c_int32), ("row0", C.c_int32), ("col0", C.c_int32),
+                ("n_valid", C.c_int32), ("k_valid", C.c_int32), ("transposed", C.c_int32),
+                ("n_rows", C.c_int32), ("dst_off", C.c_uint32)]
+
+
+_P, _I, _F, _LL = C.c_void_p, C.c_int, C.c_float, C.c_longlong
+
+# name -> argtypes; every function returns int.  Must list EVERY symbol include/dlnerf_b200.h declares
+# (tests/test_abi.py parses the header and compares).
+SIGNATURES = {
+    "dln_stratified_z": [_P, _I, _P, _P, _I, _I, _I, _P],
+    "dln_posenc": [_P, _P, _LL, _I, _P],
+    "dln_composite_fwd": [_P, _I, _P, _P, _P, _F, _I, _P, _P, _P, _P, _P, _I, _I, _P],
+    "dln_composite_bwd": [_P, _I, _P, _P, _P, _F, _I, _P, _P, _P, _P, _P, _P, _I, _I, _P],
+    "dln_composite_bwd_fused_loss": [_P, _I, _P, _P, _P, _F, _I, _P, _P, _P, _I, _F, _F, _I, _F, _P, _P, _I, _I, _P],
+    "dln_sample_pdf": [_P, _I, _I, _P, _I, _I, _P, _I, _P, _P, _I, _P, _P, _P, _I, _P],
+    "dln_searchsorted": [_P, _I, _I, _P, _I, _I, _P, _I, _P],
+    "dln_mlp_chain": [C.POINTER(ChainProgram), C.POINTER(ChainArgs), _I, _P],
+    "dln_mlp_wgrad": [_P, _I, _I, _P, _I, _P, _I, _LL, _P, _P],
+    "dln_mlp_pack_weights": [_P, _P, _I, _P, _P],
+    "dln_abi_sizes": [C.POINTER(C.c_int)],
+}
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "--expt-relaxed-constexpr", "-shared", "-Xcompiler", "-fPIC"]
+
+
+def build(verbose: bool = False, force: bool = False) -> str:
+    """Compile csrc/*.cu for sm_100a into the in-tree shared library (nvcc cross-compiles without a GPU)."""
+    srcs = [os.path.join(CSRC, s) for s in SOURCES]
+    deps = srcs + [os.path.join(CSRC, "common.cuh"), os.path.join(ROOT, "include", "dlnerf_b200.h")]
+    if not force and os.path.exists(SO_PATH) and all(os.path.getmtime(SO_PATH) >= os.path.getmtime(d) for d in deps):
+        return SO_PATH
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO_PATH] + srcs
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stderr)
+    return SO_PATH
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """The loaded library; raises (loudly) if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise RuntimeError(
+                "dlnerf_b200: %s is missing; there is no CPU fallback. Build it with "
+                "`python -c 'import __graft_entry__ as g; g.build()'`." % SO_PATH)
+        l = C.CDLL(SO_PATH)
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.argtypes = argtypes
+            fn.restype = C.c_int
+        l.dln_build_info.restype = C.c_char_p
+        l.dln_build_info.argtypes = []
+        _lib = l
+    return _lib
+
+
+class DlnError(RuntimeError):
+    pass
+
+
+def check(rc: int, what: str) -> None:
+    if rc == 0:
+        return
+    if rc == -1:
+        raise DlnError("%s: invalid argument (shape / alignment / null pointer)" % what)
+    raise DlnError("%s: CUDA error %d" % (what, rc))

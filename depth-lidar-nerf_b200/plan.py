@@ -1,0 +1,271 @@
+"""Static execution plan of one NeRF network for the tcgen05 MLP kernels.
+
+Given the network shape (run_nerf_helpers.py:78-111) this builds, once:
+  * the flat fp32 parameter layout (reference registration order, so optimizer / checkpoint
+    ordering is unchanged),
+  * the forward and dgrad chain programs (``DlnChainProgram``),
+  * the weight-pack jobs (fp32 -> bf16 swizzled stages) for both chains,
+  * the wgrad items and the stash slot maps.
+Everything here is host-side integer bookkeeping; no arithmetic on tensor data.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Sequence, Tuple
+
+from . import _lib as L
+
+
+def _ceil_div(a: int, b: int) -> int:
+    return (a + b - 1) // b
+
+
+@dataclass
+class NetShape:
+    D: int = 8
+    W: int = 256
+    input_ch: int = 63
+    input_ch_views: int = 27
+    output_ch: int = 5
+    skips: Sequence[int] = (4,)
+    use_viewdirs: bool = True
+
+    def validate(self) -> None:
+        if self.W != 256:
+            raise NotImplementedError("the sm_100a MLP kernels are built for netwidth W=256 (got %d)" % self.W)
+        if self.D < 1 or self.D + 2 > L.MAX_STEPS:
+            raise NotImplementedError("netdepth must be in [1, %d]" % (L.MAX_STEPS - 2))
+        if self.input_ch > 64 or self.input_ch_views > 64:
+            raise NotImplementedError("encoded inputs wider than 64 channels are not supported")
+        if (self.input_ch - 3) % 6 or (self.input_ch_views - 3) % 6:
+            raise NotImplementedError("input widths must be 3+6L (get_embedder)")
+        for s in self.skips:
+            if s == self.D - 1:
+                raise ValueError("a skip after the last layer changes alpha_linear's fan-in; the reference "
+                                 "module cannot be built that way either (run_nerf_helpers.py:91,:119)")
+        if not self.use_viewdirs and not (1 <= self.output_ch <= 5):
+            raise NotImplementedError("output_ch must be in [1,5]")
+
+    @property
+    def L_pts(self) -> int:
+        return (self.input_ch - 3) // 6
+
+    @property
+    def L_dir(self) -> int:
+        return (self.input_ch_views - 3) // 6
+
+    @property
+    def out_ch(self) -> int:
+        """Channels of the network output row."""
+        return 4 if self.use_viewdirs else self.output_ch
+
+    def fan_in(self, i: int) -> int:
+        if i == 0:
+            return self.input_ch
+        return self.W + self.input_ch if (i - 1) in self.skips else self.W
+
+    def param_shapes(self) -> List[Tuple[str, Tuple[int, ...]]]:
+        """Registration order of the reference module (run_nerf_helpers.py:90-111)."""
+        out: List[Tuple[str, Tuple[int, ...]]] = []
+        for i in range(self.D):
+            out.append(("pts_linears.%d.weight" % i, (self.W, self.fan_in(i))))
+            out.append(("pts_linears.%d.bias" % i, (self.W,)))
+        out.append(("views_linears.0.weight", (self.W // 2, self.input_ch_views + self.W)))
+        out.append(("views_linears.0.bias", (self.W // 2,)))
+        if self.use_viewdirs:
+            out += [("feature_linear.weight", (self.W, self.W)), ("feature_linear.bias", (self.W,)),
+                    ("alpha_linear.weight", (1, self.W)), ("alpha_linear.bias", (1,)),
+                    ("rgb_linear.weight", (3, self.W // 2)), ("rgb_linear.bias", (3,))]
+        else:
+            out += [("output_linear.weight", (self.output_ch, self.W)), ("output_linear.bias", (self.output_ch,))]
+        return out
+
+
+@dataclass
+class Plan:
+    shape: NetShape
+    offsets: Dict[str, int] = field(default_factory=dict)   # float offsets into the flat parameter buffer
+    n_params: int = 0
+    fwd: L.ChainProgram = None
+    bwd: L.ChainProgram = None
+    fwd_jobs: List[L.PackJob] = field(default_factory=list)
+    bwd_jobs: List[L.PackJob] = field(default_factory=list)
+    fwd_blob_bytes: int = 0
+    bwd_blob_bytes: int = 0
+    wgrad: List[L.WgradItem] = field(default_factory=list)
+    fwd_slots: int = 0
+    bwd_slots: int = 0
+    mask_slots: int = 0
+
+
+def _set_k(step: L.ChainStep, slabs: List[int], cnts: List[int]) -> None:
+    step.nk = len(slabs)
+    for j, (s, c) in enumerate(zip(slabs, cnts)):
+        step.kslab[j] = s
+        step.kcnt[j] = c
+
+
+def build_plan(shape: NetShape) -> Plan:
+    shape.validate()
+    D, W = shape.D, shape.W
+    pl = Plan(shape=shape)
+    off = 0
+    for name, shp in shape.param_shapes():
+        pl.offsets[name] = off
+        n = 1
+        for d in shp:
+            n *= d
+        off += (n + 3) // 4 * 4      # keep every tensor 16-byte aligned inside the flat buffer
+    pl.n_params = off
+    O = pl.offsets
+    kc_pts = _ceil_div(shape.input_ch, 16)
+    kc_dir = _ceil_div(shape.input_ch_views, 16)
+
+    # ------------------------------------------------------------------ forward chain
+    fwd = L.ChainProgram()
+    fwd.backward, fwd.use_viewdirs, fwd.out_ch = 0, int(shape.use_viewdirs), shape.out_ch
+    fwd.L_pts, fwd.L_dir = shape.L_pts, shape.L_dir
+    blob = 0
+    steps = 0
+
+    def add_job(jobs, name, ld, row0, col0, n_valid, k_valid, transposed, n_rows, dst):
+        jobs.append(L.PackJob(O[name], ld, row0, col0, n_valid, k_valid, transposed, n_rows, dst))
+
+    H_slot = lambda i: 2 + 4 * i          # forward stash slot of the output of pts layer i
+    for i in range(D):
+        st = fwd.steps[steps]
+        wname = "pts_linears.%d.weight" % i
+        ld = shape.fan_in(i)
+        st.w_off, st.bias_off, st.n_out = blob, O["pts_linears.%d.bias" % i], 256
+        if i == 0:
+            slabs, cnts, cols = [4], [kc_pts], [(0, shape.input_ch)]
+        elif (i - 1) in shape.skips:
+            slabs = [4, 0, 1, 2, 3]
+            cnts = [kc_pts, 4, 4, 4, 4]
+            cols = [(0, shape.input_ch)] + [(shape.input_ch + 64 * j, 64) for j in range(4)]
+        else:
+            slabs, cnts, cols = [0, 1, 2, 3], [4, 4, 4, 4], [(64 * j, 64) for j in range(4)]
+        _set_k(st, slabs, cnts)
+        for (c0, kv) in cols:
+            add_job(pl.fwd_jobs, wname, ld, 0, c0, 256, kv, 0, 256, blob)
+            blob += 256 * 128
+        st.stash_slot, st.mask_slot = H_slot(i), i
+        st.epi = L.EPI_RELU
+        if i == D - 1:
+            if shape.use_viewdirs:
+                st.epi, st.n_heads = L.EPI_RELU_SIGMA, 1
+                st.head_off, st.head_bias_off = O["alpha_linear.weight"], O["alpha_linear.bias"]
+            else:
+                st.epi, st.n_heads = L.EPI_RELU_OUT, shape.output_ch
+                st.head_off, st.head_bias_off = O["output_linear.weight"], O["output_linear.bias"]
+        steps += 1
+    feat_slot = H_slot(D)
+    hv_slot = feat_slot + 4
+    if shape.use_viewdirs:
+        st = fwd.steps[steps]
+        st.w_off, st.bias_off, st.n_out, st.epi = blob, O["feature_linear.bias"], 256, L.EPI_LINEAR
+        _set_k(st, [0, 1, 2, 3], [4, 4, 4, 4])
+        for j in range(4):
+            add_job(pl.fwd_jobs, "feature_linear.weight", W, 0, 64 * j, 256, 64, 0, 256, blob)
+            blob += 256 * 128
+        st.stash_slot, st.mask_slot = feat_slot, -1
+        steps += 1
+        st = fwd.steps[steps]
+        st.w_off, st.bias_off, st.n_out, st.epi = blob, O["views_linears.0.bias"], 128, L.EPI_RELU_RGB
+        _set_k(st, [0, 1, 2, 3, 5], [4, 4, 4, 4, kc_dir])
+        ldv = W + shape.input_ch_views
+        for j in range(4):
+            add_job(pl.fwd_jobs, "views_linears.0.weight", ldv, 0, 64 * j, 128, 64, 0, 128, blob)
+            blob += 128 * 128
+        add_job(pl.fwd_jobs, "views_linears.0.weight", ldv, 0, W, 128, shape.input_ch_views, 0, 128, blob)
+        blob += 128 * 128
+        st.n_heads, st.head_off, st.head_bias_off = 3, O["rgb_linear.weight"], O["rgb_linear.bias"]
+        st.stash_slot, st.mask_slot = hv_slot, D
+        steps += 1
+        pl.fwd_slots = hv_slot + 2
+        pl.mask_slots = D + 1
+    else:
+        pl.fwd_slots = feat_slot
+        pl.mask_slots = D
+    fwd.n_steps, fwd.stash_slots, fwd.mask_slots = steps, pl.fwd_slots, pl.mask_slots
+    pl.fwd, pl.fwd_blob_bytes = fwd, blob
+
+    # ------------------------------------------------------------------ dgrad chain
+    bwd = L.ChainProgram()
+    bwd.backward, bwd.use_viewdirs, bwd.out_ch = 1, int(shape.use_viewdirs), shape.out_ch
+    bwd.L_pts, bwd.L_dir = shape.L_pts, shape.L_dir
+    blob = 0
+    steps = 0
+    bwd.pro_slot = 1
+    if shape.use_viewdirs:
+        bwd.pro_head_off, bwd.pro_mask_slot = O["rgb_linear.weight"], D
+        dzv_slot, dzf_slot = 1, 3
+        dz_slot = lambda l: 7 + 4 * (D - 1 - l)
+        ldv = W + shape.input_ch_views
+        st = bwd.steps[steps]            # d feature = dZ_v * W_views[:, :W]
+        st.w_off, st.n_out, st.epi = blob, 256, L.EPI_BWD_COPY
+        _set_k(st, [0, 1], [4, 4])
+        for j in range(2):
+            add_job(pl.bwd_jobs, "views_linears.0.weight", ldv, 64 * j, 0, 256, 64, 1, 256, blob)
+            blob += 256 * 128
+        st.stash_slot, st.mask_slot = dzf_slot, -1
+        steps += 1
+        st = bwd.steps[steps]            # dH_{D-1} = d feature * W_feature + d sigma * w_alpha ; mask
+        st.w_off, st.n_out, st.epi = blob, 256, L.EPI_BWD_MASK_SIGMA
+        _set_k(st, [0, 1, 2, 3], [4, 4, 4, 4])
+        for j in range(4):
+            add_job(pl.bwd_jobs, "feature_linear.weight", W, 64 * j, 0, 256, 64, 1, 256, blob)
+            blob += 256 * 128
+        st.n_heads, st.head_off = 1, O["alpha_linear.weight"]
+        st.stash_slot, st.mask_slot = dz_slot(D - 1), D - 1
+        steps += 1
+    else:
+        bwd.pro_head_off, bwd.pro_mask_slot = O["output_linear.weight"], D - 1
+        dz_slot = lambda l: 1 + 4 * (D - 1 - l)
+    for l in range(D - 1, 0, -1):        # dH_{l-1} = dZ_l * W_l[:, h-part] ; mask_{l-1}
+        st = bwd.steps[steps]
+        st.w_off, st.n_out, st.epi = blob, 256, L.EPI_BWD_MASK
+        _set_k(st, [0, 1, 2, 3], [4, 4, 4, 4])
+        c0 = shape.input_ch if (l - 1) in shape.skips else 0
+        for j in range(4):
+            add_job(pl.bwd_jobs, "pts_linears.%d.weight" % l, shape.fan_in(l), 64 * j, c0, 256, 64, 1, 256, blob)
+            blob += 256 * 128
+        st.stash_slot, st.mask_slot = dz_slot(l - 1), l - 1
+        steps += 1
+    if steps == 0:
+        raise NotImplementedError("netdepth=1 without view directions has no hidden dgrad step")
+    pl.bwd_slots = dz_slot(0) + 4
+    bwd.n_steps, bwd.stash_slots, bwd.mask_slots = steps, pl.bwd_slots, pl.mask_slots
+    pl.bwd, pl.bwd_blob_bytes = bwd, blob
+
+    # ------------------------------------------------------------------ wgrad items
+    def item(a_slot, a_n, b_slot, b_n, wname, ld, col_off, n_cols, row_off, n_rows, bname=None, db_col=0, db_n=0):
+        it = L.WgradItem()
+        it.a_bwd_stash, it.a_slot, it.a_nslab = 1, a_slot, a_n
+        it.b_from_bwd, it.b_slot, it.b_nslab = 0, b_slot, b_n
+        it.dw_off, it.ld, it.col_off, it.n_cols = O[wname], ld, col_off, n_cols
+        it.row_off, it.n_rows = row_off, n_rows
+        it.db_off = O[bname] if bname else -1
+        it.db_col_off, it.db_n = db_col, db_n
+        pl.wgrad.append(it)
+
+    for l in range(D):
+        wn, bn, ld = "pts_linears.%d.weight" % l, "pts_linears.%d.bias" % l, shape.fan_in(l)
+        if l == 0:
+            item(dz_slot(0), 4, 0, 1, wn, ld, 0, shape.input_ch, 0, 256, bn, 0, 256)
+        elif (l - 1) in shape.skips:
+            item(dz_slot(l), 4, 0, 1, wn, ld, 0, shape.input_ch, 0, 256, bn, 0, 256)
+            item(dz_slot(l), 4, H_slot(l - 1), 4, wn, ld, shape.input_ch, 256, 0, 256)
+        else:
+            item(dz_slot(l), 4, H_slot(l - 1), 4, wn, ld, 0, 256, 0, 256, bn, 0, 256)
+    if shape.use_viewdirs:
+        item(dzf_slot, 4, H_slot(D - 1), 4, "feature_linear.weight", W, 0, 256, 0, 256, "feature_linear.bias", 0, 256)
+        item(0, 1, H_slot(D - 1), 4, "alpha_linear.weight", W, 0, 256, 3, 1, "alpha_linear.bias", 3, 1)
+        ldv = W + shape.input_ch_views
+        item(dzv_slot, 2, feat_slot, 4, "views_linears.0.weight", ldv, 0, 256, 0, 128, "views_linears.0.bias", 0, 128)
+        item(dzv_slot, 2, 1, 1, "views_linears.0.weight", ldv, W, shape.input_ch_views, 0, 128)
+        item(0, 1, hv_slot, 2, "rgb_linear.weight", W // 2, 0, 128, 0, 3, "rgb_linear.bias", 0, 3)
+    else:
+        item(0, 1, H_slot(D - 1), 4, "output_linear.weight", W, 0, 256, 0, shape.output_ch,
+             "output_linear.bias", 0, shape.output_ch)
+    return pl

@@ -1,0 +1,242 @@
+"""Drop-in for the hot-path names of the reference's ``run_nerf.py``:
+
+    batchify, run_network, batchify_rays, render, render_rays, create_nerf
+
+Same signatures and return structures (run_nerf.py:50-194, :389-675).  ``render_rays`` takes the fused
+B200 route (stratified depths -> fused sample/encode/MLP kernel -> compositing -> CDF inversion + merge ->
+fine pass) whenever the networks are this package's ``NeRF`` and ``network_query_fn`` is the one
+``create_nerf`` built; any other callable goes through the reference's generic composition with each
+stage still running on this library's kernels.
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, Optional
+
+import torch
+
+from . import ops
+from .run_nerf_helpers import NeRF, get_embedder, ndc_rays, raw2outputs, sample_pdf
+
+Tensor = torch.Tensor
+
+
+def batchify(fn, chunk):
+    """run_nerf.py:50-57."""
+    if chunk is None:
+        return fn
+
+    def ret(inputs):
+        return torch.cat([fn(inputs[i:i + chunk]) for i in range(0, inputs.shape[0], chunk)], 0)
+    return ret
+
+
+def run_network(inputs, viewdirs, fn, embed_fn, embeddirs_fn, netchunk=1024 * 64):
+    """run_nerf.py:60-74 (generic route: encode, concatenate, apply ``fn`` in netchunk slices)."""
+    inputs_flat = torch.reshape(inputs, [-1, inputs.shape[-1]])
+    embedded = embed_fn(inputs_flat)
+    if viewdirs is not None:
+        input_dirs = viewdirs[:, None].expand(inputs.shape)
+        input_dirs_flat = torch.reshape(input_dirs, [-1, input_dirs.shape[-1]])
+        embedded = torch.cat([embedded, embeddirs_fn(input_dirs_flat)], -1)
+    outputs_flat = batchify(fn, netchunk)(embedded)
+    return torch.reshape(outputs_flat, list(inputs.shape[:-1]) + [outputs_flat.shape[-1]])
+
+
+class FusedQuery:
+    """``network_query_fn`` built by create_nerf.  Calling it behaves exactly like the reference's lambda
+    (run_nerf.py:434-437); render_rays recognises the type and skips materialising pts / encodings."""
+
+    def __init__(self, embed_fn, embeddirs_fn, netchunk, multires, multires_views, i_embed):
+        self.embed_fn, self.embeddirs_fn, self.netchunk = embed_fn, embeddirs_fn, netchunk
+        self.L_pts = 0 if i_embed == -1 else multires
+        self.L_dir = 0 if i_embed == -1 else multires_views
+
+    def __call__(self, inputs, viewdirs, network_fn):
+        return run_network(inputs, viewdirs, network_fn, embed_fn=self.embed_fn, embeddirs_fn=self.embeddirs_fn,
+                           netchunk=self.netchunk)
+
+    def fused_ok(self, net, ray_batch) -> bool:
+        if not isinstance(net, NeRF):
+            return False
+        want_dir = 3 + 6 * self.L_dir if net.use_viewdirs else net.input_ch_views
+        return (net.input_ch == 3 + 6 * self.L_pts and net.input_ch_views == want_dir
+                and (not net.use_viewdirs or ray_batch.shape[-1] > 9))
+
+
+def batchify_rays(rays_flat, chunk=1024 * 32, **kwargs):
+    """run_nerf.py:77-89.  The fused kernels have no activation-memory reason to chunk, but the chunk loop
+    is kept because the reference draws its random numbers per chunk."""
+    all_ret: Dict[str, list] = {}
+    for i in range(0, rays_flat.shape[0], chunk):
+        ret = render_rays(rays_flat[i:i + chunk], **kwargs)
+        for k in ret:
+            all_ret.setdefault(k, []).append(ret[k])
+    return {k: (v[0] if len(v) == 1 else torch.cat(v, 0)) for k, v in all_ret.items()}
+
+
+def render(H, W, focal, chunk=1024 * 32, rays=None, c2w=None, ndc=True, near=0., far=1., use_viewdirs=False,
+           c2w_staticcam=None, depths=None, **kwargs):
+    """run_nerf.py:112-194.  Returns [rgb_map, disp_map, acc_map, depth_map, extras]."""
+    if c2w is not None:
+        rays_o, rays_d = get_rays(H, W, focal, c2w)
+    else:
+        rays_o, rays_d = rays
+    viewdirs = None
+    if use_viewdirs:
+        viewdirs = rays_d
+        if c2w_staticcam is not None:
+            rays_o, rays_d = get_rays(H, W, focal, c2w_staticcam)
+        viewdirs = viewdirs / torch.norm(viewdirs, dim=-1, keepdim=True)
+        viewdirs = torch.reshape(viewdirs, [-1, 3]).float()
+    sh = rays_d.shape
+    if ndc:
+        rays_o, rays_d = ndc_rays(H, W, focal, 1., rays_o, rays_d)
+    rays_o = torch.reshape(rays_o, [-1, 3]).float()
+    rays_d = torch.reshape(rays_d, [-1, 3]).float()
+    near, far = near * torch.ones_like(rays_d[..., :1]), far * torch.ones_like(rays_d[..., :1])
+    cols = [rays_o, rays_d, near, far]
+    if depths is not None:
+        cols.append(depths.reshape(-1, 1))
+    if use_viewdirs:
+        cols.append(viewdirs)
+    packed = torch.cat(cols, -1)
+    all_ret = batchify_rays(packed, chunk, **kwargs)
+    for k in all_ret:
+        all_ret[k] = torch.reshape(all_ret[k], list(sh[:-1]) + list(all_ret[k].shape[1:]))
+    k_extract = ['rgb_map', 'disp_map', 'acc_map', 'depth_map']
+    return [all_ret[k] for k in k_extract] + [{k: all_ret[k] for k in all_ret if k not in k_extract}]
+
+
+def get_rays(H, W, focal, c2w):
+    """run_nerf_helpers.py:266-282 (full-image rays for render_path; host-side set-up, torch ops)."""
+    dev = c2w.device
+    i, j = torch.meshgrid(torch.linspace(0, W - 1, W, device=dev), torch.linspace(0, H - 1, H, device=dev),
+                          indexing='ij')
+    i, j = i.t(), j.t()
+    dirs = torch.stack([(i - W * .5) / focal, -(j - H * .5) / focal, -torch.ones_like(i)], -1)
+    rays_d = torch.sum(dirs[..., None, :] * c2w[:3, :3], -1)
+    rays_o = c2w[:3, -1].expand(rays_d.shape)
+    return rays_o, rays_d
+
+
+def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False, lindisp=False, perturb=0.,
+                N_importance=0, network_fine=None, white_bkgd=False, raw_noise_std=0., verbose=False, pytest=False,
+                sigma_loss=None, semantic_loss=False, _rng=None):
+    """run_nerf.py:520-675.  Random draws happen in the reference's order on the rays' device:
+    rand[N,S] (jitter) -> randn[N,S] (coarse density noise) -> rand[N,Ni] (u) -> randn[N,S+Ni].
+    ``_rng`` (private, tests only) injects those four tensors: dict(t_rand, noise0, u, noise1)."""
+    if sigma_loss is not None:
+        raise NotImplementedError("sigma_loss reads an undefined variable in the reference train loop "
+                                  "(run_nerf.py:1527) and is not part of the hot path")
+    if semantic_loss:
+        raise NotImplementedError("semantic head is outside this round's scope")
+    if network_fn is None:
+        raise NotImplementedError("the alpha_model branch (run_nerf.py:606-622) is dead code in the reference")
+    rb = ops._f32(ray_batch, "render_rays")
+    N = rb.shape[0]
+    dev = rb.device
+    rays_o, rays_d = rb[:, 0:3], rb[:, 3:6]
+    viewdirs = rb[:, -3:] if rb.shape[-1] > 9 else None
+    rng = _rng or {}
+
+    def draw(name, kind, shape):
+        if name in rng:
+            return rng[name]
+        return (torch.rand if kind == "u" else torch.randn)(shape, device=dev)
+
+    def query(net, z):
+        if isinstance(network_query_fn, FusedQuery) and network_query_fn.fused_ok(net, rb):
+            return net.forward_rays(rb, z)
+        pts = rays_o[..., None, :] + rays_d[..., None, :] * z[..., :, None]
+        return network_query_fn(pts, viewdirs, net)
+
+    def composite(raw, z, noise_name):
+        noise = draw(noise_name, "n", (N, z.shape[1])) if raw_noise_std > 0. else None
+        return ops.composite(raw, z, rays_d, noise, float(raw_noise_std), bool(white_bkgd))
+
+    t_rand = draw("t_rand", "u", (N, N_samples)) if perturb > 0. else None
+    z_vals = ops.stratified_z(rb, N_samples, t_rand, lindisp)
+    raw = query(network_fn, z_vals)
+    rgb_map, disp_map, acc_map, weights, depth_map = composite(raw, z_vals, "noise0")
+
+    ret = {}
+    if N_importance > 0:
+        rgb_map_0, disp_map_0, acc_map_0, depth_map0 = rgb_map, disp_map, acc_map, depth_map
+        u = draw("u", "u", (N, N_importance)) if perturb != 0. else None        # det = (perturb == 0)
+        z_samples, z_vals = ops.importance_resample(z_vals, weights.detach(), N_importance, u)
+        run_fn = network_fn if network_fine is None else network_fine
+        raw = query(run_fn, z_vals)
+        rgb_map, disp_map, acc_map, weights, depth_map = composite(raw, z_vals, "noise1")
+    ret.update(rgb_map=rgb_map, disp_map=disp_map, acc_map=acc_map, depth_map=depth_map)
+    if retraw:
+        ret['raw'] = raw
+    if N_importance > 0:
+        ret['rgb0'], ret['disp0'], ret['acc0'], ret['depth_map0'] = rgb_map_0, disp_map_0, acc_map_0, depth_map0
+        ret['z_std'] = torch.std(z_samples, dim=-1, unbiased=False)
+    return ret
+
+
+def create_nerf(args):
+    """run_nerf.py:389-517: embedders, coarse + fine NeRF, query fn, Adam, checkpoint reload, kwargs dicts.
+    Differences: no torchsummary printout (:511-515, crashes when model_fine is None), and the alpha_model
+    branch (:405-419) is rejected."""
+    device = torch.device("cuda")
+    embed_fn, input_ch = get_embedder(args.multires, args.i_embed)
+    input_ch_views, embeddirs_fn = 0, None
+    if args.use_viewdirs:
+        embeddirs_fn, input_ch_views = get_embedder(args.multires_views, args.i_embed)
+    output_ch = 5 if args.N_importance > 0 else 4
+    skips = [4]
+    if getattr(args, "alpha_model_path", None) is not None:
+        raise NotImplementedError("alpha_model_path: the two-stage variant is not part of the hot path")
+    sem = getattr(args, "semantic_num_classes", None)
+    model = NeRF(D=args.netdepth, W=args.netwidth, input_ch=input_ch, output_ch=output_ch, skips=skips,
+                 input_ch_views=input_ch_views, use_viewdirs=args.use_viewdirs, semantic_num_classes=sem).to(device)
+    grad_vars = list(model.parameters())
+    model_fine = None
+    if args.N_importance > 0:
+        model_fine = NeRF(D=args.netdepth_fine, W=args.netwidth_fine, input_ch=input_ch, output_ch=output_ch,
+                          skips=skips, input_ch_views=input_ch_views, use_viewdirs=args.use_viewdirs,
+                          semantic_num_classes=sem).to(device)
+        grad_vars += list(model_fine.parameters())
+    network_query_fn = FusedQuery(embed_fn, embeddirs_fn, args.netchunk, args.multires,
+                                  getattr(args, "multires_views", 0), args.i_embed)
+    optimizer = torch.optim.Adam(params=grad_vars, lr=args.lrate, betas=(0.9, 0.999))
+
+    start = 0
+    basedir, expname = args.basedir, args.expname
+    if getattr(args, "ft_path", None) is not None and args.ft_path != 'None':
+        ckpts = [args.ft_path]
+    else:
+        d = os.path.join(basedir, expname)
+        ckpts = [os.path.join(d, f) for f in sorted(os.listdir(d)) if 'tar' in f] if os.path.isdir(d) else []
+    print('Found ckpts', ckpts)
+    if len(ckpts) > 0 and not args.no_reload:
+        ckpt = torch.load(ckpts[-1], map_location=device)
+        start = ckpt['global_step']
+        if not args.no_reload_optimizer:
+            optimizer.load_state_dict(ckpt['optimizer_state_dict'])
+        for net, key in ((model, 'network_fn_state_dict'), (model_fine, 'network_fine_state_dict')):
+            if net is None:
+                continue
+            cur = net.state_dict()
+            cur.update({k: v for k, v in ckpt[key].items() if k in cur})      # key-filtered merge (:466-477)
+            net.load_state_dict(cur)
+
+    render_kwargs_train = {
+        'network_query_fn': network_query_fn, 'perturb': args.perturb, 'N_importance': args.N_importance,
+        'network_fine': model_fine, 'N_samples': args.N_samples, 'network_fn': model,
+        'use_viewdirs': args.use_viewdirs, 'white_bkgd': args.white_bkgd, 'raw_noise_std': args.raw_noise_std,
+        'semantic_loss': getattr(args, "semantic_loss", False),
+    }
+    if args.dataset_type != 'llff' or args.no_ndc:
+        print('Not ndc!')
+        render_kwargs_train['ndc'] = False
+        render_kwargs_train['lindisp'] = args.lindisp
+    else:
+        render_kwargs_train['ndc'] = True
+    render_kwargs_test = {k: render_kwargs_train[k] for k in render_kwargs_train}
+    render_kwargs_test['perturb'] = False
+    render_kwargs_test['raw_noise_std'] = 0.
+    return render_kwargs_train, render_kwargs_test, start, grad_vars, optimizer

@@ -1,0 +1,309 @@
+"""Drop-in for the hot-path names of the reference's ``run_nerf_helpers.py``:
+
+    img2mse, mse2psnr, to8b, Embedder, get_embedder, NeRF, ndc_rays, sample_pdf, raw2outputs
+
+Same names, argument meaning and error behaviour; the arithmetic runs in the sm_100a kernels of
+``libdlnerf_b200.so`` (no CPU fallback).  Reference lines are cited per function.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from . import ops
+from .plan import NetShape, Plan, build_plan
+
+Tensor = torch.Tensor
+
+# Misc (run_nerf_helpers.py:19-21)
+img2mse = lambda x, y: torch.mean((x - y) ** 2)
+mse2psnr = lambda x: -10. * torch.log(x) / torch.log(torch.tensor([10.], device=x.device))
+to8b = lambda x: (255 * np.clip(x, 0, 1)).astype(np.uint8)
+
+
+# --------------------------------------------------------------------------------------------------
+# Positional encoding (run_nerf_helpers.py:25-73)
+# --------------------------------------------------------------------------------------------------
+class Embedder:
+    """Same constructor kwargs as the reference (:26-52).  Only the configuration get_embedder builds
+    (include_input, log-sampled octaves, [sin, cos]) has a kernel; anything else raises."""
+
+    def __init__(self, **kwargs):
+        self.kwargs = kwargs
+        self.create_embedding_fn()
+
+    def create_embedding_fn(self):
+        kw = self.kwargs
+        if not (kw.get("include_input", True) and kw.get("log_sampling", True) and kw.get("input_dims", 3) == 3
+                and kw.get("num_freqs") == kw.get("max_freq_log2") + 1):
+            raise NotImplementedError("only the get_embedder configuration is implemented on the B200 path")
+        self.n_freqs = int(kw["num_freqs"])
+        self.out_dim = 3 + 6 * self.n_freqs
+
+    def embed(self, inputs: Tensor) -> Tensor:
+        return ops.posenc(inputs, self.n_freqs)
+
+
+class _IdentityEmbed(nn.Identity):
+    n_freqs = 0
+
+
+def get_embedder(multires, i=0):
+    """(:58-73) returns (embed_fn, out_dim); i == -1 -> identity, 3 channels."""
+    if i == -1:
+        return _IdentityEmbed(), 3
+    embedder_obj = Embedder(include_input=True, input_dims=3, max_freq_log2=multires - 1, num_freqs=multires,
+                            log_sampling=True, periodic_fns=[torch.sin, torch.cos])
+
+    def embed(x, eo=embedder_obj):
+        return eo.embed(x)
+
+    embed.n_freqs = embedder_obj.n_freqs      # lets the fused renderer recognise the encoding
+    return embed, embedder_obj.out_dim
+
+
+# --------------------------------------------------------------------------------------------------
+# Model (run_nerf_helpers.py:77-174)
+# --------------------------------------------------------------------------------------------------
+class _MLP(torch.autograd.Function):
+    """Fused MLP forward + (dgrad chain, wgrad GEMMs) backward.  Gradients flow to the parameters
+    only: on the reference's training path the network inputs never require grad."""
+
+    @staticmethod
+    def forward(ctx, net: "NeRF", mode, a, b, P, *params):
+        train = any(ctx.needs_input_grad[5:])
+        out, saved = net._run_forward(mode, a, b, P, keep=train)
+        ctx.net, ctx.saved, ctx.P = net, saved, P
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        net: "NeRF" = ctx.net
+        grads = net._run_backward(d_out, ctx.saved, ctx.P)
+        ctx.saved = None
+        return (None, None, None, None, None) + tuple(grads)
+
+
+class NeRF(nn.Module):
+    def __init__(self, D=8, W=256, input_ch=3, input_ch_views=3, output_ch=5, skips=[4], use_viewdirs=False,
+                 semantic_num_classes=None):
+        super().__init__()
+        if semantic_num_classes:
+            raise NotImplementedError("the semantic head (run_nerf_helpers.py:107-111) is outside the B200 "
+                                      "hot-path scope of this round")
+        self.D, self.W = D, W
+        self.input_ch, self.input_ch_views = input_ch, input_ch_views
+        self.skips, self.use_viewdirs = skips, use_viewdirs
+        self.semantic_num_classes = semantic_num_classes
+        self.semantic_linear = False
+        # identical registration order / names / shapes / init to the reference (:90-105)
+        self.pts_linears = nn.ModuleList(
+            [nn.Linear(input_ch, W)] + [nn.Linear(W, W) if i not in self.skips else nn.Linear(W + input_ch, W)
+                                        for i in range(D - 1)])
+        self.views_linears = nn.ModuleList([nn.Linear(input_ch_views + W, W // 2)])
+        if use_viewdirs:
+            self.feature_linear = nn.Linear(W, W)
+            self.alpha_linear = nn.Linear(W, 1)
+            self.rgb_linear = nn.Linear(W // 2, 3)
+        else:
+            self.output_linear = nn.Linear(W, output_ch)
+        self.output_ch = output_ch
+        self._shape = NetShape(D=D, W=W, input_ch=input_ch, input_ch_views=input_ch_views, output_ch=output_ch,
+                               skips=tuple(skips), use_viewdirs=use_viewdirs)
+        self._plan: Optional[Plan] = None
+        self._dev_state = None
+
+    # ------------------------------------------------------------------ device-side state
+    def _ordered_params(self) -> List[nn.Parameter]:
+        d = dict(self.named_parameters())
+        return [d[name] for name, _ in self._shape.param_shapes()]
+
+    def _state(self):
+        """Flat fp32 parameter buffer (each nn.Parameter is re-pointed to a view of it), packed bf16
+        weight blobs, device copies of the pack jobs / wgrad items."""
+        if self._plan is None:
+            self._plan = build_plan(self._shape)
+        pl = self._plan
+        params = self._ordered_params()
+        dev = params[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("dlnerf_b200.NeRF: parameters are on %s; the B200 path has no CPU fallback" % dev)
+        st = self._dev_state
+        names = [n for n, _ in self._shape.param_shapes()]
+        stale = st is None or st["device"] != dev or any(
+            p.data_ptr() != st["flat"].data_ptr() + 4 * pl.offsets[n] for p, n in zip(params, names))
+        if stale:
+            flat = torch.zeros(pl.n_params, device=dev, dtype=torch.float32)
+            for p, n in zip(params, names):
+                view = flat[pl.offsets[n]: pl.offsets[n] + p.numel()].view(p.shape)
+                view.copy_(p.data)
+                p.data = view
+
+            def upload(items):
+                raw = b"".join(bytes(i) for i in items)
+                return torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
+
+            st = dict(device=dev, flat=flat, wf=torch.zeros(pl.fwd_blob_bytes, device=dev, dtype=torch.uint8),
+                      wb=torch.zeros(pl.bwd_blob_bytes, device=dev, dtype=torch.uint8),
+                      fwd_jobs=upload(pl.fwd_jobs), bwd_jobs=upload(pl.bwd_jobs), items=upload(pl.wgrad),
+                      version=None, sms=torch.cuda.get_device_properties(dev).multi_processor_count)
+            self._dev_state = st
+        return st
+
+    def _pack(self, st):
+        params = self._ordered_params()
+        ver = tuple(p._version for p in params)
+        if st["version"] == ver:
+            return
+        pl = self._plan
+        lib, s = L.lib(), ops._stream()
+        L.check(lib.dln_mlp_pack_weights(st["flat"].data_ptr(), st["fwd_jobs"].data_ptr(), len(pl.fwd_jobs),
+                                         st["wf"].data_ptr(), s), "pack_weights(fwd)")
+        L.check(lib.dln_mlp_pack_weights(st["flat"].data_ptr(), st["bwd_jobs"].data_ptr(), len(pl.bwd_jobs),
+                                         st["wb"].data_ptr(), s), "pack_weights(bwd)")
+        st["version"] = ver
+
+    # ------------------------------------------------------------------ kernels
+    def _run_forward(self, mode, a, b, P, keep):
+        st = self._state()
+        self._pack(st)
+        pl = self._plan
+        dev = st["device"]
+        n_tiles = (P + L.TILE_ROWS - 1) // L.TILE_ROWS
+        out = torch.empty(P, self._shape.out_ch, device=dev, dtype=torch.float32)
+        args = L.ChainArgs()
+        args.P = P
+        if mode == "rays":                       # a = ray_batch [N, C], b = z_vals [N, S]
+            args.rays, args.ray_stride, args.vd_col = a.data_ptr(), a.stride(0), a.shape[1] - 3
+            args.z, args.S = b.data_ptr(), b.shape[1]
+        else:                                    # a = x [P, in]
+            args.x, args.x_ld = a.data_ptr(), a.stride(0)
+        args.wblob, args.fblob, args.out = st["wf"].data_ptr(), st["flat"].data_ptr(), out.data_ptr()
+        saved = None
+        if keep:
+            stash = torch.empty(n_tiles * pl.fwd_slots * L.SLAB_BYTES, device=dev, dtype=torch.uint8)
+            masks = torch.empty(pl.mask_slots * n_tiles * 2 * 128 * 4, device=dev, dtype=torch.int32)
+            args.stash, args.masks = stash.data_ptr(), masks.data_ptr()
+            saved = (stash, masks)
+        L.check(L.lib().dln_mlp_chain(C.byref(pl.fwd), C.byref(args), st["sms"], ops._stream()), "mlp_chain(fwd)")
+        return out, saved
+
+    def _run_backward(self, d_out, saved, P):
+        st = self._state()
+        pl = self._plan
+        dev = st["device"]
+        stash_f, masks = saved
+        n_tiles = (P + L.TILE_ROWS - 1) // L.TILE_ROWS
+        d = d_out.reshape(P, self._shape.out_ch)
+        d = d.contiguous() if d.dtype == torch.float32 else d.float().contiguous()
+        stash_b = torch.empty(n_tiles * pl.bwd_slots * L.SLAB_BYTES, device=dev, dtype=torch.uint8)
+        args = L.ChainArgs()
+        args.P = P
+        args.wblob, args.fblob = st["wb"].data_ptr(), st["flat"].data_ptr()
+        args.d_out, args.stash, args.masks = d.data_ptr(), stash_b.data_ptr(), masks.data_ptr()
+        lib, s = L.lib(), ops._stream()
+        L.check(lib.dln_mlp_chain(C.byref(pl.bwd), C.byref(args), st["sms"], s), "mlp_chain(dgrad)")
+        gflat = torch.zeros(pl.n_params, device=dev, dtype=torch.float32)
+        n_items = len(pl.wgrad)
+        splits = int(max(1, min(n_tiles, (2 * st["sms"]) // n_items)))
+        L.check(lib.dln_mlp_wgrad(st["items"].data_ptr(), n_items, splits, stash_f.data_ptr(), pl.fwd_slots,
+                                  stash_b.data_ptr(), pl.bwd_slots, n_tiles, gflat.data_ptr(), s), "mlp_wgrad")
+        grads = []
+        for (name, shp), p in zip(self._shape.param_shapes(), self._ordered_params()):
+            o = pl.offsets[name]
+            grads.append(gflat[o: o + p.numel()].view(p.shape) if p.requires_grad else None)
+        return grads
+
+    # ------------------------------------------------------------------ public interface
+    def forward(self, x: Tensor) -> Tensor:
+        """(:113-145) x[..., input_ch + input_ch_views] -> [..., 4] (view dirs) or [..., output_ch]."""
+        n_in = self.input_ch + (self.input_ch_views if self.use_viewdirs else 0)
+        if x.shape[-1] < n_in:
+            raise RuntimeError("expected at least %d input channels, got %d" % (n_in, x.shape[-1]))
+        xs = ops._f32(x, "NeRF.forward").reshape(-1, x.shape[-1])
+        P = xs.shape[0]
+        out = _MLP.apply(self, "x", xs, None, P, *self._ordered_params())
+        return out.reshape(*x.shape[:-1], out.shape[-1])
+
+    def forward_rays(self, ray_batch: Tensor, z_vals: Tensor) -> Tensor:
+        """Fused path of run_nerf.py:595 + run_network (:60-74) + forward: points o + d*z are formed,
+        encoded (positions per sample, the unit view direction once per ray) and pushed through the MLP
+        inside one kernel.  ray_batch is the packed [N, 8|11] batch of render(); returns raw[N, S, C]."""
+        rb, z = ops._f32(ray_batch, "forward_rays"), ops._f32(z_vals, "forward_rays")
+        if self.use_viewdirs and rb.shape[1] < 11:
+            raise RuntimeError("use_viewdirs=True needs the unit view direction in the last 3 ray columns")
+        N, S = z.shape
+        out = _MLP.apply(self, "rays", rb, z, N * S, *self._ordered_params())
+        return out.reshape(N, S, out.shape[-1])
+
+    def load_weights_from_keras(self, weights):
+        """(:147-174) same index arithmetic as the reference: transposed Keras kernels."""
+        assert self.use_viewdirs, "Not implemented if use_viewdirs=False"
+        with torch.no_grad():
+            for i in range(self.D):
+                self.pts_linears[i].weight.copy_(torch.from_numpy(np.transpose(weights[2 * i])))
+                self.pts_linears[i].bias.copy_(torch.from_numpy(np.transpose(weights[2 * i + 1])))
+            k = 2 * self.D
+            self.feature_linear.weight.copy_(torch.from_numpy(np.transpose(weights[k])))
+            self.feature_linear.bias.copy_(torch.from_numpy(np.transpose(weights[k + 1])))
+            self.views_linears[0].weight.copy_(torch.from_numpy(np.transpose(weights[k + 2])))
+            self.views_linears[0].bias.copy_(torch.from_numpy(np.transpose(weights[k + 3])))
+            self.rgb_linear.weight.copy_(torch.from_numpy(np.transpose(weights[k + 4])))
+            self.rgb_linear.bias.copy_(torch.from_numpy(np.transpose(weights[k + 5])))
+            self.alpha_linear.weight.copy_(torch.from_numpy(np.transpose(weights[k + 6])))
+            self.alpha_linear.bias.copy_(torch.from_numpy(np.transpose(weights[k + 7])))
+
+
+# --------------------------------------------------------------------------------------------------
+# Ray helpers (run_nerf_helpers.py:320-337)
+# --------------------------------------------------------------------------------------------------
+def ndc_rays(H, W, focal, near, rays_o, rays_d):
+    """Near-plane shift + projective warp.  A dozen element-wise ops on [N,3]; negligible,
+    left to torch on the device."""
+    t = -(near + rays_o[..., 2]) / rays_d[..., 2]
+    rays_o = rays_o + t[..., None] * rays_d
+    sx, sy = -1. / (W / (2. * focal)), -1. / (H / (2. * focal))
+    ox, oy = rays_o[..., 0] / rays_o[..., 2], rays_o[..., 1] / rays_o[..., 2]
+    o = torch.stack([sx * ox, sy * oy, 1. + 2. * near / rays_o[..., 2]], -1)
+    d = torch.stack([sx * (rays_d[..., 0] / rays_d[..., 2] - ox), sy * (rays_d[..., 1] / rays_d[..., 2] - oy),
+                     -2. * near / rays_o[..., 2]], -1)
+    return o, d
+
+
+# --------------------------------------------------------------------------------------------------
+# Hierarchical sampling (run_nerf_helpers.py:497-540)
+# --------------------------------------------------------------------------------------------------
+def sample_pdf(bins, weights, N_samples, det=False, pytest=False):
+    """Same signature as the reference.  Draw order is unchanged: one torch.rand([..., N_samples]) on the
+    inputs' device unless det.  The result carries no gradient (the reference detaches it at
+    run_nerf.py:634 before any use)."""
+    lead = list(bins.shape[:-1])
+    u = None
+    if not det:
+        u = torch.rand(lead + [N_samples], device=bins.device)
+    if pytest:
+        np.random.seed(0)
+        u = None if det else torch.tensor(np.random.rand(*(lead + [N_samples])), dtype=torch.float32,
+                                         device=bins.device)
+    return ops.sample_pdf(bins.detach(), weights.detach(), N_samples, u)
+
+
+# --------------------------------------------------------------------------------------------------
+# Compositing (run_nerf_helpers.py:542-595)
+# --------------------------------------------------------------------------------------------------
+def raw2outputs(raw, z_vals, rays_d, raw_noise_std=0, white_bkgd=False, pytest=False, semantic_loss=False):
+    """Returns (rgb_map, disp_map, acc_map, weights, depth_map), differentiable w.r.t. raw."""
+    if semantic_loss:
+        raise NotImplementedError("semantic logits (run_nerf_helpers.py:586-593) are outside this round's scope")
+    noise = None
+    if raw_noise_std > 0.:
+        noise = torch.randn(raw[..., 3].shape, device=raw.device)
+        if pytest:       # the reference's hook draws UNIFORM numbers here (:567-571)
+            np.random.seed(0)
+            noise = torch.tensor(np.random.rand(*list(raw[..., 3].shape)), dtype=torch.float32, device=raw.device)
+    return ops.composite(raw, z_vals, rays_d, noise, float(raw_noise_std), bool(white_bkgd))

@@ -1,0 +1,208 @@
+/* dlnerf_b200 — C ABI of the B200 (sm_100a) ray-rendering hot path.
+ *
+ * The reference (mertkiray/depth-lidar-nerf) has no FFI layer: its hot path is plain Python/PyTorch
+ * (run_nerf.py / run_nerf_helpers.py).  This header is the drop-in boundary a maintainer binds with
+ * ctypes; each entry point names the reference code it replaces.
+ *
+ * Conventions: every function returns 0 on success, -1 on an invalid argument (shape / alignment /
+ * null pointer), or a positive cudaError_t from the launch.  All pointers are DEVICE pointers unless
+ * the name ends in `_host`.  No allocation, no host synchronisation; `stream` is a cudaStream_t.
+ * All float tensors are contiguous fp32 row-major; indices are int64.
+ */
+#ifndef DLNERF_B200_H
+#define DLNERF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ----------------------------------------------------------------------------------------------
+ * Sampling / encoding
+ * -------------------------------------------------------------------------------------------- */
+
+/* Stratified depths along each ray.  Replaces run_nerf.py:571-593 (t_vals linspace, near/far lerp or
+ * lindisp, mids/upper/lower jitter).  rays[N, ray_stride] holds near at column 6 and far at column 7
+ * (the packed ray_batch of run_nerf.py:178-183).  t_rand[N,S] may be null (perturb == 0). */
+int dln_stratified_z(const float* rays, int ray_stride, const float* t_rand, float* z, int N, int S, int lindisp,
+                     void* stream);
+
+/* Positional encoding gamma(x): [P,3] -> [P, 3+6L].  Replaces Embedder.embed, run_nerf_helpers.py:25-73. */
+int dln_posenc(const float* x, float* out, long long P, int L, void* stream);
+
+/* ----------------------------------------------------------------------------------------------
+ * Alpha compositing (raw2outputs) and its backward
+ * -------------------------------------------------------------------------------------------- */
+
+/* Replaces raw2outputs, run_nerf_helpers.py:542-595.  raw[N,S,raw_ch] (raw_ch >= 4; channels 0..3 used),
+ * noise[N,S] standard-normal draws or null, scaled by noise_std in-kernel.  weights may be null. */
+int dln_composite_fwd(const float* raw, int raw_ch, const float* z_vals, const float* rays_d, const float* noise,
+                      float noise_std, int white_bkgd, float* rgb_map, float* disp_map, float* acc_map,
+                      float* weights, float* depth_map, int N, int S, void* stream);
+
+/* Autograd backward of the above (run_nerf.py:1773 replays it through ATen).  Any upstream gradient
+ * pointer may be null (= zero).  d_raw[N,S,raw_ch] is fully written (channels >= 4 get 0). */
+int dln_composite_bwd(const float* raw, int raw_ch, const float* z_vals, const float* rays_d, const float* noise,
+                      float noise_std, int white_bkgd, const float* g_rgb, const float* g_disp, const float* g_acc,
+                      const float* g_weights, const float* g_depth, float* d_raw, int N, int S, void* stream);
+
+/* Backward with the loss of run_nerf.py:1451-1466,1500-1536,1759-1761 fused in: rays [0,n_rgb) carry the
+ * colour MSE against target_rgb (null = none), rays [n_rgb,N) the depth loss against target_depth
+ * (null = none).  coef_rgb = 2/(3 n_rgb); coef_depth = 2 * depth_lambda * depth_importance / n_depth
+ * (callers fold every scalar factor in).  depth_mode: 0 mse (:1524), 1 weighted (:1517),
+ * 2 weighted+normalised by depth_norm=max(target) (:1520), 3 relative (:1522).
+ * loss_sums[0] += sum (rgb-target)^2, loss_sums[1] += sum of depth terms (caller zeroes / normalises). */
+int dln_composite_bwd_fused_loss(const float* raw, int raw_ch, const float* z_vals, const float* rays_d,
+                                 const float* noise, float noise_std, int white_bkgd, const float* target_rgb,
+                                 const float* target_depth, const float* ray_weights, int n_rgb, float coef_rgb,
+                                 float coef_depth, int depth_mode, float depth_norm, float* loss_sums, float* d_raw,
+                                 int N, int S, void* stream);
+
+/* ----------------------------------------------------------------------------------------------
+ * Hierarchical sampling
+ * -------------------------------------------------------------------------------------------- */
+
+/* Replaces sample_pdf, run_nerf_helpers.py:497-540 (the torch.searchsorted call at :524 included) and,
+ * when z_merged != null, the sort(cat(z_vals, z_samples)) of run_nerf.py:636.
+ *   bins:    row n at bins + n*bins_stride; n_bins entries, or (mid_from_z) n_bins+1 depths whose
+ *            midpoints are the bins (run_nerf.py:632).
+ *   weights: row n at weights + n*weights_stride; n_bins-1 entries (pass the interior slice's pointer).
+ *   u[N,n_samples] uniform draws, or null for the deterministic linspace (det=True).
+ *   samples[N,n_samples] out.  z_coarse[N,S] + z_merged[N,S+n_samples] optional merge.
+ *   cdf_out[N,n_bins], inds_out[N,n_samples] (searchsorted right=True indices) optional. */
+int dln_sample_pdf(const float* bins, int bins_stride, int mid_from_z, const float* weights, int weights_stride,
+                   int n_bins, const float* u, int n_samples, float* samples, const float* z_coarse, int S,
+                   float* z_merged, float* cdf_out, long long* inds_out, int N, void* stream);
+
+/* Batched row-wise search with row broadcast: the contract of the vendored extension
+ * torchsearchsorted/src/cuda/searchsorted_cuda_kernel.cu:110-142 (searchsorted.py:20-53). */
+int dln_searchsorted(const float* a, int rows_a, int A, const float* v, int rows_v, int V, long long* out,
+                     int side_right, void* stream);
+
+/* ----------------------------------------------------------------------------------------------
+ * NeRF MLP (run_nerf_helpers.py:77-145 forward; autograd backward) on tcgen05 tensor cores
+ * -------------------------------------------------------------------------------------------- */
+
+#define DLN_MAX_STEPS 12
+#define DLN_MAX_KSLABS 6
+#define DLN_SLAB_BYTES 16384 /* one [128 points x 64 features] bf16 panel, SWIZZLE_128B image */
+#define DLN_TILE_ROWS 128
+
+/* Epilogue kinds of a chain step. */
+enum {
+  DLN_EPI_RELU = 0,       /* h = relu(acc + b)                                  -> next activations   */
+  DLN_EPI_RELU_SIGMA = 1, /* same, and sigma = <h, head> + head_bias            (alpha_linear)        */
+  DLN_EPI_LINEAR = 2,     /* h = acc + b                                        (feature_linear)      */
+  DLN_EPI_RELU_RGB = 3,   /* h = relu(acc + b); rgb = heads*h + b; write [rgb, sigma]                 */
+  DLN_EPI_RELU_OUT = 4,   /* h = relu(acc + b); out = heads*h + b (output_linear, no view dirs)       */
+  DLN_EPI_BWD_COPY = 8,   /* dZ = acc                                                                  */
+  DLN_EPI_BWD_MASK = 9,   /* dZ = acc * relu'                                                          */
+  DLN_EPI_BWD_MASK_SIGMA = 10 /* dZ = (acc + dsigma * head) * relu'                                   */
+};
+
+/* One GEMM step of the fused chain: acc[128 x n_out] = sum over K slabs of A_slab * W_stage^T. */
+typedef struct {
+  uint32_t w_off;     /* byte offset of this step's first weight stage in the packed bf16 blob        */
+  uint32_t bias_off;  /* float offset of the bias vector in the fp32 blob                              */
+  uint32_t head_off;  /* float offset of head weights [n_heads][n_out] (or the rank-1 vector)          */
+  uint32_t head_bias_off; /* float offset of the head biases                                           */
+  uint16_t n_out;     /* 256 or 128                                                                    */
+  uint8_t nk;         /* number of K slab entries                                                      */
+  uint8_t epi;        /* DLN_EPI_*                                                                     */
+  uint8_t kslab[DLN_MAX_KSLABS]; /* 0..3 activation slabs, 4 encoded position, 5 encoded direction    */
+  uint8_t kcnt[DLN_MAX_KSLABS];  /* K=16 MMA steps taken from that slab (4 = all 64 columns)           */
+  int16_t stash_slot; /* first stash slot of the output slabs, -1 = not kept                           */
+  int16_t mask_slot;  /* relu bit-mask slot written (fwd) / read (bwd), -1 = none                      */
+  uint8_t n_heads;
+  uint8_t pad_[3];
+} DlnChainStep;
+
+typedef struct {
+  int32_t n_steps;
+  int32_t backward;        /* 0 forward chain, 1 dgrad chain                                           */
+  int32_t use_viewdirs;
+  int32_t out_ch;          /* channels of raw / d_raw rows                                             */
+  int32_t L_pts, L_dir;    /* frequencies of the two encodings                                         */
+  int32_t stash_slots;     /* slabs kept per 128-point tile (0 = keep nothing)                         */
+  int32_t mask_slots;
+  /* backward prologue: d_raw -> dZ of the first backward layer through rgb_linear / output_linear */
+  int32_t pro_head_off;    /* float offset of W_rgb[3][128] (or W_out[out_ch][256]) in the fp32 blob    */
+  int32_t pro_mask_slot;   /* relu mask of that layer's forward output                                  */
+  int32_t pro_slot;        /* first stash slot of the prologue's activation slabs                       */
+  int32_t pad_;
+  DlnChainStep steps[DLN_MAX_STEPS];
+} DlnChainProgram;
+
+/* Inputs of one chain launch.  Forward: either (rays, z) for the fused sampling+encoding prologue
+ * (replaces run_nerf.py:595 + run_network :60-74) or x[P, x_ld] pre-encoded rows (NeRF.forward).
+ * Backward: d_out[P,out_ch] in, dZ slabs to `stash`. */
+typedef struct {
+  long long P;             /* points (rows)                                                            */
+  const float* rays;       /* [N, ray_stride]: o 0:3, d 3:6, unit view dir at vd_col (fused mode)      */
+  int32_t ray_stride, vd_col;
+  const float* z;          /* [N,S]                                                                    */
+  int32_t S;
+  const float* x;          /* [P, x_ld] encoded inputs (generic mode) or null                         */
+  int32_t x_ld;
+  const void* wblob;       /* packed bf16 weight stages                                                */
+  const float* fblob;      /* fp32 biases / head vectors                                               */
+  float* out;              /* fwd: raw[P,out_ch]            bwd: unused                                */
+  const float* d_out;      /* bwd: d raw[P,out_ch]                                                     */
+  void* stash;             /* [tiles][stash_slots][DLN_SLAB_BYTES] or null                             */
+  uint32_t* masks;         /* [mask_slots][tiles][2][128][4] relu bit masks                            */
+} DlnChainArgs;
+
+/* Fused MLP chain (forward or dgrad).  prog_host / args_host are HOST structs passed by value to the
+ * kernel.  Replaces NeRF.forward (run_nerf_helpers.py:113-145), batchify/run_network (run_nerf.py:50-74)
+ * and the dgrad half of its autograd backward. */
+int dln_mlp_chain(const DlnChainProgram* prog_host, const DlnChainArgs* args_host, int num_sms, void* stream);
+
+/* One weight-gradient GEMM  dW[rows, cols] += A^T B  over all points, A/B read from the stashes. */
+typedef struct {
+  int32_t a_bwd_stash;     /* 1: A slabs come from the backward stash (always)                        */
+  int32_t a_slot, a_nslab; /* dZ slabs: 1, 2 or 4 (64 output features each)                           */
+  int32_t b_from_bwd;      /* 0: B from the forward stash                                              */
+  int32_t b_slot, b_nslab; /* input-activation slabs (64 input features each)                          */
+  int64_t dw_off;          /* float offset of dW[0,0] in the flat gradient buffer                      */
+  int32_t ld;              /* row pitch of dW (fan_in of the layer)                                    */
+  int32_t col_off;         /* first column written                                                     */
+  int32_t n_cols;          /* valid columns of B (<= 64*b_nslab)                                       */
+  int32_t row_off;         /* first A feature (row of the accumulator) stored                          */
+  int32_t n_rows;          /* rows stored; accumulator row row_off+i -> dW row i                       */
+  int64_t db_off;          /* float offset of the bias gradient, or -1                                 */
+  int32_t db_col_off;      /* first A feature summed                                                   */
+  int32_t db_n;            /* features summed                                                          */
+} DlnWgradItem;
+
+/* items_dev: DEVICE array of n_items; each item is split over `splits` CTAs along the points. */
+int dln_mlp_wgrad(const DlnWgradItem* items_dev, int n_items, int splits, const void* stash_fwd,
+                  int fwd_slots, const void* stash_bwd, int bwd_slots, long long n_tiles, float* grads_flat,
+                  void* stream);
+
+/* fp32 master parameters -> bf16 SWIZZLE_128B weight stages. */
+typedef struct {
+  int64_t src_off;     /* float offset of W[0,0] in the flat parameter buffer                          */
+  int32_t ld;          /* row pitch of W (fan_in)                                                      */
+  int32_t row0, col0;  /* top-left corner of the block                                                 */
+  int32_t n_valid;     /* valid stage rows (output features, or input features if transposed)          */
+  int32_t k_valid;     /* valid K columns (<= 64)                                                      */
+  int32_t transposed;  /* 0: stage[n][k] = W[row0+n][col0+k]   1: stage[n][k] = W[row0+k][col0+n]      */
+  int32_t n_rows;      /* stage rows (128 or 256)                                                      */
+  uint32_t dst_off;    /* byte offset of the stage in the blob                                         */
+} DlnPackJob;
+
+int dln_mlp_pack_weights(const float* params_flat, const DlnPackJob* jobs_dev, int n_jobs, void* wblob,
+                         void* stream);
+
+/* Library / build information (arch string, e.g. "sm_100a"). */
+const char* dln_build_info(void);
+
+/* Host-only: sizeof of the five ABI structs, in the order ChainStep, ChainProgram, ChainArgs, WgradItem,
+ * PackJob, so a binding can verify its mirror of this header without touching a GPU. */
+int dln_abi_sizes(int* out5_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DLNERF_B200_H */

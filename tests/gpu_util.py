@@ -1,0 +1,127 @@
+"""Helpers shared by the `-m gpu` parity tests (test infrastructure, not product code)."""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from oracle import nerf_oracle as O  # noqa: E402
+
+SLAB = 16384
+
+
+def dn():
+    import dlnerf_b200
+    return dlnerf_b200
+
+
+def report(name, got, ref, atol=0.0, rtol=0.0, quiet=False):
+    """Print and return (max_abs_err, max_ref); asserts |got-ref| <= atol + rtol*|ref| on finite entries."""
+    g = torch.as_tensor(got).detach().double().cpu()
+    r = torch.as_tensor(ref).detach().double().cpu()
+    assert g.shape == r.shape, (name, g.shape, r.shape)
+    fin = torch.isfinite(r)
+    assert torch.equal(torch.isfinite(g), fin), "%s: non-finite pattern differs" % name
+    err = (g[fin] - r[fin]).abs()
+    bound = atol + rtol * r[fin].abs()
+    mx = err.max().item() if err.numel() else 0.0
+    if not quiet:
+        print("  %-34s max|err| %.3e  max|ref| %.3e  (atol %.1e rtol %.1e)" % (
+            name, mx, r[fin].abs().max().item() if err.numel() else 0.0, atol, rtol))
+    bad = err > bound
+    assert not bad.any(), "%s: %d / %d entries out of tolerance, worst %.3e" % (name, int(bad.sum()), err.numel(), mx)
+    return mx
+
+
+def rel_l2(got, ref):
+    g = torch.as_tensor(got).detach().double().cpu().flatten()
+    r = torch.as_tensor(ref).detach().double().cpu().flatten()
+    return ((g - r).norm() / (r.norm() + 1e-30)).item()
+
+
+def cosine(got, ref):
+    g = torch.as_tensor(got).detach().double().cpu().flatten()
+    r = torch.as_tensor(ref).detach().double().cpu().flatten()
+    return (g @ r / (g.norm() * r.norm() + 1e-30)).item()
+
+
+def bf16r(t):
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+_UNSWZ = None
+
+
+def unswizzle_index():
+    """int16-element index of (row, col) inside a SWIZZLE_128B slab image (see csrc/common.cuh slab_off)."""
+    global _UNSWZ
+    if _UNSWZ is None:
+        r = torch.arange(128)[:, None]
+        c = torch.arange(64)[None, :]
+        off = (r >> 3) * 1024 + (r & 7) * 128 + ((((c >> 3) ^ r) & 7) << 4) + ((c & 7) << 1)
+        _UNSWZ = (off // 2).long()
+    return _UNSWZ
+
+
+def read_stash(stash_u8, n_tiles, slots):
+    """uint8 stash -> float tensor [n_tiles, slots, 128, 64]."""
+    raw = stash_u8.detach().cpu().view(torch.int16).reshape(n_tiles, slots, SLAB // 2)
+    idx = unswizzle_index().reshape(-1)
+    vals = raw[:, :, idx].reshape(n_tiles, slots, 128, 64)
+    return vals.contiguous().view(torch.bfloat16).float()
+
+
+def stash_rows(st, slot, nslab, P):
+    """[n_tiles, slots, 128, 64] -> [P, 64*nslab] (points x features) for `nslab` consecutive slots."""
+    n_tiles = st.shape[0]
+    x = st[:, slot:slot + nslab]                       # [T, nslab, 128, 64]
+    x = x.permute(0, 2, 1, 3).reshape(n_tiles * 128, nslab * 64)
+    return x[:P]
+
+
+def mlp_reference(params, x, spec: O.MLPSpec, emulate_bf16=True):
+    """Layer-by-layer torch reference of the MLP that mirrors the kernel's numerics: bf16 weights and
+    bf16 activations between GEMM layers, fp32 accumulation, fp32 heads (alpha / rgb / output) on the
+    un-rounded fp32 activations.  Returns dict with every intermediate."""
+    q = (lambda t: bf16r(t)) if emulate_bf16 else (lambda t: t)
+    xp, xd = torch.split(x, [spec.input_ch, spec.input_ch_views], dim=-1)
+    out = {}
+    xp_q, xd_q = q(xp), q(xd)
+    h_q = xp_q
+    h32 = None
+    for i in range(spec.D):
+        w = q(params["pts_linears.%d.weight" % i])
+        h32 = torch.relu(h_q @ w.T + params["pts_linears.%d.bias" % i])
+        out["H%d" % i] = q(h32)
+        h_q = q(h32)
+        if i in spec.skips:
+            h_q = torch.cat([xp_q, h_q], -1)
+    if not spec.use_viewdirs:
+        out["raw"] = h32 @ params["output_linear.weight"].T + params["output_linear.bias"]
+        return out
+    sigma = h32 @ params["alpha_linear.weight"].T + params["alpha_linear.bias"]
+    feat32 = h_q @ q(params["feature_linear.weight"]).T + params["feature_linear.bias"]
+    out["feat"] = q(feat32)
+    hv32 = torch.relu(torch.cat([q(feat32), xd_q], -1) @ q(params["views_linears.0.weight"]).T
+                      + params["views_linears.0.bias"])
+    out["HV"] = q(hv32)
+    rgb = hv32 @ params["rgb_linear.weight"].T + params["rgb_linear.bias"]
+    out["raw"] = torch.cat([rgb, sigma], -1)
+    return out
+
+
+def make_net(D, use_viewdirs=True, seed=0, device="cuda", sigma_bias=0.0):
+    """(package NeRF on device, oracle params dict on CPU, MLPSpec) with identical parameters."""
+    spec = O.MLPSpec(D=D, use_viewdirs=use_viewdirs)
+    p = O.init_params(spec, seed=3407 + D + seed)
+    if sigma_bias and use_viewdirs:
+        p = O.trained_like(p, sigma_bias)
+    net = dn().NeRF(D=D, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=use_viewdirs)
+    net.load_state_dict(p)
+    return net.to(device), p, spec

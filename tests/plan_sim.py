@@ -1,0 +1,137 @@
+"""Pure-numpy interpreter of the MLP execution plan (depth-lidar-nerf_b200/plan.py): executes the chain
+programs, pack jobs and wgrad items with the semantics the CUDA kernels implement (csrc/mlp_kernels.cu),
+in float64 and without the bf16 rounding or the smem swizzle.  Test infrastructure: lets the CPU suite
+prove that the *plan* (offsets, transposes, slab/slot maps, K-slab lists, heads) reproduces the
+reference MLP and its gradients before any GPU time is spent."""
+from __future__ import annotations
+
+import numpy as np
+
+import dlnerf_b200 as dn
+
+L = dn._lib
+
+
+def _stage_matrix(flat, job):
+    """Logical [n_rows, 64] weight stage a PackJob describes."""
+    M = np.zeros((job.n_rows, 64))
+    W = flat[job.src_off:]
+    for n in range(min(job.n_rows, job.n_valid)):
+        for k in range(job.k_valid):
+            if job.transposed:
+                M[n, k] = W[(job.row0 + k) * job.ld + job.col0 + n]
+            else:
+                M[n, k] = W[(job.row0 + n) * job.ld + job.col0 + k]
+    return M
+
+
+def _stage_matrix_fast(flat, job):
+    M = np.zeros((job.n_rows, 64))
+    nv, kv = min(job.n_rows, job.n_valid), job.k_valid
+    if job.transposed:
+        rows = job.row0 + np.arange(kv)
+        cols = job.col0 + np.arange(nv)
+        M[:nv, :kv] = flat[job.src_off + rows[None, :] * job.ld + cols[:, None]]
+    else:
+        rows = job.row0 + np.arange(nv)
+        cols = job.col0 + np.arange(kv)
+        M[:nv, :kv] = flat[job.src_off + rows[:, None] * job.ld + cols[None, :]]
+    return M
+
+
+def _stages_by_offset(flat, jobs):
+    return {j.dst_off: _stage_matrix_fast(flat, j) for j in jobs}
+
+
+def run_forward(plan, flat, enc_pts, enc_dir):
+    """enc_pts [P, <=64], enc_dir [P, <=64] (already encoded rows).  Returns (out [P,out_ch], stash dict
+    slot -> [P,64], masks dict slot -> bool [P, n_out])."""
+    prog = plan.fwd
+    P = enc_pts.shape[0]
+    slabs = [np.zeros((P, 64)) for _ in range(6)]
+    slabs[4][:, :enc_pts.shape[1]] = enc_pts
+    slabs[5][:, :enc_dir.shape[1]] = enc_dir
+    stash = {0: slabs[4].copy(), 1: slabs[5].copy()}
+    masks = {}
+    stages = _stages_by_offset(flat, plan.fwd_jobs)
+    sigma = None
+    out = None
+    for s in range(prog.n_steps):
+        st = prog.steps[s]
+        acc = np.zeros((P, st.n_out))
+        for j in range(st.nk):
+            Wst = stages[st.w_off + j * st.n_out * 128]
+            k = 16 * st.kcnt[j]
+            acc += slabs[st.kslab[j]][:, :k] @ Wst[:, :k].T
+        x = acc + flat[st.bias_off: st.bias_off + st.n_out]
+        if st.epi in (L.EPI_RELU, L.EPI_RELU_SIGMA, L.EPI_RELU_RGB, L.EPI_RELU_OUT):
+            if st.mask_slot >= 0:
+                masks[st.mask_slot] = x > 0
+            x = np.maximum(x, 0)
+        heads = None
+        if st.n_heads:
+            Hw = flat[st.head_off: st.head_off + st.n_heads * st.n_out].reshape(st.n_heads, st.n_out)
+            heads = x @ Hw.T + flat[st.head_bias_off: st.head_bias_off + st.n_heads]
+        for i in range(st.n_out // 64):
+            slabs[i] = x[:, 64 * i: 64 * i + 64].copy()
+            if st.stash_slot >= 0:
+                stash[st.stash_slot + i] = slabs[i].copy()
+        if st.epi == L.EPI_RELU_SIGMA:
+            sigma = heads[:, 0]
+        elif st.epi == L.EPI_RELU_RGB:
+            out = np.concatenate([heads[:, :3], sigma[:, None]], 1)
+        elif st.epi == L.EPI_RELU_OUT:
+            out = heads[:, :prog.out_ch]
+    return out, stash, masks
+
+
+def run_backward(plan, flat, d_out, masks):
+    """Returns the backward stash dict slot -> [P,64]."""
+    prog = plan.bwd
+    P = d_out.shape[0]
+    slabs = [np.zeros((P, 64)) for _ in range(6)]
+    stash = {}
+    nh = 3 if prog.use_viewdirs else prog.out_ch
+    width = 128 if prog.use_viewdirs else 256
+    Hw = flat[prog.pro_head_off: prog.pro_head_off + nh * width].reshape(nh, width)
+    dz = (d_out[:, :nh] @ Hw) * masks[prog.pro_mask_slot][:, :width]
+    for i in range(width // 64):
+        slabs[i] = dz[:, 64 * i: 64 * i + 64].copy()
+        stash[prog.pro_slot + i] = slabs[i].copy()
+    slabs[4][:, :prog.out_ch] = d_out[:, :prog.out_ch]
+    stash[0] = slabs[4].copy()
+    dsig = d_out[:, 3] if prog.out_ch > 3 else np.zeros(P)
+    stages = _stages_by_offset(flat, plan.bwd_jobs)
+    for s in range(prog.n_steps):
+        st = prog.steps[s]
+        acc = np.zeros((P, st.n_out))
+        for j in range(st.nk):
+            Wst = stages[st.w_off + j * st.n_out * 128]
+            k = 16 * st.kcnt[j]
+            acc += slabs[st.kslab[j]][:, :k] @ Wst[:, :k].T
+        x = acc
+        if st.epi == L.EPI_BWD_MASK_SIGMA:
+            x = x + dsig[:, None] * flat[st.head_off: st.head_off + st.n_out][None, :]
+        if st.epi in (L.EPI_BWD_MASK, L.EPI_BWD_MASK_SIGMA):
+            x = x * masks[st.mask_slot]
+        for i in range(st.n_out // 64):
+            slabs[i] = x[:, 64 * i: 64 * i + 64].copy()
+            if st.stash_slot >= 0:
+                stash[st.stash_slot + i] = slabs[i].copy()
+    return stash
+
+
+def run_wgrad(plan, stash_f, stash_b):
+    g = np.zeros(plan.n_params)
+    for it in plan.wgrad:
+        A = np.concatenate([stash_b[it.a_slot + i] for i in range(it.a_nslab)], 1)        # [P, 64*a_nslab]
+        src = stash_b if it.b_from_bwd else stash_f
+        B = np.concatenate([src[it.b_slot + i] for i in range(it.b_nslab)], 1)            # [P, 64*b_nslab]
+        acc = A.T @ B
+        for i in range(it.n_rows):
+            row = it.row_off + i
+            g[it.dw_off + i * it.ld + it.col_off: it.dw_off + i * it.ld + it.col_off + it.n_cols] += acc[row, :it.n_cols]
+        if it.db_off >= 0:
+            colsum = A.sum(0)
+            g[it.db_off: it.db_off + it.db_n] += colsum[it.db_col_off: it.db_col_off + it.db_n]
+    return g
