@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""Benchmark of the ray-rendering training hot path (BASELINE.json metric: training rays/sec, fwd+bwd).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--n-rand R] [--impl ours|reference]
+
+One "step" = render(coarse+fine) + RGB/depth loss + backward over one batch of synthetic LLFF-shaped rays
+(config B of SURVEY.md §8: fern_dsnerf.txt shapes, N_rand=4096 -> 2048 RGB + 2048 depth rays, 64+64
+samples, coarse D=4 / fine D=8, W=256, use_viewdirs, perturb=1, raw_noise_std=1, NDC), the optimiser
+step excluded as in BASELINE.md §3.  For N>1 every rank renders its own N_rand rays (weak scaling) and the
+MLP gradients are all-reduced over NCCL inside the step.
+
+Prints ONE JSON line (see the task contract): `value` = rays/s with the ray batch resident in HBM;
+`e2e` = the same step through the drop-in API from pinned HOST buffers (H2D of the ray batch + targets,
+D2H of the loss, every step); `roofline` for the dominant kernel from CUDA events recorded around every
+launch of the timed region; `cpu_baseline` = the oracle port of the reference on the host cores.
+
+`--impl reference` times the reference's own CPU implementation (the oracle port: the reference is Python
+and cannot travel to the GPU box) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+H, W, FOCAL = 378, 504, 407.6
+N_SAMPLES, N_IMPORTANCE = 64, 64
+COARSE_D, FINE_D = 4, 8
+DEPTH_LAMBDA = 0.01
+
+# algorithmic (unpadded) MACs per point, SURVEY.md §8(d)
+MACS_FWD = {8: 593408, 4: 315136}
+MACS_DGRAD = {8: 557696, 4: 295552}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        sm.sort()
+        # under load = upper half of the samples (the sampler also sees the idle edges)
+        load = sm[len(sm) // 2:] if sm else []
+        med = load[len(load) // 2] if load else None
+        return {"sm_mhz": med, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------
+def make_batch(n_rand, seed):
+    """Synthetic LLFF-shaped batch: forward-facing pinhole cameras near the origin with small
+    pose jitter, uniformly random pixels; colour targets U(0,1)^3; NDC depth targets U(0.25,1) with ~15 %
+    'sky' rays at 1-1e-7.  RGB rays first, depth rays after (run_nerf.py:1409-1411)."""
+    import math
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    n_dep = n_rand // 2
+    n_rgb = n_rand - n_dep
+    px, py = torch.rand(n_rand, generator=g) * (W - 1), torch.rand(n_rand, generator=g) * (H - 1)
+    d = torch.stack([(px - W * .5) / FOCAL, -(py - H * .5) / FOCAL, -torch.ones_like(px)], -1)
+    ang = (torch.rand(n_rand, 2, generator=g) - .5) * (10. * math.pi / 180.)
+    cx, sx, cy, sy = torch.cos(ang[:, 0]), torch.sin(ang[:, 0]), torch.cos(ang[:, 1]), torch.sin(ang[:, 1])
+    dy, dz = d[:, 1] * cx - d[:, 2] * sx, d[:, 1] * sx + d[:, 2] * cx
+    rd = torch.stack([d[:, 0] * cy + dz * sy, dy, -d[:, 0] * sy + dz * cy], -1)
+    t = torch.rand(n_rand, 3, generator=g)
+    ro = torch.stack([(t[:, 0] - .5) * .6, (t[:, 1] - .5) * .6, (t[:, 2] - .5) * .1], -1)
+    tgt = torch.rand(n_rgb, 3, generator=g)
+    dep = .25 + .75 * torch.rand(n_dep, generator=g)
+    dep = torch.where(torch.rand(n_dep, generator=g) < .15, torch.full_like(dep, 1. - 1e-7), dep)
+    return ro.float(), rd.float(), tgt.float(), dep.float(), n_rgb, n_dep
+
+
+def run_reference(args):
+    """CPU arm: the oracle port of the reference's render + loss + backward on a bounded ray sample."""
+    import torch
+    from oracle import nerf_oracle as O
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    torch.manual_seed(3407)
+    total = args.steps + args.warmup
+    n_sample = int(max(128, min(1024, (60000 // max(total, 1)) // 64 * 64)))
+    spec_c, spec_f = O.MLPSpec(D=COARSE_D), O.MLPSpec(D=FINE_D)
+    pc = {k: v.requires_grad_(True) for k, v in O.init_params(spec_c, 3407 + COARSE_D).items()}
+    pf = {k: v.requires_grad_(True) for k, v in O.init_params(spec_f, 3407 + FINE_D).items()}
+    ro, rd, tgt, dep, n_rgb, n_dep = make_batch(n_sample, 3407)
+    rb = O.pack_rays(H, W, FOCAL, ro, rd)
+
+    def step():
+        rng = O.RenderRNG(torch.rand(n_sample, N_SAMPLES), torch.randn(n_sample, N_SAMPLES),
+                          torch.rand(n_sample, N_IMPORTANCE), torch.randn(n_sample, N_SAMPLES + N_IMPORTANCE))
+        out = O.render_rays(rb, pc, spec_c, pf, spec_f, N_SAMPLES, N_IMPORTANCE, rng, raw_noise_std=1.0)
+        res = O.train_loss(out, n_rgb, tgt, dep, depth_lambda=DEPTH_LAMBDA, depth_importance=1.0)
+        for p in list(pc.values()) + list(pf.values()):
+            p.grad = None
+        res["loss"].backward()
+        return float(res["loss"].detach())
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / max(args.steps, 1)
+    v = n_sample / dt
+    cores = torch.get_num_threads()
+    sample = "%d of the %d rays of the step (%d RGB + %d depth), full 64+64 samples, D=%d/%d nets" % (
+        n_sample, args.n_rand, n_rgb, n_dep, COARSE_D, FINE_D)
+    print(json.dumps({
+        "impl": "reference", "metric": "training rays/sec (fwd+bwd)", "value": v, "unit": "rays/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": v, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample,
+                         "os_cpu_count": os.cpu_count(), "anomaly_detection": False},
+        "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def workload_config(args, world):
+    return {"workload": "fern_dsnerf.txt coarse+fine training step with depth loss, synthetic LLFF-shaped rays",
+            "n_rand_per_gpu": args.n_rand, "global_rays_per_step": args.n_rand * world,
+            "rgb_rays": args.n_rand - args.n_rand // 2, "depth_rays": args.n_rand // 2,
+            "N_samples": N_SAMPLES, "N_importance": N_IMPORTANCE, "netdepth": COARSE_D, "netdepth_fine": FINE_D,
+            "netwidth": 256, "use_viewdirs": True, "perturb": 1.0, "raw_noise_std": 1.0, "ndc": True,
+            "depth_lambda": DEPTH_LAMBDA, "optimizer_step": "excluded (BASELINE.md §3)",
+            "parallelism": "ray-sharded dp%d, NCCL all-reduce of MLP grads" % world,
+            "l2": "per-step working set (activation stashes, ~1.3 MB/ray) is far larger than the 126 MB L2; no flush"}
+
+
+def cpu_baseline(seconds_budget=25.0):
+    """Oracle port of the reference on the host cores, config A (1024 rays), bounded to ~25 s."""
+    import torch
+    from oracle import nerf_oracle as O
+    n = 1024
+    spec_c, spec_f = O.MLPSpec(D=COARSE_D), O.MLPSpec(D=FINE_D)
+    pc = {k: v.requires_grad_(True) for k, v in O.init_params(spec_c, 3407 + COARSE_D).items()}
+    pf = {k: v.requires_grad_(True) for k, v in O.init_params(spec_f, 3407 + FINE_D).items()}
+    ro, rd, tgt, dep, n_rgb, n_dep = make_batch(n, 3407)
+    rb = O.pack_rays(H, W, FOCAL, ro, rd)
+    times = []
+    t_start = time.perf_counter()
+    it = 0
+    while True:
+        rng = O.synth_rng(n, N_SAMPLES, N_IMPORTANCE, seed=it)
+        t0 = time.perf_counter()
+        out = O.render_rays(rb, pc, spec_c, pf, spec_f, N_SAMPLES, N_IMPORTANCE, rng, raw_noise_std=1.0)
+        res = O.train_loss(out, n_rgb, tgt, dep, depth_lambda=DEPTH_LAMBDA, depth_importance=1.0)
+        for p in list(pc.values()) + list(pf.values()):
+            p.grad = None
+        res["loss"].backward()
+        times.append(time.perf_counter() - t0)
+        it += 1
+        if it >= 2 and (time.perf_counter() - t_start > seconds_budget or it >= 8):
+            break
+    ts = sorted(times[1:])
+    med = ts[len(ts) // 2]
+    return {"value": n / med, "unit": "rays/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": "config A: 1024 rays (512 RGB + 512 depth), 64+64 samples, D=4/8; median of %d steps after 1 warm-up"
+                      % len(ts), "os_cpu_count": os.cpu_count(), "ms_per_step": med * 1e3, "anomaly_detection": False}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import dlnerf_b200 as dn
+    L = dn._lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(3407 + rank)
+
+    torch.manual_seed(3407)              # identical random-init weights (nn.Linear default) on every rank
+    net_c = dn.NeRF(D=COARSE_D, W=256, input_ch=63, input_ch_views=27, use_viewdirs=True).to(dev)
+    net_f = dn.NeRF(D=FINE_D, W=256, input_ch=63, input_ch_views=27, use_viewdirs=True).to(dev)
+    torch.manual_seed(3407 + rank)
+    params = list(net_c.parameters()) + list(net_f.parameters())
+    q = dn.FusedQuery(dn.get_embedder(10, 0)[0], dn.get_embedder(4, 0)[0], 65536, 10, 4, 0)
+    kw = dict(network_query_fn=q, perturb=1.0, N_importance=N_IMPORTANCE, network_fine=net_f, N_samples=N_SAMPLES,
+              network_fn=net_c, use_viewdirs=True, white_bkgd=False, raw_noise_std=1.0, ndc=True, near=0., far=1.)
+
+    ro, rd, tgt, dep, n_rgb, n_dep = make_batch(args.n_rand, 3407 + rank)
+    host_rays = torch.stack([ro, rd], 0).pin_memory()
+    host_tgt, host_dep = tgt.pin_memory(), dep.pin_memory()
+    d_rays, d_tgt, d_dep = host_rays.to(dev), host_tgt.to(dev), host_dep.to(dev)
+
+    def allreduce_grads():
+        if world == 1:
+            return
+        flat = torch.cat([p.grad.reshape(-1) for p in params])
+        dist.all_reduce(flat)
+        flat.div_(world)
+        o = 0
+        for p in params:
+            p.grad.copy_(flat[o:o + p.numel()].view_as(p))
+            o += p.numel()
+
+    def step(rays, t_rgb, t_dep):
+        rgb, disp, acc, depth, extras = dn.render(H, W, FOCAL, chunk=1 << 30, rays=rays, retraw=True, **kw)
+        for p in params:
+            p.grad = None
+        loss = dn.img2mse(rgb[:n_rgb], t_rgb) + DEPTH_LAMBDA * dn.img2mse(depth[n_rgb:], t_dep) \
+            + dn.img2mse(extras["rgb0"][:n_rgb], t_rgb)
+        loss.backward()
+        allreduce_grads()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1) / steps
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    # ---- device-resident throughput -------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        step(d_rays, d_tgt, d_dep)
+    L.TRACE = []
+    n0 = L.LAUNCHES
+    with ClockSampler(local) as clk:
+        ms = timed(lambda: step(d_rays, d_tgt, d_dep), args.steps)
+    trace, L.TRACE = L.TRACE, None
+    launches = (L.LAUNCHES - n0) // max(args.steps, 1)
+    value = args.n_rand * world / (ms * 1e-3)
+
+    # ---- per-kernel times from the events of the timed region --------------------------------------
+    agg = {}
+    for tag, a, b in trace:
+        t = a.elapsed_time(b)
+        s = agg.setdefault(tag, [0.0, 0])
+        s[0] += t
+        s[1] += 1
+    kern = {k: {"ms_per_launch": v[0] / v[1], "launches_per_step": v[1] / args.steps,
+                "ms_per_step": v[0] / args.steps} for k, v in agg.items()}
+    pk = peaks()
+    pts = {COARSE_D: args.n_rand * N_SAMPLES, FINE_D: args.n_rand * (N_SAMPLES + N_IMPORTANCE)}
+    flops = {}
+    for D in (COARSE_D, FINE_D):
+        flops["mlp_fwd D=%d" % D] = 2.0 * MACS_FWD[D] * pts[D]
+        flops["mlp_dgrad D=%d" % D] = 2.0 * MACS_DGRAD[D] * pts[D]
+        flops["mlp_wgrad D=%d" % D] = 2.0 * MACS_FWD[D] * pts[D]
+    for k in kern:
+        if k in flops:
+            kern[k]["tflops"] = flops[k] / (kern[k]["ms_per_launch"] * 1e-3) / 1e12
+            kern[k]["frac_of_sustained_peak"] = kern[k]["tflops"] / pk["tf_sust"]
+    mlp_keys = [k for k in kern if k in flops]
+    top = max(mlp_keys, key=lambda k: kern[k]["ms_per_step"])
+    mlp_ms = sum(kern[k]["ms_per_step"] for k in mlp_keys)
+    mlp_tflops = sum(flops[k] for k in mlp_keys) / (mlp_ms * 1e-3) / 1e12
+    roofline = {"kernel": top, "bound": "tensor", "achieved": kern[top]["tflops"], "peak": pk["tf_sust"],
+                "unit": "TFLOP/s", "frac": kern[top]["tflops"] / pk["tf_sust"], "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (%s)" % pk["src"],
+                "share_of_step": kern[top]["ms_per_step"] / ms,
+                "all_mlp_kernels": {"tflops": mlp_tflops, "frac": mlp_tflops / pk["tf_sust"],
+                                    "ms_per_step": mlp_ms, "share_of_step": mlp_ms / ms},
+                "flops_basis": "algorithmic unpadded MACs/point (SURVEY §8d) x points per launch"}
+
+    # ---- end to end from pinned host memory ------------------------------------------------------------
+    def e2e_step():
+        r = host_rays.to(dev, non_blocking=True)
+        t1 = host_tgt.to(dev, non_blocking=True)
+        t2 = host_dep.to(dev, non_blocking=True)
+        return float(step(r, t1, t2).item())
+
+    for _ in range(3):
+        e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+    e2e = {"value": args.n_rand * world / (ms_e2e * 1e-3), "unit": "rays/s", "ms_per_step": ms_e2e,
+           "h2d_bytes_per_step": int(host_rays.numel() + host_tgt.numel() + host_dep.numel()) * 4,
+           "d2h_bytes_per_step": 4, "api": "dlnerf_b200.render(...) + img2mse + loss.backward() (drop-in path)"}
+
+    cb = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cb = cpu_baseline()
+    if rank == 0:
+        print(json.dumps({
+            "metric": "training rays/sec (fwd+bwd)", "value": value, "unit": "rays/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": workload_config(args, world), "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches,
+            "roofline": roofline, "cpu_baseline": cb, "kernels": kern}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--n-rand", type=int, default=4096, help="rays per step per GPU (config B: 4096)")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

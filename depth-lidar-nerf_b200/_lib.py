@@ -124,6 +124,29 @@ class DlnError(RuntimeError):
     pass
 
 
+# Launch accounting (bench.py): LAUNCHES counts kernel-launching ABI calls; when TRACE is a list every call
+# is bracketed by CUDA events recorded on the launching (current) stream and appended as (tag, ev0, ev1).
+LAUNCHES = 0
+TRACE = None
+
+
+def call(name: str, *args, tag: str = None) -> None:
+    """Invoke one ABI entry point, raise on a non-zero return code."""
+    global LAUNCHES
+    fn = getattr(lib(), name)
+    LAUNCHES += 1
+    if TRACE is not None:
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args)
+        e1.record()
+        TRACE.append((tag or name, e0, e1))
+    else:
+        rc = fn(*args)
+    check(rc, tag or name)
+
+
 def check(rc: int, what: str) -> None:
     if rc == 0:
         return

@@ -36,7 +36,8 @@ __device__ __forceinline__ float warp_sum(float v) {
 __device__ __forceinline__ float linspace01(int i, int n) {
   if (n <= 1) return 0.f;
   const float step = __fdiv_rn(1.0f, (float)(n - 1));
-  return (i < n / 2) ? __fmul_rn(step, (float)i) : __fsub_rn(1.0f, __fmul_rn(step, (float)(n - 1 - i)));
+  // ATen evaluates both branches as one fused multiply-add (single rounding)
+  return (i < n / 2) ? __fmul_rn(step, (float)i) : __fmaf_rn(-step, (float)(n - 1 - i), 1.0f);
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

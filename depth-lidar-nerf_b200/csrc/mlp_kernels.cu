@@ -209,6 +209,12 @@ __global__ void __launch_bounds__(kThreads, 1)
           umma_commit(&sm->acc_full[gstep & 1]);
           par ^= step_out_mask(st);
         }
+        // Parity waits are only sound while a waiter is never two phases ahead of the barrier.  No MMA
+        // consumes the slabs the LAST step produces (they only go to the stash), so observe them here
+        // before waiting for the next tile's productions of the same slabs.
+        const uint32_t om = step_out_mask(prog.steps[prog.n_steps - 1]);
+        for (int slab = 0; slab < 4; ++slab)
+          if ((om >> slab) & 1) mbar_wait(&sm->a_ready[slab], ((par >> slab) & 1) ^ 1);
       }
     }
   } else if (warp == 2) {
@@ -616,7 +622,9 @@ int dln_mlp_chain(const DlnChainProgram* prog, const DlnChainArgs* args, int num
   DLN_CHECK_ARG(prog->n_steps >= 1 && prog->n_steps <= DLN_MAX_STEPS);
   DLN_CHECK_ARG(prog->out_ch >= 1 && prog->out_ch <= 5);
   DLN_CHECK_ARG(prog->L_pts >= 0 && prog->L_pts <= 10 && prog->L_dir >= 0 && prog->L_dir <= 10);
-  DLN_CHECK_ARG(args->wblob && args->fblob && args->P >= 0);
+  DLN_CHECK_ARG(args->P >= 0);
+  if (args->P == 0) return DLN_OK;
+  DLN_CHECK_ARG(args->wblob && args->fblob);
   int head_floats = prog->backward ? (prog->use_viewdirs ? 3 * 128 : prog->out_ch * 256) : 0;
   for (int s = 0; s < prog->n_steps; ++s) {
     const DlnChainStep& st = prog->steps[s];

@@ -40,8 +40,8 @@ def stratified_z(ray_batch: Tensor, n_samples: int, t_rand: Optional[Tensor] = N
     tr = None if t_rand is None else _f32(t_rand, "stratified_z")
     if tr is not None and tuple(tr.shape) != (N, n_samples):
         raise ValueError("t_rand must be [N, N_samples]")
-    L.check(L.lib().dln_stratified_z(rb.data_ptr(), rb.stride(0), _ptr(tr), z.data_ptr(), N, n_samples,
-                                     int(bool(lindisp)), _stream()), "stratified_z")
+    L.call("dln_stratified_z", rb.data_ptr(), rb.stride(0), _ptr(tr), z.data_ptr(), N, n_samples,
+                                     int(bool(lindisp)), _stream(), tag="stratified_z")
     return z
 
 
@@ -52,7 +52,7 @@ def posenc(x: Tensor, n_freqs: int) -> Tensor:
         raise ValueError("posenc expects [..., 3]")
     flat = xs.reshape(-1, 3)
     out = torch.empty(flat.shape[0], 3 + 6 * n_freqs, device=xs.device, dtype=torch.float32)
-    L.check(L.lib().dln_posenc(flat.data_ptr(), out.data_ptr(), flat.shape[0], n_freqs, _stream()), "posenc")
+    L.call("dln_posenc", flat.data_ptr(), out.data_ptr(), flat.shape[0], n_freqs, _stream(), tag="posenc")
     return out.reshape(*xs.shape[:-1], out.shape[-1])
 
 
@@ -71,10 +71,9 @@ class _Composite(torch.autograd.Function):
         rgb = torch.empty(N, 3, device=dev)
         disp, acc, depth = torch.empty(N, device=dev), torch.empty(N, device=dev), torch.empty(N, device=dev)
         w = torch.empty(N, S, device=dev)
-        L.check(L.lib().dln_composite_fwd(raw_c.data_ptr(), Cc, z_c.data_ptr(), d_c.data_ptr(), _ptr(nz),
+        L.call("dln_composite_fwd", raw_c.data_ptr(), Cc, z_c.data_ptr(), d_c.data_ptr(), _ptr(nz),
                                           float(noise_std), int(white_bkgd), rgb.data_ptr(), disp.data_ptr(),
-                                          acc.data_ptr(), w.data_ptr(), depth.data_ptr(), N, S, _stream()),
-                "composite_fwd")
+                                          acc.data_ptr(), w.data_ptr(), depth.data_ptr(), N, S, _stream(), tag="composite_fwd")
         ctx.save_for_backward(raw_c, z_c, d_c, nz if nz is not None else torch.empty(0, device=dev))
         ctx.cfg = (float(noise_std), int(white_bkgd), nz is not None)
         return rgb, disp, acc, w, depth
@@ -86,10 +85,10 @@ class _Composite(torch.autograd.Function):
         N, S, Cc = raw_c.shape
         gs = [None if g is None else _f32(g, "raw2outputs.backward") for g in (g_rgb, g_disp, g_acc, g_w, g_depth)]
         d_raw = torch.empty_like(raw_c)
-        L.check(L.lib().dln_composite_bwd(raw_c.data_ptr(), Cc, z_c.data_ptr(), d_c.data_ptr(),
+        L.call("dln_composite_bwd", raw_c.data_ptr(), Cc, z_c.data_ptr(), d_c.data_ptr(),
                                           nz.data_ptr() if has_noise else None, noise_std, white,
                                           _ptr(gs[0]), _ptr(gs[1]), _ptr(gs[2]), _ptr(gs[3]), _ptr(gs[4]),
-                                          d_raw.data_ptr(), N, S, _stream()), "composite_bwd")
+                                          d_raw.data_ptr(), N, S, _stream(), tag="composite_bwd")
         return d_raw, None, None, None, None, None
 
 
@@ -112,11 +111,10 @@ def composite_bwd_fused_loss(raw: Tensor, z_vals: Tensor, rays_d: Tensor, noise:
     N, S, Cc = raw_c.shape
     nz = None if noise is None else _f32(noise, "fused_loss")
     d_raw = torch.empty_like(raw_c)
-    L.check(L.lib().dln_composite_bwd_fused_loss(
+    L.call("dln_composite_bwd_fused_loss", 
         raw_c.data_ptr(), Cc, z_c.data_ptr(), d_c.data_ptr(), _ptr(nz), float(noise_std), int(white_bkgd),
         _ptr(target_rgb), _ptr(target_depth), _ptr(ray_weights), int(n_rgb), float(coef_rgb), float(coef_depth),
-        int(depth_mode), float(depth_norm), loss_sums.data_ptr(), d_raw.data_ptr(), N, S, _stream()),
-        "composite_bwd_fused_loss")
+        int(depth_mode), float(depth_norm), loss_sums.data_ptr(), d_raw.data_ptr(), N, S, _stream(), tag="composite_bwd_fused_loss")
     return d_raw
 
 
@@ -137,8 +135,8 @@ def sample_pdf(bins: Tensor, weights: Tensor, n_samples: int, u: Optional[Tensor
     out = torch.empty(N, n_samples, device=b.device)
     cdf = torch.empty(N, B, device=b.device) if return_debug else None
     inds = torch.empty(N, n_samples, device=b.device, dtype=torch.int64) if return_debug else None
-    L.check(L.lib().dln_sample_pdf(b2.data_ptr(), B, 0, w2.data_ptr(), B - 1, B, _ptr(uu), n_samples, out.data_ptr(),
-                                   None, 0, None, _ptr(cdf), _ptr(inds), N, _stream()), "sample_pdf")
+    L.call("dln_sample_pdf", b2.data_ptr(), B, 0, w2.data_ptr(), B - 1, B, _ptr(uu), n_samples, out.data_ptr(),
+                                   None, 0, None, _ptr(cdf), _ptr(inds), N, _stream(), tag="sample_pdf")
     out = out.reshape(*lead, n_samples)
     if return_debug:
         return out, cdf.reshape(*lead, B), inds.reshape(*lead, n_samples)
@@ -158,9 +156,8 @@ def importance_resample(z_vals: Tensor, weights: Tensor, n_importance: int, u: O
     zm = torch.empty(N, S + n_importance, device=z.device)
     cdf = torch.empty(N, S - 1, device=z.device) if return_debug else None
     inds = torch.empty(N, n_importance, device=z.device, dtype=torch.int64) if return_debug else None
-    L.check(L.lib().dln_sample_pdf(z.data_ptr(), S, 1, w.data_ptr() + 4, S, S - 1, _ptr(uu), n_importance,
-                                   zs.data_ptr(), z.data_ptr(), S, zm.data_ptr(), _ptr(cdf), _ptr(inds), N, _stream()),
-            "importance_resample")
+    L.call("dln_sample_pdf", z.data_ptr(), S, 1, w.data_ptr() + 4, S, S - 1, _ptr(uu), n_importance,
+                                   zs.data_ptr(), z.data_ptr(), S, zm.data_ptr(), _ptr(cdf), _ptr(inds), N, _stream(), tag="importance_resample")
     if return_debug:
         return zs, zm, cdf, inds
     return zs, zm
@@ -177,6 +174,6 @@ def searchsorted(a: Tensor, v: Tensor, side: str = "left") -> Tensor:
         raise ValueError("`a` and `v` must have the same number of rows or one of them must have only one")
     rows = max(aa.shape[0], vv.shape[0])
     out = torch.empty(rows, vv.shape[1], device=aa.device, dtype=torch.int64)
-    L.check(L.lib().dln_searchsorted(aa.data_ptr(), aa.shape[0], aa.shape[1], vv.data_ptr(), vv.shape[0], vv.shape[1],
-                                     out.data_ptr(), int(side == "right"), _stream()), "searchsorted")
+    L.call("dln_searchsorted", aa.data_ptr(), aa.shape[0], aa.shape[1], vv.data_ptr(), vv.shape[0], vv.shape[1],
+                                     out.data_ptr(), int(side == "right"), _stream(), tag="searchsorted")
     return out

@@ -162,10 +162,10 @@ class NeRF(nn.Module):
             return
         pl = self._plan
         lib, s = L.lib(), ops._stream()
-        L.check(lib.dln_mlp_pack_weights(st["flat"].data_ptr(), st["fwd_jobs"].data_ptr(), len(pl.fwd_jobs),
-                                         st["wf"].data_ptr(), s), "pack_weights(fwd)")
-        L.check(lib.dln_mlp_pack_weights(st["flat"].data_ptr(), st["bwd_jobs"].data_ptr(), len(pl.bwd_jobs),
-                                         st["wb"].data_ptr(), s), "pack_weights(bwd)")
+        L.call("dln_mlp_pack_weights", st["flat"].data_ptr(), st["fwd_jobs"].data_ptr(), len(pl.fwd_jobs),
+                                         st["wf"].data_ptr(), s, tag="pack_weights(fwd)")
+        L.call("dln_mlp_pack_weights", st["flat"].data_ptr(), st["bwd_jobs"].data_ptr(), len(pl.bwd_jobs),
+                                         st["wb"].data_ptr(), s, tag="pack_weights(bwd)")
         st["version"] = ver
 
     # ------------------------------------------------------------------ kernels
@@ -190,7 +190,7 @@ class NeRF(nn.Module):
             masks = torch.empty(pl.mask_slots * n_tiles * 2 * 128 * 4, device=dev, dtype=torch.int32)
             args.stash, args.masks = stash.data_ptr(), masks.data_ptr()
             saved = (stash, masks)
-        L.check(L.lib().dln_mlp_chain(C.byref(pl.fwd), C.byref(args), st["sms"], ops._stream()), "mlp_chain(fwd)")
+        L.call("dln_mlp_chain", C.byref(pl.fwd), C.byref(args), st["sms"], ops._stream(), tag="mlp_fwd D=%d" % self.D)
         return out, saved
 
     def _run_backward(self, d_out, saved, P):
@@ -207,12 +207,12 @@ class NeRF(nn.Module):
         args.wblob, args.fblob = st["wb"].data_ptr(), st["flat"].data_ptr()
         args.d_out, args.stash, args.masks = d.data_ptr(), stash_b.data_ptr(), masks.data_ptr()
         lib, s = L.lib(), ops._stream()
-        L.check(lib.dln_mlp_chain(C.byref(pl.bwd), C.byref(args), st["sms"], s), "mlp_chain(dgrad)")
+        L.call("dln_mlp_chain", C.byref(pl.bwd), C.byref(args), st["sms"], s, tag="mlp_dgrad D=%d" % self.D)
         gflat = torch.zeros(pl.n_params, device=dev, dtype=torch.float32)
         n_items = len(pl.wgrad)
         splits = int(max(1, min(n_tiles, (2 * st["sms"]) // n_items)))
-        L.check(lib.dln_mlp_wgrad(st["items"].data_ptr(), n_items, splits, stash_f.data_ptr(), pl.fwd_slots,
-                                  stash_b.data_ptr(), pl.bwd_slots, n_tiles, gflat.data_ptr(), s), "mlp_wgrad")
+        L.call("dln_mlp_wgrad", st["items"].data_ptr(), n_items, splits, stash_f.data_ptr(), pl.fwd_slots,
+                                  stash_b.data_ptr(), pl.bwd_slots, n_tiles, gflat.data_ptr(), s, tag="mlp_wgrad D=%d" % self.D)
         grads = []
         for (name, shp), p in zip(self._shape.param_shapes(), self._ordered_params()):
             o = pl.offsets[name]

@@ -130,7 +130,7 @@ def mlp_forward(p: Dict[str, Tensor], x: Tensor, spec: MLPSpec) -> Tensor:
 
 
 def run_network(pts: Tensor, viewdirs: Optional[Tensor], p: Dict[str, Tensor], spec: MLPSpec,
-                L_pts: int = 10, L_dir: int = 4) -> Tensor:
+                L_pts: int = 10, L_dir: int = 4, mlp_fn=None) -> Tensor:
     """run_nerf.py:60-74.  Encodes [N,S,3] points, broadcasts the per-ray view
     direction to every sample (:66-69) and applies the MLP.  (The reference's
     ``netchunk`` slicing (:50-57, :72) does not change results.)"""
@@ -139,7 +139,7 @@ def run_network(pts: Tensor, viewdirs: Optional[Tensor], p: Dict[str, Tensor], s
     if viewdirs is not None:
         d = viewdirs[:, None, :].expand(pts.shape).reshape(-1, 3)
         enc = torch.cat([enc, posenc(d, L_dir)], dim=-1)
-    out = mlp_forward(p, enc, spec)
+    out = (mlp_fn or mlp_forward)(p, enc, spec)   # mlp_fn: tests plug in a bf16-emulating forward
     return out.reshape(*pts.shape[:-1], out.shape[-1])
 
 
@@ -285,7 +285,7 @@ def stratified_z(near: Tensor, far: Tensor, n_samples: int, t_rand: Optional[Ten
 def render_rays(ray_batch: Tensor, p_coarse, spec_coarse: MLPSpec, p_fine, spec_fine: MLPSpec,
                 N_samples: int, N_importance: int, rng: RenderRNG, raw_noise_std: float = 0.0,
                 white_bkgd: bool = False, lindisp: bool = False, L_pts: int = 10, L_dir: int = 4,
-                retraw: bool = True) -> Dict[str, Tensor]:
+                retraw: bool = True, mlp_fn=None) -> Dict[str, Tensor]:
     """run_nerf.py:520-675 (the network_fn-is-not-None / no alpha_model /
     no sigma_loss / no semantic branch, i.e. what every shipped config runs)."""
     o, d = ray_batch[:, 0:3], ray_batch[:, 3:6]
@@ -293,7 +293,7 @@ def render_rays(ray_batch: Tensor, p_coarse, spec_coarse: MLPSpec, p_fine, spec_
     near, far = ray_batch[:, 6:7], ray_batch[:, 7:8]
     z = stratified_z(near, far, N_samples, rng.t_rand, lindisp)
     pts = o[:, None, :] + d[:, None, :] * z[:, :, None]                    # :595
-    raw = run_network(pts, vdir, p_coarse, spec_coarse, L_pts, L_dir)
+    raw = run_network(pts, vdir, p_coarse, spec_coarse, L_pts, L_dir, mlp_fn)
     n0 = None if rng.noise0 is None else rng.noise0 * raw_noise_std
     rgb, disp, acc, w, depth = raw2outputs(raw, z, d, n0, white_bkgd)
     out: Dict[str, Tensor] = {}
@@ -305,7 +305,7 @@ def render_rays(ray_batch: Tensor, p_coarse, spec_coarse: MLPSpec, p_fine, spec_
         z, _ = torch.sort(torch.cat([z, z_new], dim=-1), dim=-1)           # :636
         pts = o[:, None, :] + d[:, None, :] * z[:, :, None]
         raw = run_network(pts, vdir, p_fine if p_fine is not None else p_coarse,
-                          spec_fine if p_fine is not None else spec_coarse, L_pts, L_dir)
+                          spec_fine if p_fine is not None else spec_coarse, L_pts, L_dir, mlp_fn)
         n1 = None if rng.noise1 is None else rng.noise1 * raw_noise_std
         rgb, disp, acc, w, depth = raw2outputs(raw, z, d, n1, white_bkgd)
         out.update(rgb0=rgb0, disp0=disp0, acc0=acc0, depth_map0=depth0,

@@ -116,6 +116,54 @@ def mlp_reference(params, x, spec: O.MLPSpec, emulate_bf16=True):
     return out
 
 
+def _ste(t):
+    """bf16 rounding with a straight-through gradient."""
+    return t + (bf16r(t) - t).detach()
+
+
+def mlp_forward_emulated(params, x, spec: O.MLPSpec):
+    """Differentiable twin of mlp_reference (same numerics as the kernels, straight-through rounding):
+    autograd through it gives the gradient of the function the kernels actually evaluate, i.e. with the
+    ReLU masks of the bf16 forward pass.  Drop-in for oracle.mlp_forward (mlp_fn=...)."""
+    xp, xd = torch.split(x, [spec.input_ch, spec.input_ch_views], dim=-1)
+    xp_q, xd_q = _ste(xp), _ste(xd)
+    h_q, h32 = xp_q, None
+    for i in range(spec.D):
+        h32 = torch.relu(h_q @ _ste(params["pts_linears.%d.weight" % i]).T + params["pts_linears.%d.bias" % i])
+        h_q = _ste(h32)
+        if i in spec.skips:
+            h_q = torch.cat([xp_q, h_q], -1)
+    if not spec.use_viewdirs:
+        return h32 @ params["output_linear.weight"].T + params["output_linear.bias"]
+    sigma = h32 @ params["alpha_linear.weight"].T + params["alpha_linear.bias"]
+    feat = _ste(h_q @ _ste(params["feature_linear.weight"]).T + params["feature_linear.bias"])
+    hv32 = torch.relu(torch.cat([feat, xd_q], -1) @ _ste(params["views_linears.0.weight"]).T
+                      + params["views_linears.0.bias"])
+    rgb = hv32 @ params["rgb_linear.weight"].T + params["rgb_linear.bias"]
+    return torch.cat([rgb, sigma], -1)
+
+
+def compare_grads(named_got, ref_emul, ref_fp32, tag=""):
+    """Print per-tensor cosine / rel-L2 against both references; return worst numbers and aggregates."""
+    stats = dict(worst_cos_e=1.0, worst_l2_e=0.0, worst_cos_f=1.0, worst_l2_f=0.0)
+    num_e = num_f = den_e = den_f = 0.0
+    for name, g in named_got:
+        if ref_fp32.get(name) is None:
+            continue
+        ce, le = cosine(g, ref_emul[name]), rel_l2(g, ref_emul[name])
+        cf, lf = cosine(g, ref_fp32[name]), rel_l2(g, ref_fp32[name])
+        print("  %s%-26s vs bf16-emulated: cos %.5f relL2 %.3e | vs fp32: cos %.5f relL2 %.3e | |ref| %.3e" % (
+            tag, name, ce, le, cf, lf, ref_fp32[name].norm().item()))
+        stats["worst_cos_e"], stats["worst_l2_e"] = min(stats["worst_cos_e"], ce), max(stats["worst_l2_e"], le)
+        stats["worst_cos_f"], stats["worst_l2_f"] = min(stats["worst_cos_f"], cf), max(stats["worst_l2_f"], lf)
+        gd = torch.as_tensor(g).detach().double().cpu()
+        num_e += float((gd - ref_emul[name].double()).pow(2).sum()); den_e += float(ref_emul[name].double().pow(2).sum())
+        num_f += float((gd - ref_fp32[name].double()).pow(2).sum()); den_f += float(ref_fp32[name].double().pow(2).sum())
+    stats["agg_e"], stats["agg_f"] = (num_e / den_e) ** 0.5, (num_f / den_f) ** 0.5
+    print("  %saggregate rel-L2: vs bf16-emulated %.3e, vs fp32 %.3e" % (tag, stats["agg_e"], stats["agg_f"]))
+    return stats
+
+
 def make_net(D, use_viewdirs=True, seed=0, device="cuda", sigma_bias=0.0):
     """(package NeRF on device, oracle params dict on CPU, MLPSpec) with identical parameters."""
     spec = O.MLPSpec(D=D, use_viewdirs=use_viewdirs)

@@ -4,12 +4,16 @@ Checker: a torch reference with the kernel's numerics (bf16 weights/activations,
 tests/gpu_util.mlp_reference) for tight per-layer checks, and the fp32 oracle (oracle/nerf_oracle.py,
 pinned to the reference) for the stated bf16 tolerances:
     raw outputs      |err| <= 3e-2 * max|ref|  against the fp32 oracle
-    gradients        cosine >= 0.995 and rel-L2 <= 5e-2 per tensor against fp32 autograd
+    gradients        per tensor, against autograd through the bf16-emulating torch forward (the function the
+                     kernels evaluate; ReLU masks of the bf16 pass): cosine >= 0.999, rel-L2 <= 3e-2;
+                     against fp32 autograd (different ReLU masks where a pre-activation is within bf16
+                     rounding of 0): cosine >= 0.99, rel-L2 <= 0.15
 """
 import pytest
 import torch
 
-from gpu_util import (O, bf16r, cosine, dn, make_net, mlp_reference, read_stash, rel_l2, report, stash_rows)
+from gpu_util import (O, bf16r, compare_grads, cosine, dn, make_net, mlp_forward_emulated, mlp_reference,
+                      read_stash, rel_l2, report, stash_rows)
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -66,6 +70,13 @@ def test_forward_module_interface_and_shapes():
     assert [n for n, _ in net.named_parameters()] == list(spec.param_shapes().keys())
     with torch.no_grad():
         assert net(torch.zeros(0, 90, device=DEV)).shape == (0, 4)
+    # tile-boundary sizes
+    for P in (1, 127, 129, 256):
+        xs = _inputs(P, seed=P)
+        with torch.no_grad():
+            yy = net(xs.to(DEV))
+        ff = O.mlp_forward(params, xs, spec)
+        report("P=%d" % P, yy, ff, atol=3e-2 * ff.abs().max().item(), quiet=True)
 
 
 def test_forward_without_viewdirs():
@@ -93,31 +104,28 @@ def test_fused_rays_forward_matches_encode_then_forward():
     report("forward_rays vs fp32 oracle", raw, full, atol=3e-2 * full.abs().max().item())
 
 
-def _reference_grads(params, x, spec, cot):
+def _reference_grads(params, x, spec, cot, fwd=O.mlp_forward):
     pl = {k: v.clone().requires_grad_(True) for k, v in params.items()}
-    (O.mlp_forward(pl, x, spec) * cot).sum().backward()
+    (fwd(pl, x, spec) * cot).sum().backward()
     return {k: v.grad for k, v in pl.items()}
 
 
-@pytest.mark.parametrize("D,P,vd", [(8, 128, True), (8, 900, True), (4, 515, True), (8, 300, False)])
+# the last two cases put several 128-point tiles on every persistent CTA (> 148 tiles) and wrap the wgrad ring
+@pytest.mark.parametrize("D,P,vd", [(8, 128, True), (8, 900, True), (4, 515, True), (8, 300, False),
+                                    (8, 128 * 330 + 5, True), (4, 128 * 300, False)])
 def test_backward_gradients(D, P, vd):
     net, params, spec = make_net(D, use_viewdirs=vd)
     x = _inputs(P, seed=10 + D)
     g = torch.Generator().manual_seed(5)
     out_ch = 4 if vd else 5
     cot = torch.randn(P, out_ch, generator=g)
-    ref = _reference_grads(params, x, spec, cot)
+    ref32 = _reference_grads(params, x, spec, cot)
+    refem = _reference_grads(params, x, spec, cot, mlp_forward_emulated)
     y = net(x.to(DEV))
     (y * cot.to(DEV)).sum().backward()
-    worst = 0.0
-    for name, p in net.named_parameters():
-        if ref[name] is None:
-            continue
-        c, e = cosine(p.grad, ref[name]), rel_l2(p.grad, ref[name])
-        print("  grad %-26s cosine %.5f  rel-L2 %.3e  |ref| %.3e" % (name, c, e, ref[name].norm().item()))
-        worst = max(worst, e)
-        assert c >= 0.995 and e <= 5e-2, name
-    print("  worst rel-L2 %.3e" % worst)
+    st = compare_grads([(n, p.grad) for n, p in net.named_parameters()], refem, ref32)
+    assert st["worst_cos_e"] >= 0.999 and st["worst_l2_e"] <= 3e-2
+    assert st["worst_cos_f"] >= 0.99 and st["worst_l2_f"] <= 0.15
 
 
 def test_backward_dz_per_layer():
@@ -126,21 +134,23 @@ def test_backward_dz_per_layer():
     net, params, spec = make_net(D)
     x = _inputs(P, seed=33)
     cot = torch.randn(P, 4, generator=torch.Generator().manual_seed(6))
-    # fp32 reference with hooks on the pre-activations
+    # bf16-emulating reference graph (same ReLU masks as the kernels) with the pre-activations retained
+    from gpu_util import _ste
     pl = {k: v.clone().requires_grad_(True) for k, v in params.items()}
-    xp, xd = x[:, :63], x[:, 63:]
+    xp, xd = _ste(x[:, :63]), _ste(x[:, 63:])
     zs, h = [], xp
     for i in range(D):
-        zpre = h @ pl["pts_linears.%d.weight" % i].T + pl["pts_linears.%d.bias" % i]
+        zpre = h @ _ste(pl["pts_linears.%d.weight" % i]).T + pl["pts_linears.%d.bias" % i]
         zpre.retain_grad()
         zs.append(zpre)
-        h = torch.relu(zpre)
+        h32 = torch.relu(zpre)
+        h = _ste(h32)
         if i in spec.skips:
             h = torch.cat([xp, h], -1)
-    sigma = h @ pl["alpha_linear.weight"].T + pl["alpha_linear.bias"]
-    feat = h @ pl["feature_linear.weight"].T + pl["feature_linear.bias"]
+    sigma = h32 @ pl["alpha_linear.weight"].T + pl["alpha_linear.bias"]
+    feat = h @ _ste(pl["feature_linear.weight"]).T + pl["feature_linear.bias"]
     feat.retain_grad()
-    zv = torch.cat([feat, xd], -1) @ pl["views_linears.0.weight"].T + pl["views_linears.0.bias"]
+    zv = torch.cat([_ste(feat), xd], -1) @ _ste(pl["views_linears.0.weight"]).T + pl["views_linears.0.bias"]
     zv.retain_grad()
     rgb = torch.relu(zv) @ pl["rgb_linear.weight"].T + pl["rgb_linear.bias"]
     (torch.cat([rgb, sigma], -1) * cot).sum().backward()
@@ -167,7 +177,7 @@ def test_backward_dz_per_layer():
             [("dZ layer %d" % l, 7 + 4 * (D - 1 - l), 4, zs[l].grad) for l in range(D - 1, -1, -1)]:
         got = stash_rows(sb, slot, n, P)
         print("  %-12s cosine %.5f rel-L2 %.3e" % (name, cosine(got, refg), rel_l2(got, refg)))
-        assert cosine(got, refg) >= 0.995 and rel_l2(got, refg) <= 6e-2, name
+        assert cosine(got, refg) >= 0.999 and rel_l2(got, refg) <= 3e-2, name
 
 
 def test_weights_are_repacked_after_an_optimizer_step():
