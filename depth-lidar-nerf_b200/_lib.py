@@ -36,14 +36,14 @@ class ChainProgram(C.Structure):
     _fields_ = [("n_steps", C.c_int32), ("backward", C.c_int32), ("use_viewdirs", C.c_int32),
                 ("out_ch", C.c_int32), ("L_pts", C.c_int32), ("L_dir", C.c_int32), ("stash_slots", C.c_int32),
                 ("mask_slots", C.c_int32), ("pro_head_off", C.c_int32), ("pro_mask_slot", C.c_int32),
-                ("pro_slot", C.c_int32), ("pad_", C.c_int32), ("steps", ChainStep * MAX_STEPS)]
+                ("pro_slot", C.c_int32), ("reload_step", C.c_int32), ("steps", ChainStep * MAX_STEPS)]
 
 
 class ChainArgs(C.Structure):
     _fields_ = [("P", C.c_longlong), ("rays", C.c_void_p), ("ray_stride", C.c_int32), ("vd_col", C.c_int32),
                 ("z", C.c_void_p), ("S", C.c_int32), ("x", C.c_void_p), ("x_ld", C.c_int32),
                 ("wblob", C.c_void_p), ("fblob", C.c_void_p), ("out", C.c_void_p), ("d_out", C.c_void_p),
-                ("stash", C.c_void_p), ("masks", C.c_void_p)]
+                ("stash", C.c_void_p), ("masks", C.c_void_p), ("trace", C.c_void_p)]
 
 
 class WgradItem(C.Structure):

@@ -25,33 +25,35 @@ using namespace dln;
 
 namespace {
 
-constexpr int kThreads = 384;
+constexpr int kThreads = 640;
 constexpr int kEpiWarp0 = 4;
-constexpr int kEpiThreads = 256;
-constexpr int kNumStages = 3;
+constexpr int kEpiThreads = 512;   // 16 epilogue warps: 4 per scheduler, one warpgroup per 64-column slab
+constexpr int kNumStages = 4;      // the ring holds one whole 256x256 layer: it is refilled during the epilogue
 constexpr int kStageBytes = 32768;
 constexpr int kSlab = DLN_SLAB_BYTES;
-constexpr int kNumSlabs = 6;  // 0..3 activations, 4 encoded position / d_raw, 5 encoded direction
-constexpr int kMaxHeadFloats = 1280;
+constexpr int kNumSlabs = 5;       // 0..3 activations, 4 encoded position -> encoded direction (fwd) / d_raw (bwd)
+constexpr int kMaxBiasFloats = 2432;   // 9 x 256 + 128: netdepth <= 8 with view directions, <= 9 without
 
 struct ChainSmall {
   uint64_t w_full[kNumStages], w_empty[kNumStages];
   uint64_t a_ready[kNumSlabs], s_free[kNumSlabs];
   uint64_t acc_full[2];
+  uint64_t grp_full[kNumStages];   // weights of a group of <=4 stages have landed (helper -> MMA thread); rotating,
+                                   // so a parity wait can never alias: at most kNumStages groups are ever in flight
   uint32_t tmem_base;
   uint32_t pad_;
-  float bias[2][256];
-  float heads[kMaxHeadFloats];
-  float part[2][5][128];
+  alignas(16) float bias[kMaxBiasFloats];   // bias vectors of all steps, packed back to back (forward only)
+  float part[4][4][128];                    // per-warpgroup partial head sums: rgb 0..2 (or out 0..3), sigma 3
 };
 
 constexpr size_t kChainSmemBytes = (size_t)kNumSlabs * kSlab + (size_t)kNumStages * kStageBytes + sizeof(ChainSmall) + 1024;
+static_assert(kChainSmemBytes <= 232448, "chain kernel shared memory exceeds the 227 KB per-CTA limit");
 
-__device__ __forceinline__ void named_bar_epi() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_epi() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
 // slabs produced by the tile prologue
 __device__ __forceinline__ uint32_t prologue_mask(const DlnChainProgram& p) {
-  if (!p.backward) return 0x30u;                 // encoded position + direction
+  if (!p.backward) return 0x10u;                 // encoded position
   return p.use_viewdirs ? 0x13u : 0x1Fu;         // d_raw slab + dZ of the first backward layer
 }
 __device__ __forceinline__ uint32_t step_out_mask(const DlnChainStep& s) { return s.n_out == 256 ? 0xFu : 0x3u; }
@@ -84,9 +86,9 @@ __device__ __forceinline__ void encode_row(float x, float y, float z, int L, flo
   }
 }
 
-// write one 64-wide row (bf16) of a slab
-__device__ __forceinline__ void store_row64(uint8_t* slab, int r, const float (&e)[64]) {
-  uint8_t* row = slab + (r >> 3) * 1024 + (r & 7) * 128;
+// write one 64-wide row (bf16) of a slab; `gslab` (optional) is the same slab image in the global stash
+__device__ __forceinline__ void store_row64(uint8_t* slab, uint8_t* gslab, int r, const float (&e)[64]) {
+  const int rowoff = (r >> 3) * 1024 + (r & 7) * 128;
 #pragma unroll
   for (int ch = 0; ch < 8; ++ch) {
     uint4 v;
@@ -94,23 +96,116 @@ __device__ __forceinline__ void store_row64(uint8_t* slab, int r, const float (&
     v.y = pack_bf16(e[8 * ch + 2], e[8 * ch + 3]);
     v.z = pack_bf16(e[8 * ch + 4], e[8 * ch + 5]);
     v.w = pack_bf16(e[8 * ch + 6], e[8 * ch + 7]);
-    *reinterpret_cast<uint4*>(row + ((ch ^ (r & 7)) << 4)) = v;
+    const int off = rowoff + ((ch ^ (r & 7)) << 4);
+    *reinterpret_cast<uint4*>(slab + off) = v;
+    if (gslab) *reinterpret_cast<uint4*>(gslab + off) = v;
   }
 }
 
-// write 32 consecutive columns [cb, cb+32) of row r into the activation slabs
-__device__ __forceinline__ void store_cols32(uint8_t* act, int r, int cb, const float (&f)[32]) {
-  uint8_t* row = act + (cb >> 6) * kSlab + (r >> 3) * 1024 + (r & 7) * 128;
+__device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));   // relu fused into the conversion
+  return r;
+}
+
+// write 32 consecutive columns [cb, cb+32) of row r into the activation slabs (optionally relu'd on the fly) and,
+// when `gslab0` is given, into the same position of the stash image in global memory (slab cb>>6 at gslab0).
+// A thread's four 16-byte chunks fill two complete 32-byte sectors of the 128-byte row.
+template <bool kRelu>
+__device__ __forceinline__ void store_cols32(uint8_t* act, uint8_t* gslab, int r, int cb, const float (&f)[32]) {
+  const int rowoff = (r >> 3) * 1024 + (r & 7) * 128;
+  uint8_t* row = act + (cb >> 6) * kSlab + rowoff;
   const int ch0 = (cb & 63) >> 3;
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     uint4 v;
-    v.x = pack_bf16(f[8 * q + 0], f[8 * q + 1]);
-    v.y = pack_bf16(f[8 * q + 2], f[8 * q + 3]);
-    v.z = pack_bf16(f[8 * q + 4], f[8 * q + 5]);
-    v.w = pack_bf16(f[8 * q + 6], f[8 * q + 7]);
-    *reinterpret_cast<uint4*>(row + (((ch0 + q) ^ (r & 7)) << 4)) = v;
+    if (kRelu) {
+      v.x = pack_bf16_relu(f[8 * q + 0], f[8 * q + 1]), v.y = pack_bf16_relu(f[8 * q + 2], f[8 * q + 3]);
+      v.z = pack_bf16_relu(f[8 * q + 4], f[8 * q + 5]), v.w = pack_bf16_relu(f[8 * q + 6], f[8 * q + 7]);
+    } else {
+      v.x = pack_bf16(f[8 * q + 0], f[8 * q + 1]), v.y = pack_bf16(f[8 * q + 2], f[8 * q + 3]);
+      v.z = pack_bf16(f[8 * q + 4], f[8 * q + 5]), v.w = pack_bf16(f[8 * q + 6], f[8 * q + 7]);
+    }
+    const int off = ((ch0 + q) ^ (r & 7)) << 4;
+    *reinterpret_cast<uint4*>(row + off) = v;
+    if (gslab) *reinterpret_cast<uint4*>(gslab + rowoff + off) = v;
   }
+}
+
+// two fp32 adds in one instruction (FADD2)
+__device__ __forceinline__ void add2(float& a0, float& a1, float b0, float b1) {
+  unsigned long long a, b;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(a) : "l"(b));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(a));
+}
+
+// Column ownership inside a tile: every epilogue thread owns one row and two 32-column chunks, chunk h (0/1) of
+// warpgroup g being columns [128h + 32g, +32), i.e. slab 2h + (g>>1), half g&1.  Two warpgroups therefore
+// finish slabs 0 and 1 (the first K slabs of the next layer) together before anybody starts on slabs 2 and 3,
+// and a 128-wide output keeps all four warpgroups busy.  relu-mask word h of the thread's uint2 covers chunk h.
+//
+// One 32-column chunk of an epilogue: TMEM values -> (+bias | +dsigma*head) -> relu / mask -> bf16 slab.
+template <int EPI>
+__device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], const float* __restrict__ bias,
+                                          const float* __restrict__ hw, int n_out, int nheads, float dsig,
+                                          uint32_t mw_in, uint32_t& mw_out, float (&hacc)[5], uint8_t* slabs,
+                                          uint8_t* gslab, int r, int cb) {
+  constexpr bool kFwd = EPI <= DLN_EPI_RELU_OUT;
+  constexpr bool kRelu = EPI == DLN_EPI_RELU || EPI == DLN_EPI_RELU_SIGMA || EPI == DLN_EPI_RELU_RGB || EPI == DLN_EPI_RELU_OUT;
+  float f[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+  if (kFwd) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 b = *reinterpret_cast<const float4*>(bias + cb + 4 * q);   // smem broadcast
+      add2(f[4 * q], f[4 * q + 1], b.x, b.y);
+      add2(f[4 * q + 2], f[4 * q + 3], b.z, b.w);
+    }
+  }
+  if (EPI == DLN_EPI_BWD_MASK_SIGMA) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 h = __ldg(reinterpret_cast<const float4*>(hw + cb + 4 * q));
+      f[4 * q] += dsig * h.x, f[4 * q + 1] += dsig * h.y, f[4 * q + 2] += dsig * h.z, f[4 * q + 3] += dsig * h.w;
+    }
+  }
+  if (kRelu) {
+    // sign bits -> mask word with one funnel shift per element (bit i <-> column cb+i); relu' := (x >= +0)
+    uint32_t neg = 0;
+#pragma unroll
+    for (int i = 31; i >= 0; --i) neg = __funnelshift_l(__float_as_uint(f[i]), neg, 1);
+    mw_out = ~neg;
+  }
+  if (EPI >= DLN_EPI_BWD_MASK) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) f[i] = (mw_in & (1u << i)) ? f[i] : 0.f;
+  }
+  if (kFwd && nheads > 0) {
+    // heads (alpha / rgb / output_linear) act on the fp32 relu'd activations
+#pragma unroll
+    for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
+#pragma unroll
+    for (int h = 0; h < 5; ++h)
+      if (h < nheads) {
+        float a = 0.f;
+        const float* w = hw + h * n_out + cb;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 w4 = __ldg(reinterpret_cast<const float4*>(w + 4 * q));
+          a += f[4 * q] * w4.x + f[4 * q + 1] * w4.y + f[4 * q + 2] * w4.z + f[4 * q + 3] * w4.w;
+        }
+        hacc[h] += a;
+      }
+  }
+  store_cols32<kRelu>(slabs, gslab, r, cb, f);
+}
+
+// debug timeline: trace[role][gstep][event] = SM clock (CTA 0 only, first 64 steps)
+__device__ __forceinline__ void trace_ev(long long* trace, int role, uint32_t gstep, int ev) {
+  if (trace != nullptr && blockIdx.x == 0 && gstep < 64) trace[(role * 64 + gstep) * 8 + ev] = clock64();
 }
 
 struct ProdTrack {
@@ -120,41 +215,38 @@ struct ProdTrack {
 // ---------------------------------------------------------------------------------------------
 // the chain kernel
 // ---------------------------------------------------------------------------------------------
+template <bool kBwd>
 __global__ void __launch_bounds__(kThreads, 1)
     chain_kernel(const __grid_constant__ DlnChainProgram prog, const __grid_constant__ DlnChainArgs args,
                  const long long n_tiles) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* slabs = smem;                              // 6 x 16 KB
-  uint8_t* wring = smem + kNumSlabs * kSlab;          // 3 x 32 KB
+  uint8_t* slabs = smem;                              // 5 x 16 KB
+  uint8_t* wring = smem + kNumSlabs * kSlab;          // 4 x 32 KB
   ChainSmall* sm = reinterpret_cast<ChainSmall*>(wring + kNumStages * kStageBytes);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool keep = args.stash != nullptr && prog.stash_slots > 0;
+  // forward: the encoded-direction rows replace the encoded position in slab 4 after step `reload_step`
+  const int reload_step = (!kBwd && prog.use_viewdirs) ? prog.reload_step : -1;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kNumStages; ++i) mbar_init(&sm->w_full[i], 1), mbar_init(&sm->w_empty[i], 1);
-    for (int i = 0; i < kNumSlabs; ++i) mbar_init(&sm->a_ready[i], 128), mbar_init(&sm->s_free[i], 1);
+    for (int i = 0; i < kNumSlabs; ++i) mbar_init(&sm->a_ready[i], i < 4 ? 256 : 128), mbar_init(&sm->s_free[i], 1);
     mbar_init(&sm->acc_full[0], 1), mbar_init(&sm->acc_full[1], 1);
+    for (int i = 0; i < kNumStages; ++i) mbar_init(&sm->grp_full[i], 1);
     mbar_fence_init();
   }
   if (warp == 1) {
     tmem_alloc(&sm->tmem_base, 512);
     tmem_relinquish();
   }
-  // head vectors -> smem: [prologue heads (bwd)] then the heads of every step, in step order
-  if (warp >= kEpiWarp0) {
+  if (!kBwd && warp >= kEpiWarp0) {       // all bias vectors -> smem, packed in step order
     const int t = threadIdx.x - kEpiWarp0 * 32;
     int base = 0;
-    if (prog.backward) {
-      const int n = (prog.use_viewdirs ? 3 * 128 : prog.out_ch * 256);
-      for (int i = t; i < n; i += kEpiThreads) sm->heads[i] = args.fblob[prog.pro_head_off + i];
-      base = n;
-    }
     for (int s = 0; s < prog.n_steps; ++s) {
-      const int n = prog.steps[s].n_heads * prog.steps[s].n_out;
-      for (int i = t; i < n; i += kEpiThreads) sm->heads[base + i] = args.fblob[prog.steps[s].head_off + i];
-      base += n;
+      if (t < prog.steps[s].n_out) sm->bias[base + t] = args.fblob[prog.steps[s].bias_off + t];
+      base += prog.steps[s].n_out;
     }
   }
   tc_fence_before();
@@ -183,31 +275,43 @@ __global__ void __launch_bounds__(kThreads, 1)
   } else if (warp == 1) {
     // ===================================================== MMA issuer
     if (lane == 0) {
-      uint32_t stage = 0, phase = 0, gstep = 0;
+      uint32_t stage = 0, gstep = 0, grp = 0;
       uint32_t par = 0;  // parity of the production count per slab
       const uint32_t pmask = prologue_mask(prog);
+      const uint64_t desc_k = umma_desc_sw128(0, 16, 1024);      // K-major SWIZZLE_128B, SBO 1024 B
+      const uint32_t slab_addr0 = smem_u32(slabs), ring_addr0 = smem_u32(wring);
       for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         par ^= pmask;
         for (int s = 0; s < prog.n_steps; ++s, ++gstep) {
           const DlnChainStep& st = prog.steps[s];
           const uint32_t d_tmem = tmem_base + (gstep & 1) * 256;
           const uint32_t idesc = umma_idesc_bf16(128, st.n_out, 0, 0);
+          trace_ev(args.trace, 0, gstep, 0);
           for (int j = 0; j < st.nk; ++j) {
             const int slab = st.kslab[j];
             mbar_wait(&sm->a_ready[slab], ((par >> slab) & 1) ^ 1);   // last production completed
-            mbar_wait(&sm->w_full[stage], phase);
-            tc_fence_after();
-            const uint32_t a_base = smem_u32(slabs + slab * kSlab);
-            const uint32_t b_base = smem_u32(wring + stage * kStageBytes);
-            for (int k = 0; k < st.kcnt[j]; ++k) {
-              umma_bf16(d_tmem, umma_desc_sw128(a_base + k * 32, 16, 1024), umma_desc_sw128(b_base + k * 32, 16, 1024),
-                        idesc, (j | k) != 0);
+            if (j < 5) trace_ev(args.trace, 0, gstep, 1 + j);
+            if ((j & 3) == 0) {            // the helper thread has seen w_full of this group of <=4 stages
+              mbar_wait(&sm->grp_full[grp & (kNumStages - 1)], (grp / kNumStages) & 1);
+              ++grp;
             }
+            if (j == st.nk - 1) trace_ev(args.trace, 0, gstep, 6);
+            tc_fence_after();
+            // descriptors differ only in the 14-bit start-address field: +2 (= 32 B) per K=16 step
+            const uint64_t ad = desc_k | (uint64_t)((slab_addr0 + slab * kSlab) >> 4);
+            const uint64_t bd = desc_k | (uint64_t)((ring_addr0 + stage * kStageBytes) >> 4);
+            const int kc = st.kcnt[j];
+            umma_bf16(d_tmem, ad, bd, idesc, j != 0);
+            if (kc > 1) umma_bf16(d_tmem, ad + 2, bd + 2, idesc, 1);
+            if (kc > 2) umma_bf16(d_tmem, ad + 4, bd + 4, idesc, 1);
+            if (kc > 3) umma_bf16(d_tmem, ad + 6, bd + 6, idesc, 1);
             umma_commit(&sm->w_empty[stage]);
-            if (++stage == kNumStages) stage = 0, phase ^= 1;
+            if (++stage == kNumStages) stage = 0;
           }
           umma_commit(&sm->acc_full[gstep & 1]);
+          trace_ev(args.trace, 0, gstep, 7);
           par ^= step_out_mask(st);
+          if (s == reload_step) par ^= 0x10u;
         }
         // Parity waits are only sound while a waiter is never two phases ahead of the barrier.  No MMA
         // consumes the slabs the LAST step produces (they only go to the stash), so observe them here
@@ -218,42 +322,71 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
     }
   } else if (warp == 2) {
-    // ===================================================== stash writer (training only)
+    // ===================================================== stash writer (training only): bulk smem -> global copies
+    // of every produced slab, two in flight (slab i is issued before slab i-1 is retired)
     if (lane == 0 && keep) {
       uint32_t par = 0;
       const uint32_t pmask = prologue_mask(prog);
       uint8_t* stash = reinterpret_cast<uint8_t*>(args.stash);
+      int pending = -1;               // slab whose store has been issued but whose smem read is not yet retired
+      auto retire = [&](int keep_newer) {
+        if (pending >= 0) {
+          if (keep_newer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          else bulk_wait_read0();
+          mbar_arrive(&sm->s_free[pending]);
+          pending = -1;
+        }
+      };
       for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         uint8_t* tbase = stash + (size_t)tile * prog.stash_slots * kSlab;
         auto handle = [&](int slab, int slot) {
           mbar_wait(&sm->a_ready[slab], (par >> slab) & 1);
+          par ^= 1u << slab;
           if (slot >= 0) {
             bulk_s2g(tbase + (size_t)slot * kSlab, slabs + slab * kSlab, kSlab);
             bulk_commit();
-            bulk_wait_read0();
+            const int prev = pending;
+            pending = prev;           // retire the previous store while this one is in flight
+            retire(1);
+            pending = slab;
+          } else {
+            retire(0);
+            mbar_arrive(&sm->s_free[slab]);
           }
-          mbar_arrive(&sm->s_free[slab]);
-          par ^= 1u << slab;
         };
-        // prologue productions: aux slabs go to slots 0 (and 1), activation slabs to pro_slot + slab
         for (int slab = 0; slab < kNumSlabs; ++slab)
-          if ((pmask >> slab) & 1) handle(slab, slab >= 4 ? slab - 4 : prog.pro_slot + slab);
+          if ((pmask >> slab) & 1) handle(slab, slab == 4 ? 0 : prog.pro_slot + slab);
         for (int s = 0; s < prog.n_steps; ++s) {
           const DlnChainStep& st = prog.steps[s];
           const uint32_t om = step_out_mask(st);
-          const int order[4] = {0, 2, 1, 3};
-          for (int i = 0; i < 4; ++i) {
-            const int slab = order[i];
+          for (int slab = 0; slab < 4; ++slab)
             if ((om >> slab) & 1) handle(slab, st.stash_slot >= 0 ? st.stash_slot + slab : -1);
-          }
+          if (s == reload_step) handle(4, 1);        // encoded direction -> slot 1
+          retire(0);                                 // nothing stays pending across a step boundary
         }
       }
       bulk_wait_all0();
     }
+  } else if (warp == 3) {
+    // ===================================================== weight-arrival helper: takes the per-stage
+    // mbarrier latency off the MMA thread's critical path (one grp_full wait per <=4 stages instead)
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, grp = 0;
+      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int s = 0; s < prog.n_steps; ++s) {
+          const int nk = prog.steps[s].nk;
+          for (int j = 0; j < nk; ++j) {
+            mbar_wait(&sm->w_full[stage], phase);
+            if (++stage == kNumStages) stage = 0, phase ^= 1;
+            if ((j & 3) == 3 || j == nk - 1) mbar_arrive(&sm->grp_full[grp++ & (kNumStages - 1)]);
+          }
+        }
+      }
+    }
   } else if (warp >= kEpiWarp0) {
     // ===================================================== prologue + epilogue warps
-    const int et = threadIdx.x - kEpiWarp0 * 32;   // 0..255
-    const int g = et >> 7;                         // warpgroup: column half
+    const int et = threadIdx.x - kEpiWarp0 * 32;   // 0..511
+    const int g = et >> 7;                         // warpgroup 0..3: owns slab g of the output
     const int r = ((warp & 3) << 5) | lane;        // tile row == TMEM lane
     const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
     ProdTrack pt;
@@ -267,51 +400,48 @@ __global__ void __launch_bounds__(kThreads, 1)
       tc_fence_before();
       mbar_arrive(&sm->a_ready[slab]);
     };
-    // offsets of the head vectors in smem
-    int head_base[DLN_MAX_STEPS];
-    {
-      int base = prog.backward ? (prog.use_viewdirs ? 3 * 128 : prog.out_ch * 256) : 0;
-      for (int s = 0; s < DLN_MAX_STEPS; ++s) {
-        head_base[s] = base;
-        if (s < prog.n_steps) base += prog.steps[s].n_heads * prog.steps[s].n_out;
+    // one encoded row (position g==0 / direction g==1) for tile row r, fused (rays, z) or pre-encoded (x) input
+    auto encoded_row = [&](long long p, bool valid, int which, float (&e)[64]) {
+      if (args.x == nullptr) {
+        float vx = 0.f, vy = 0.f, vz = 0.f;
+        if (valid) {
+          const long long ray = p / args.S;
+          const float* rp = args.rays + (size_t)ray * args.ray_stride;
+          if (which == 0) {
+            const float zz = args.z[p];
+            vx = rp[0] + rp[3] * zz, vy = rp[1] + rp[4] * zz, vz = rp[2] + rp[5] * zz;
+          } else {
+            vx = rp[args.vd_col], vy = rp[args.vd_col + 1], vz = rp[args.vd_col + 2];
+          }
+        }
+        encode_row(vx, vy, vz, which == 0 ? prog.L_pts : prog.L_dir, e);
+        if (!valid) {
+#pragma unroll
+          for (int i = 0; i < 64; ++i) e[i] = 0.f;
+        }
+      } else {
+        const int n_pts = 3 + 6 * prog.L_pts, n_dir = 3 + 6 * prog.L_dir;
+        const int n = which == 0 ? n_pts : n_dir;
+        const float* xp = args.x + (size_t)(valid ? p : 0) * args.x_ld + (which == 0 ? 0 : n_pts);
+#pragma unroll
+        for (int i = 0; i < 64; ++i) e[i] = (valid && i < n) ? xp[i] : 0.f;
       }
-    }
+    };
 
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const long long p = tile * DLN_TILE_ROWS + r;
       const bool valid = p < args.P;
       float dsig = 0.f;
+      auto gslot = [&](int) -> uint8_t* { return nullptr; };   // the stash goes through the bulk-copy engine (warp 2)
       // ------------------------------------------------------------------ prologue
-      if (!prog.backward) {
-        float e[64];
-        const int slab = 4 + g;
-        if (args.x == nullptr) {
-          float vx = 0.f, vy = 0.f, vz = 0.f;
-          if (valid) {
-            const long long ray = p / args.S;
-            const float* rp = args.rays + (size_t)ray * args.ray_stride;
-            if (g == 0) {
-              const float zz = args.z[p];
-              vx = rp[0] + rp[3] * zz, vy = rp[1] + rp[4] * zz, vz = rp[2] + rp[5] * zz;
-            } else if (prog.use_viewdirs) {
-              vx = rp[args.vd_col], vy = rp[args.vd_col + 1], vz = rp[args.vd_col + 2];
-            }
-          }
-          encode_row(vx, vy, vz, g == 0 ? prog.L_pts : prog.L_dir, e);
-          if (!valid || (g == 1 && !prog.use_viewdirs)) {
-#pragma unroll
-            for (int i = 0; i < 64; ++i) e[i] = 0.f;
-          }
-        } else {
-          const int n_pts = 3 + 6 * prog.L_pts, n_dir = prog.use_viewdirs ? 3 + 6 * prog.L_dir : 0;
-          const int n = g == 0 ? n_pts : n_dir;
-          const float* xp = args.x + (size_t)(valid ? p : 0) * args.x_ld + (g == 0 ? 0 : n_pts);
-#pragma unroll
-          for (int i = 0; i < 64; ++i) e[i] = (valid && i < n) ? xp[i] : 0.f;
+      if (!kBwd) {
+        if (g == 0) {
+          float e[64];
+          encoded_row(p, valid, 0, e);
+          begin_produce(4);
+          store_row64(slabs + 4 * kSlab, gslot(0), r, e);
+          end_produce(4);
         }
-        begin_produce(slab);
-        store_row64(slabs + slab * kSlab, r, e);
-        end_produce(slab);
       } else {
         // d raw row -> dZ of the first backward layer (through rgb_linear / output_linear) + d_raw slab
         float dr[5];
@@ -320,115 +450,153 @@ __global__ void __launch_bounds__(kThreads, 1)
         dsig = dr[3];
         const int nh = prog.use_viewdirs ? 3 : prog.out_ch;
         const int width = prog.use_viewdirs ? 128 : 256;
-        const int ncols = width / 2, col0 = g * ncols;
-        const uint4 mw = reinterpret_cast<const uint4*>(args.masks)[(((size_t)prog.pro_mask_slot * n_tiles + tile) * 2 + g) * 128 + r];
-        const uint32_t mwords[4] = {mw.x, mw.y, mw.z, mw.w};
-        for (int c = 0; c < ncols / 32; ++c) {
-          const int cb = col0 + 32 * c;
-          if ((cb & 63) == 0) begin_produce(cb >> 6);
-          float f[32];
+        const float* ph = args.fblob + prog.pro_head_off;
+        {
+          const uint2 mw = reinterpret_cast<const uint2*>(args.masks)[(((size_t)prog.pro_mask_slot * n_tiles + tile) * 4 + g) * 128 + r];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float v = 0.f;
+          for (int h = 0; h < 2; ++h) {
+            if (128 * h < width) {
+              const int cb = 128 * h + 32 * g;
+              const uint32_t mk = h ? mw.y : mw.x;
+              begin_produce(cb >> 6);
+              float f[32];
 #pragma unroll
-            for (int j = 0; j < 5; ++j)
-              if (j < nh) v += dr[j] * sm->heads[j * width + cb + i];
-            f[i] = ((mwords[c] >> i) & 1u) ? v : 0.f;
+              for (int i = 0; i < 32; ++i) f[i] = 0.f;
+#pragma unroll
+              for (int j = 0; j < 5; ++j)
+                if (j < nh) {
+#pragma unroll
+                  for (int q = 0; q < 8; ++q) {
+                    const float4 w4 = __ldg(reinterpret_cast<const float4*>(ph + j * width + cb + 4 * q));
+                    f[4 * q] += dr[j] * w4.x, f[4 * q + 1] += dr[j] * w4.y, f[4 * q + 2] += dr[j] * w4.z, f[4 * q + 3] += dr[j] * w4.w;
+                  }
+                }
+#pragma unroll
+              for (int i = 0; i < 32; ++i) f[i] = (mk & (1u << i)) ? f[i] : 0.f;
+              store_cols32<false>(slabs, gslot(prog.pro_slot + (cb >> 6)), r, cb, f);
+              end_produce(cb >> 6);
+            }
           }
-          store_cols32(slabs, r, cb, f);
-          if ((cb & 63) == 32) end_produce(cb >> 6);
         }
-        if (g == 0) {
+        if (g == (prog.use_viewdirs ? 2 : 0)) {
           float e[64];
 #pragma unroll
           for (int i = 0; i < 64; ++i) e[i] = 0.f;
 #pragma unroll
           for (int j = 0; j < 5; ++j) e[j] = dr[j];
           begin_produce(4);
-          store_row64(slabs + 4 * kSlab, r, e);
+          store_row64(slabs + 4 * kSlab, gslot(0), r, e);
           end_produce(4);
         }
       }
       pt.par ^= pmask, pt.any |= pmask;
 
       // ------------------------------------------------------------------ layer epilogues
+      int bias_base = 0;
       for (int s = 0; s < prog.n_steps; ++s, ++gstep) {
         const DlnChainStep& st = prog.steps[s];
         const int epi = st.epi;
-        const bool has_bias = epi <= DLN_EPI_RELU_OUT;
-        float* bias = sm->bias[gstep & 1];
-        if (et < st.n_out) bias[et] = has_bias ? args.fblob[st.bias_off + et] : 0.f;
-        uint4 mw = make_uint4(0, 0, 0, 0);
-        const size_t mask_idx = (((size_t)(st.mask_slot < 0 ? 0 : st.mask_slot) * n_tiles + tile) * 2 + g) * 128 + r;
-        if (epi >= DLN_EPI_BWD_MASK && st.mask_slot >= 0) mw = reinterpret_cast<const uint4*>(args.masks)[mask_idx];
-        named_bar_epi();
+        const float* bias = sm->bias + bias_base;
+        bias_base += st.n_out;
+        uint2 mw = make_uint2(0, 0);
+        const size_t mask_idx = (((size_t)(st.mask_slot < 0 ? 0 : st.mask_slot) * n_tiles + tile) * 4 + g) * 128 + r;
+        if (epi >= DLN_EPI_BWD_MASK && st.mask_slot >= 0) mw = reinterpret_cast<const uint2*>(args.masks)[mask_idx];
+        const int trole = (et == 0) ? 1 : (et == 384 ? 2 : -1);
+        if (trole > 0) trace_ev(args.trace, trole, gstep, 0);
         mbar_wait(&sm->acc_full[gstep & 1], (gstep >> 1) & 1);
         tc_fence_after();
+        if (trole > 0) trace_ev(args.trace, trole, gstep, 1);
 
-        const int ncols = st.n_out / 2, col0 = g * ncols;
         const uint32_t t_acc = tmem_base + (gstep & 1) * 256 + lane_addr;
         const bool relu = (epi == DLN_EPI_RELU || epi == DLN_EPI_RELU_SIGMA || epi == DLN_EPI_RELU_RGB || epi == DLN_EPI_RELU_OUT);
         const int nheads = (epi <= DLN_EPI_RELU_OUT) ? st.n_heads : 0;
-        const float* hw = sm->heads + head_base[s];
+        const float* hw = args.fblob + st.head_off;
         float hacc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-        uint32_t mwords_in[4] = {mw.x, mw.y, mw.z, mw.w};
-        uint32_t mwords_out[4] = {0, 0, 0, 0};
-        for (int c = 0; c < ncols / 32; ++c) {
-          const int cb = col0 + 32 * c;
-          uint32_t v[32];
-          tmem_ld32(t_acc + cb, v);
-          tmem_ld_wait();
-          if ((cb & 63) == 0) begin_produce(cb >> 6);
-          float f[32];
-          uint32_t mo = 0;
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float x = __uint_as_float(v[i]) + bias[cb + i];
-            if (epi == DLN_EPI_BWD_MASK_SIGMA) x += dsig * hw[cb + i];
-            if (relu) {
-              mo |= (x > 0.f ? 1u : 0u) << i;
-              x = fmaxf(x, 0.f);
+        uint32_t mo0 = 0, mo1 = 0;
+        {
+          auto run = [&](auto tag, const uint32_t(&v)[32], uint32_t mi, uint32_t& mo, int cb) {
+            constexpr int E = decltype(tag)::value;
+            epi_chunk<E>(v, bias, hw, st.n_out, nheads, dsig, mi, mo, hacc, slabs,
+                         gslot(st.stash_slot >= 0 ? st.stash_slot + (cb >> 6) : -1), r, cb);
+          };
+          auto dispatch = [&](const uint32_t(&v)[32], uint32_t mi, uint32_t& mo, int cb) {
+            if (!kBwd) {
+              if (epi == DLN_EPI_LINEAR) run(std::integral_constant<int, DLN_EPI_LINEAR>{}, v, mi, mo, cb);
+              else run(std::integral_constant<int, DLN_EPI_RELU_OUT>{}, v, mi, mo, cb);     // relu (+ heads when nheads > 0)
+            } else {
+              if (epi == DLN_EPI_BWD_COPY) run(std::integral_constant<int, DLN_EPI_BWD_COPY>{}, v, mi, mo, cb);
+              else if (epi == DLN_EPI_BWD_MASK) run(std::integral_constant<int, DLN_EPI_BWD_MASK>{}, v, mi, mo, cb);
+              else run(std::integral_constant<int, DLN_EPI_BWD_MASK_SIGMA>{}, v, mi, mo, cb);
             }
-            if (epi >= DLN_EPI_BWD_MASK) x = ((mwords_in[c] >> i) & 1u) ? x : 0.f;
-            f[i] = x;
+          };
+          uint32_t v[32];
+          const int cb0 = 32 * g;                    // chunk 0: slab g>>1
+          tmem_ld32(t_acc + cb0, v);
+          tmem_ld_wait();
+          if (trole > 0) trace_ev(args.trace, trole, gstep, 2);
+          begin_produce(cb0 >> 6);
+          if (trole > 0) trace_ev(args.trace, trole, gstep, 3);
+          dispatch(v, mw.x, mo0, cb0);
+          end_produce(cb0 >> 6);
+          if (trole > 0) trace_ev(args.trace, trole, gstep, 4);
+          if (st.n_out == 256) {                     // chunk 1: slab 2 + (g>>1)
+            const int cb1 = 128 + 32 * g;
+            tmem_ld32(t_acc + cb1, v);
+            tmem_ld_wait();
+            begin_produce(cb1 >> 6);
+            dispatch(v, mw.y, mo1, cb1);
+            if (trole > 0) trace_ev(args.trace, trole, gstep, 5);
+            end_produce(cb1 >> 6);
           }
-          mwords_out[c] = mo;
-          if (nheads > 0) {
-#pragma unroll
-            for (int h = 0; h < 5; ++h)
-              if (h < nheads) {
-                float a = 0.f;
-#pragma unroll
-                for (int i = 0; i < 32; ++i) a += f[i] * hw[h * st.n_out + cb + i];
-                hacc[h] += a;
-              }
-          }
-          store_cols32(slabs, r, cb, f);
-          if ((cb & 63) == 32) end_produce(cb >> 6);
+          if (trole > 0) trace_ev(args.trace, trole, gstep, 6);
+          if (relu && st.mask_slot >= 0 && args.masks != nullptr)
+            reinterpret_cast<uint2*>(args.masks)[mask_idx] = make_uint2(mo0, mo1);
         }
-        if (relu && st.mask_slot >= 0 && args.masks != nullptr)
-          reinterpret_cast<uint4*>(args.masks)[mask_idx] = make_uint4(mwords_out[0], mwords_out[1], mwords_out[2], mwords_out[3]);
         pt.par ^= step_out_mask(st), pt.any |= step_out_mask(st);
 
+        if (s == reload_step) {
+          // every MMA that reads the encoded position has completed (acc_full of this step): warpgroup 1
+          // overwrites slab 4 with the encoded view direction for the views layer
+          if (g == 1) {
+            float e[64];
+            encoded_row(p, valid, 1, e);
+            begin_produce(4);
+            store_row64(slabs + 4 * kSlab, gslot(1), r, e);
+            end_produce(4);
+          }
+          pt.par ^= 0x10u;
+        }
+
         if (epi == DLN_EPI_RELU_SIGMA) {
-          sm->part[g][4][r] = hacc[0] + (g == 0 ? args.fblob[st.head_bias_off] : 0.f);
-        } else if (epi == DLN_EPI_RELU_RGB || epi == DLN_EPI_RELU_OUT) {
+          sm->part[g][3][r] = hacc[0] + (g == 0 ? args.fblob[st.head_bias_off] : 0.f);
+        } else if (epi == DLN_EPI_RELU_RGB) {
 #pragma unroll
-          for (int h = 0; h < 5; ++h)
-            if (h < nheads) sm->part[g][h][r] = hacc[h];
+          for (int h = 0; h < 3; ++h) sm->part[g][h][r] = hacc[h];       // idle warpgroups contribute 0
           named_bar_epi();
           if (g == 0 && valid) {
-            float o[5];
+            float o[4];
 #pragma unroll
-            for (int h = 0; h < 5; ++h)
-              o[h] = (h < nheads) ? sm->part[0][h][r] + sm->part[1][h][r] + args.fblob[st.head_bias_off + h] : 0.f;
-            if (epi == DLN_EPI_RELU_RGB) o[3] = sm->part[0][4][r] + sm->part[1][4][r];
-            float* op = args.out + (size_t)p * prog.out_ch;
-            if (prog.out_ch == 4) {
-              *reinterpret_cast<float4*>(op) = make_float4(o[0], o[1], o[2], o[3]);
-            } else {
-              for (int j = 0; j < prog.out_ch; ++j) op[j] = o[j];
+            for (int h = 0; h < 3; ++h)
+              o[h] = (sm->part[0][h][r] + sm->part[1][h][r]) + (sm->part[2][h][r] + sm->part[3][h][r]) +
+                     args.fblob[st.head_bias_off + h];
+            o[3] = (sm->part[0][3][r] + sm->part[1][3][r]) + (sm->part[2][3][r] + sm->part[3][3][r]);
+            *reinterpret_cast<float4*>(args.out + (size_t)p * 4) = make_float4(o[0], o[1], o[2], o[3]);
+          }
+          named_bar_epi();      // part[] may be rewritten by the next tile only after everybody has read it
+        } else if (epi == DLN_EPI_RELU_OUT) {
+          // output_linear: up to 5 heads through the 4-deep partial-sum buffer, in two rounds
+          for (int h0 = 0; h0 < nheads; h0 += 4) {
+#pragma unroll
+            for (int h = 0; h < 4; ++h)
+              if (h0 + h < nheads) sm->part[g][h][r] = (h0 == 0) ? hacc[h] : hacc[4];
+            named_bar_epi();
+            if (g == 0 && valid) {
+              for (int h = 0; h < 4 && h0 + h < nheads; ++h)
+                args.out[(size_t)p * prog.out_ch + h0 + h] =
+                    (sm->part[0][h][r] + sm->part[1][h][r]) + (sm->part[2][h][r] + sm->part[3][h][r]) +
+                    args.fblob[st.head_bias_off + h0 + h];
             }
+            named_bar_epi();
           }
         }
       }
@@ -514,17 +682,18 @@ __global__ void __launch_bounds__(kWgThreads, 1)
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       const uint32_t idesc = umma_idesc_bf16(128, N, 1, 1);
+      const uint64_t desc_mn = umma_desc_sw128(0, kHalfSlab, 1024);   // MN-major: LBO = slab pitch, SBO = 8-row group
+      const uint32_t smem0 = smem_u32(smem);
       for (long long q = 0; q < n_stages; ++q) {
         mbar_wait(&sm->full[stage], phase);
         tc_fence_after();
-        const uint32_t abuf = smem_u32(smem + stage * kWgStageBytes);
-        const uint32_t bbuf = abuf + 4 * kHalfSlab;
-        for (int kk = 0; kk < 4; ++kk) {          // 16 points per MMA
-          const uint64_t bdesc = umma_desc_sw128(bbuf + kk * 2048, kHalfSlab, 1024);
-          for (int h = 0; h < nh; ++h) {
-            const uint64_t adesc = umma_desc_sw128(abuf + h * 2 * kHalfSlab + kk * 2048, kHalfSlab, 1024);
-            umma_bf16(tmem_base + h * 256, adesc, bdesc, idesc, (q | kk) != 0);
-          }
+        const uint32_t abuf = smem0 + stage * kWgStageBytes;
+        const uint64_t ad = desc_mn | (uint64_t)(abuf >> 4);
+        const uint64_t bd = desc_mn | (uint64_t)((abuf + 4 * kHalfSlab) >> 4);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {          // 16 points (2048 B = 128 descriptor units) per MMA
+          umma_bf16(tmem_base, ad + 128 * kk, bd + 128 * kk, idesc, (q | kk) != 0);
+          if (nh == 2) umma_bf16(tmem_base + 256, ad + 128 * kk + (2 * kHalfSlab >> 4), bd + 128 * kk, idesc, (q | kk) != 0);
         }
         umma_commit(&sm->empty[stage]);
         if (++stage == kWgStages) stage = 0, phase ^= 1;
@@ -625,16 +794,17 @@ int dln_mlp_chain(const DlnChainProgram* prog, const DlnChainArgs* args, int num
   DLN_CHECK_ARG(args->P >= 0);
   if (args->P == 0) return DLN_OK;
   DLN_CHECK_ARG(args->wblob && args->fblob);
-  int head_floats = prog->backward ? (prog->use_viewdirs ? 3 * 128 : prog->out_ch * 256) : 0;
+  int bias_floats = 0;
   for (int s = 0; s < prog->n_steps; ++s) {
     const DlnChainStep& st = prog->steps[s];
     DLN_CHECK_ARG(st.n_out == 256 || st.n_out == 128);
     DLN_CHECK_ARG(st.nk >= 1 && st.nk <= DLN_MAX_KSLABS && st.n_heads <= 5);
     for (int j = 0; j < st.nk; ++j) DLN_CHECK_ARG(st.kslab[j] < kNumSlabs && st.kcnt[j] >= 1 && st.kcnt[j] <= 4);
     DLN_CHECK_ARG((st.w_off & 1023u) == 0);
-    head_floats += st.n_heads * st.n_out;
+    bias_floats += st.n_out;
   }
-  DLN_CHECK_ARG(head_floats <= kMaxHeadFloats);
+  DLN_CHECK_ARG(bias_floats <= kMaxBiasFloats);
+  DLN_CHECK_ARG(prog->reload_step < prog->n_steps);
   if (prog->backward) {
     DLN_CHECK_ARG(args->d_out && args->masks);
   } else {
@@ -646,12 +816,17 @@ int dln_mlp_chain(const DlnChainProgram* prog, const DlnChainArgs* args, int num
   const long long n_tiles = (args->P + DLN_TILE_ROWS - 1) / DLN_TILE_ROWS;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemBytes);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemBytes);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
   const unsigned grid = (unsigned)(n_tiles < num_sms ? n_tiles : num_sms);
-  chain_kernel<<<grid, kThreads, kChainSmemBytes, (cudaStream_t)stream>>>(*prog, *args, n_tiles);
+  if (prog->backward)
+    chain_kernel<true><<<grid, kThreads, kChainSmemBytes, (cudaStream_t)stream>>>(*prog, *args, n_tiles);
+  else
+    chain_kernel<false><<<grid, kThreads, kChainSmemBytes, (cudaStream_t)stream>>>(*prog, *args, n_tiles);
   return dln_launch_status();
 }
 

@@ -33,8 +33,9 @@ class NetShape:
     def validate(self) -> None:
         if self.W != 256:
             raise NotImplementedError("the sm_100a MLP kernels are built for netwidth W=256 (got %d)" % self.W)
-        if self.D < 1 or self.D + 2 > L.MAX_STEPS:
-            raise NotImplementedError("netdepth must be in [1, %d]" % (L.MAX_STEPS - 2))
+        if self.D < 1 or self.D > (8 if self.use_viewdirs else 9):
+            raise NotImplementedError("netdepth must be in [1, %d] (bias staging in shared memory)"
+                                      % (8 if self.use_viewdirs else 9))
         if self.input_ch > 64 or self.input_ch_views > 64:
             raise NotImplementedError("encoded inputs wider than 64 channels are not supported")
         if (self.input_ch - 3) % 6 or (self.input_ch_views - 3) % 6:
@@ -172,7 +173,7 @@ def build_plan(shape: NetShape) -> Plan:
         steps += 1
         st = fwd.steps[steps]
         st.w_off, st.bias_off, st.n_out, st.epi = blob, O["views_linears.0.bias"], 128, L.EPI_RELU_RGB
-        _set_k(st, [0, 1, 2, 3, 5], [4, 4, 4, 4, kc_dir])
+        _set_k(st, [0, 1, 2, 3, 4], [4, 4, 4, 4, kc_dir])     # slab 4 holds the encoded direction by now
         ldv = W + shape.input_ch_views
         for j in range(4):
             add_job(pl.fwd_jobs, "views_linears.0.weight", ldv, 0, 64 * j, 128, 64, 0, 128, blob)
@@ -187,6 +188,8 @@ def build_plan(shape: NetShape) -> Plan:
     else:
         pl.fwd_slots = feat_slot
         pl.mask_slots = D
+    # slab 4 carries the encoded position until the last pts layer that reads it, then the encoded direction
+    fwd.reload_step = max([0] + [i for i in range(D) if (i - 1) in shape.skips]) if shape.use_viewdirs else -1
     fwd.n_steps, fwd.stash_slots, fwd.mask_slots = steps, pl.fwd_slots, pl.mask_slots
     pl.fwd, pl.fwd_blob_bytes = fwd, blob
 
@@ -197,6 +200,7 @@ def build_plan(shape: NetShape) -> Plan:
     blob = 0
     steps = 0
     bwd.pro_slot = 1
+    bwd.reload_step = -1
     if shape.use_viewdirs:
         bwd.pro_head_off, bwd.pro_mask_slot = O["rgb_linear.weight"], D
         dzv_slot, dzf_slot = 1, 3

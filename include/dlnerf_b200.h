@@ -110,7 +110,7 @@ typedef struct {
   uint16_t n_out;     /* 256 or 128                                                                    */
   uint8_t nk;         /* number of K slab entries                                                      */
   uint8_t epi;        /* DLN_EPI_*                                                                     */
-  uint8_t kslab[DLN_MAX_KSLABS]; /* 0..3 activation slabs, 4 encoded position, 5 encoded direction    */
+  uint8_t kslab[DLN_MAX_KSLABS]; /* 0..3 activation slabs, 4 encoded position / direction / d_raw     */
   uint8_t kcnt[DLN_MAX_KSLABS];  /* K=16 MMA steps taken from that slab (4 = all 64 columns)           */
   int16_t stash_slot; /* first stash slot of the output slabs, -1 = not kept                           */
   int16_t mask_slot;  /* relu bit-mask slot written (fwd) / read (bwd), -1 = none                      */
@@ -130,7 +130,7 @@ typedef struct {
   int32_t pro_head_off;    /* float offset of W_rgb[3][128] (or W_out[out_ch][256]) in the fp32 blob    */
   int32_t pro_mask_slot;   /* relu mask of that layer's forward output                                  */
   int32_t pro_slot;        /* first stash slot of the prologue's activation slabs                       */
-  int32_t pad_;
+  int32_t reload_step;     /* forward: after this step slab 4 is rewritten with the encoded direction   */
   DlnChainStep steps[DLN_MAX_STEPS];
 } DlnChainProgram;
 
@@ -150,7 +150,8 @@ typedef struct {
   float* out;              /* fwd: raw[P,out_ch]            bwd: unused                                */
   const float* d_out;      /* bwd: d raw[P,out_ch]                                                     */
   void* stash;             /* [tiles][stash_slots][DLN_SLAB_BYTES] or null                             */
-  uint32_t* masks;         /* [mask_slots][tiles][2][128][4] relu bit masks                            */
+  uint32_t* masks;         /* [mask_slots][tiles][4][128][2] relu bit masks                            */
+  long long* trace;        /* optional debug timeline [4 roles][64 steps][8 events] of SM clocks, CTA 0 only */
 } DlnChainArgs;
 
 /* Fused MLP chain (forward or dgrad).  prog_host / args_host are HOST structs passed by value to the

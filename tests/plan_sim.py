@@ -48,10 +48,9 @@ def run_forward(plan, flat, enc_pts, enc_dir):
     slot -> [P,64], masks dict slot -> bool [P, n_out])."""
     prog = plan.fwd
     P = enc_pts.shape[0]
-    slabs = [np.zeros((P, 64)) for _ in range(6)]
+    slabs = [np.zeros((P, 64)) for _ in range(5)]
     slabs[4][:, :enc_pts.shape[1]] = enc_pts
-    slabs[5][:, :enc_dir.shape[1]] = enc_dir
-    stash = {0: slabs[4].copy(), 1: slabs[5].copy()}
+    stash = {0: slabs[4].copy()}
     masks = {}
     stages = _stages_by_offset(flat, plan.fwd_jobs)
     sigma = None
@@ -76,6 +75,10 @@ def run_forward(plan, flat, enc_pts, enc_dir):
             slabs[i] = x[:, 64 * i: 64 * i + 64].copy()
             if st.stash_slot >= 0:
                 stash[st.stash_slot + i] = slabs[i].copy()
+        if s == prog.reload_step:          # slab 4: encoded position -> encoded direction
+            slabs[4] = np.zeros((P, 64))
+            slabs[4][:, :enc_dir.shape[1]] = enc_dir
+            stash[1] = slabs[4].copy()
         if st.epi == L.EPI_RELU_SIGMA:
             sigma = heads[:, 0]
         elif st.epi == L.EPI_RELU_RGB:
@@ -89,7 +92,7 @@ def run_backward(plan, flat, d_out, masks):
     """Returns the backward stash dict slot -> [P,64]."""
     prog = plan.bwd
     P = d_out.shape[0]
-    slabs = [np.zeros((P, 64)) for _ in range(6)]
+    slabs = [np.zeros((P, 64)) for _ in range(5)]
     stash = {}
     nh = 3 if prog.use_viewdirs else prog.out_ch
     width = 128 if prog.use_viewdirs else 256

@@ -123,7 +123,7 @@ def test_plan_reproduces_oracle_forward_and_gradients(D, vd):
         else:
             np.testing.assert_allclose(got, ref.numpy(), atol=1e-9, err_msg=name)
     # slot bookkeeping: every slot below the advertised count is produced
-    assert set(stash_f) == set(range(plan.fwd_slots))
+    assert set(stash_f) == set(range(plan.fwd_slots)) - (set() if vd else {1})   # slot 1 = encoded direction
     assert set(stash_b) == set(range(plan.bwd_slots))
     assert plan.fwd.n_steps <= dn._lib.MAX_STEPS and plan.bwd.n_steps <= dn._lib.MAX_STEPS
 

@@ -1,0 +1,35 @@
+"""Print the in-kernel timeline of CTA 0 for the forward chain (debug)."""
+import sys, os, ctypes as C
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import dlnerf_b200 as dn
+L = dn._lib
+DEV = "cuda"
+N, S, D = 4096, 128, 8
+keep = int(os.environ.get("KEEP", "1"))
+net = dn.NeRF(D=D, W=256, input_ch=63, input_ch_views=27, use_viewdirs=True).to(DEV)
+rb = torch.randn(N, 11, device=DEV); rb[:, 6] = 0; rb[:, 7] = 1
+z = torch.sort(torch.rand(N, S, device=DEV), -1)[0]
+P = N * S
+st = net._state(); net._pack(st); pl = net._plan
+n_tiles = P // 128
+out = torch.empty(P, 4, device=DEV)
+stash = torch.empty(n_tiles * pl.fwd_slots * L.SLAB_BYTES, device=DEV, dtype=torch.uint8)
+masks = torch.empty(pl.mask_slots * n_tiles * 1024, device=DEV, dtype=torch.int32)
+trace = torch.zeros(4 * 64 * 8, device=DEV, dtype=torch.int64)
+args = L.ChainArgs(); args.P = P
+args.rays, args.ray_stride, args.vd_col = rb.data_ptr(), 11, 8
+args.z, args.S = z.data_ptr(), S
+args.wblob, args.fblob, args.out = st["wf"].data_ptr(), st["flat"].data_ptr(), out.data_ptr()
+if keep:
+    args.stash, args.masks = stash.data_ptr(), masks.data_ptr()
+for it in range(3):
+    args.trace = trace.data_ptr() if it == 2 else None
+    L.check(L.lib().dln_mlp_chain(C.byref(pl.fwd), C.byref(args), st["sms"], dn.ops._stream()), "fwd")
+torch.cuda.synchronize()
+t = trace.cpu().view(4, 64, 8)
+t0 = int(t[0, 0, 0])
+rel = lambda x: int(x) - t0 if int(x) else -1
+print("keep=%d; per step (gstep): MMA[start, a_ready j0..j4, w_full(last), commit]  EPI_WG0[wait0, acc_full, ld, begin, chunk0, chunk1, arrive]  EPI_WG3[...]" % keep)
+for gs in range(24):
+    print("g%02d MMA %s | WG0 %s | WG3 %s" % (gs, [rel(x) for x in t[0, gs]], [rel(x) for x in t[1, gs, :7]], [rel(x) for x in t[2, gs, :7]]))
