@@ -48,54 +48,55 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons sampled every 10 ms through NVML while the timed region runs (the timed
+    region of a default run is ~0.1 s, too short for `nvidia-smi -lms 200`)."""
+    REASONS = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "sw_power_cap": 0x4}
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.sm, self.mask, self.max_mhz, self.power = index, [], 0, None, []
+        self._stop = threading.Event()
+        self.th = None
 
     def __enter__(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.th = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.index]) if vis and vis.split(",")[0].isdigit() else self.index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.th = threading.Thread(target=self._run, daemon=True)
             self.th.start()
-        except Exception:
-            self.proc = None
+        except Exception as e:       # NVML missing: record nothing rather than fail the bench
+            self.err = repr(e)
         return self
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
-    def __exit__(self, *a):
-        if self.proc is not None:
-            self.proc.terminate()
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
             try:
-                self.proc.wait(timeout=2)
-            except Exception:
-                self.proc.kill()
-
-    def summary(self):
-        sm, mx, reasons = [], 0.0, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[0]))
-                mx = max(mx, float(r[1]))
-                for n, v in zip(names, r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    self.mask |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    self.mask |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
             except Exception:
                 pass
-        sm.sort()
-        # under load = upper half of the samples (the sampler also sees the idle edges)
-        load = sm[len(sm) // 2:] if sm else []
-        med = load[len(load) // 2] if load else None
-        return {"sm_mhz": med, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+            time.sleep(0.01)
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self.th is not None:
+            self.th.join(timeout=1)
+
+    def summary(self):
+        sm = sorted(self.sm)
+        med = sm[len(sm) // 2] if sm else None
+        return {"sm_mhz": med, "sm_min_mhz": sm[0] if sm else None, "sm_max_mhz": self.max_mhz,
+                "power_w_max": max(self.power) if self.power else None,
+                "reasons": sorted(k for k, b in self.REASONS.items() if self.mask & b), "samples": len(sm)}
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -253,6 +254,7 @@ def run_ours(args):
             o += p.numel()
 
     def step(rays, t_rgb, t_dep):
+        """Drop-in route: the reference's own call sequence (run_nerf.py:1416-1418, :1500-1536, :1759-1761, :1773)."""
         rgb, disp, acc, depth, extras = dn.render(H, W, FOCAL, chunk=1 << 30, rays=rays, retraw=True, **kw)
         for p in params:
             p.grad = None
@@ -261,6 +263,15 @@ def run_ours(args):
         loss.backward()
         allreduce_grads()
         return loss
+
+    def fused_step(rays, t_rgb, t_dep):
+        """Same step through dlnerf_b200.train_step: loss gradient fused into the compositing backward kernel."""
+        out = dn.train_step(H, W, FOCAL, rays, t_rgb, t_dep, n_rgb, net_c, net_f, N_samples=N_SAMPLES,
+                            N_importance=N_IMPORTANCE, perturb=1., raw_noise_std=1., depth_lambda=DEPTH_LAMBDA,
+                            depth_importance=1., world_size=world)
+        return out["loss"]
+
+    dev_step = step if args.path == "dropin" else fused_step
 
     def barrier():
         if world > 1:
@@ -284,11 +295,11 @@ def run_ours(args):
 
     # ---- device-resident throughput -------------------------------------------------------------
     for _ in range(max(args.warmup, 3)):
-        step(d_rays, d_tgt, d_dep)
+        dev_step(d_rays, d_tgt, d_dep)
     L.TRACE = []
     n0 = L.LAUNCHES
     with ClockSampler(local) as clk:
-        ms = timed(lambda: step(d_rays, d_tgt, d_dep), args.steps)
+        ms = timed(lambda: dev_step(d_rays, d_tgt, d_dep), args.steps)
     trace, L.TRACE = L.TRACE, None
     launches = (L.LAUNCHES - n0) // max(args.steps, 1)
     value = args.n_rand * world / (ms * 1e-3)
@@ -347,7 +358,7 @@ def run_ours(args):
             "metric": "training rays/sec (fwd+bwd)", "value": value, "unit": "rays/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": workload_config(args, world), "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches,
+            "config": dict(workload_config(args, world), value_route=("dlnerf_b200.train_step" if args.path == "fused" else "render()+loss.backward()")), "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches,
             "roofline": roofline, "cpu_baseline": cb, "kernels": kern}))
     if world > 1:
         dist.destroy_process_group()
@@ -361,6 +372,9 @@ def main():
     ap.add_argument("--n-rand", type=int, default=4096, help="rays per step per GPU (config B: 4096)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--path", default="fused", choices=["fused", "dropin"],
+                    help="route of the device-resident `value`: train_step (fused loss) or render()+loss.backward(); "
+                         "`e2e` always uses the drop-in route")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

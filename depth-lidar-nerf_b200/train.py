@@ -1,0 +1,163 @@
+"""One training iteration of the hot path, and its ray-sharded data-parallel form.
+
+* ``train_step``  — render (coarse + fine) + RGB / LiDAR-depth loss + backward without building an autograd
+  graph: the loss gradient is formed inside the compositing backward kernel
+  (``dln_composite_bwd_fused_loss``, north_star part 5) and handed straight to the MLP dgrad / wgrad
+  kernels.  Same arithmetic as the drop-in route ``render(...)`` + ``img2mse`` + ``loss.backward()``
+  (run_nerf.py:1416-1418, :1451-1466, :1500-1536, :1759-1761, :1773); parameter ``.grad`` tensors are filled
+  for the reference's ``optimizer.step()``.
+* ``shard_ray_batch`` / ``allreduce_gradients`` — rays are independent, so G GPUs each render an equal
+  slice of the RGB rays and of the depth rays (per-class, so the per-rank means are unbiased) and the MLP
+  gradients are averaged with ONE all-reduce over a flat buffer.  The reference itself has
+  no distributed code; this is the only collective on the path.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional, Sequence
+
+import torch
+
+from . import ops
+from .run_nerf import FusedQuery
+from .run_nerf_helpers import NeRF, ndc_rays
+
+Tensor = torch.Tensor
+
+_DEPTH_MODES = {"mse": 0, "weighted": 1, "weighted_norm": 2, "relative": 3}
+
+
+# ----------------------------------------------------------------------------------------------------
+# ray-sharded data parallelism
+# ----------------------------------------------------------------------------------------------------
+def shard_bounds(n: int, rank: int, world: int):
+    """Contiguous equal split of n items; the first n % world ranks get one extra."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_ray_batch(batch_rays: Tensor, target_s: Tensor, target_depth: Optional[Tensor], n_rgb: int, rank: int,
+                    world: int, ray_weights: Optional[Tensor] = None):
+    """Slice the step's batch [2, n_rgb + n_depth, 3] (RGB rays first, run_nerf.py:1409-1411) for one rank,
+    per ray class.  Returns (rays, target_s, target_depth, ray_weights, n_rgb_local)."""
+    n = batch_rays.shape[1]
+    a0, a1 = shard_bounds(n_rgb, rank, world)
+    b0, b1 = shard_bounds(n - n_rgb, rank, world)
+    rays = torch.cat([batch_rays[:, a0:a1], batch_rays[:, n_rgb + b0:n_rgb + b1]], dim=1)
+    td = None if target_depth is None else target_depth[b0:b1]
+    rw = None if ray_weights is None else ray_weights[b0:b1]
+    return rays, target_s[a0:a1], td, rw, a1 - a0
+
+
+def allreduce_gradients(params: Sequence[Tensor], world: int, group=None) -> None:
+    """Average the gradients over the ranks with one all-reduce of a flat fp32 buffer (4.8 MB for the two
+    8x256 nets): on NVLink 5 / NVSwitch this is latency-bound, so one bucket beats many."""
+    if world <= 1:
+        return
+    import torch.distributed as dist
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads:
+        return
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    flat.div_(world)
+    o = 0
+    for g in grads:
+        g.copy_(flat[o:o + g.numel()].view_as(g))
+        o += g.numel()
+
+
+# ----------------------------------------------------------------------------------------------------
+# fused training step
+# ----------------------------------------------------------------------------------------------------
+def pack_ray_batch(H: int, W: int, focal: float, batch_rays: Tensor, ndc: bool = True, near: float = 0.,
+                   far: float = 1., use_viewdirs: bool = True) -> Tensor:
+    """The [N, 8|11] ray_batch of render() (run_nerf.py:145-183): unit view directions from the PRE-warp
+    directions, NDC warp with near plane 1, [o, d, near, far, viewdirs]."""
+    rays_o, rays_d = batch_rays[0], batch_rays[1]
+    viewdirs = None
+    if use_viewdirs:
+        viewdirs = rays_d / torch.norm(rays_d, dim=-1, keepdim=True)
+    if ndc:
+        rays_o, rays_d = ndc_rays(H, W, focal, 1., rays_o, rays_d)
+    ones = torch.ones_like(rays_d[..., :1])
+    cols = [rays_o, rays_d, near * ones, far * ones]
+    if viewdirs is not None:
+        cols.append(viewdirs)
+    return torch.cat(cols, -1).float().contiguous()
+
+
+@torch.no_grad()
+def train_step(H, W, focal, batch_rays: Tensor, target_s: Tensor, target_depth: Optional[Tensor], n_rgb: int,
+               network_fn: NeRF, network_fine: NeRF, N_samples: int = 64, N_importance: int = 64,
+               perturb: float = 1., raw_noise_std: float = 1., white_bkgd: bool = False, lindisp: bool = False,
+               ndc: bool = True, near: float = 0., far: float = 1., depth_lambda: float = 0.,
+               depth_importance: float = 1., ray_weights: Optional[Tensor] = None, depth_mode: str = "mse",
+               coarse_loss: bool = True, world_size: int = 1, group=None, _rng: Optional[Dict[str, Tensor]] = None
+               ) -> Dict[str, Tensor]:
+    """render + loss + backward for one ray batch; fills ``.grad`` of both networks (averaged over
+    ``world_size`` ranks when > 1) and returns the loss terms as 0-d tensors (no host sync).
+
+    Random draws follow the reference's order (rand jitter, randn coarse noise, rand u, randn fine noise);
+    ``_rng`` (tests) injects them."""
+    if network_fine is None or N_importance <= 0:
+        raise NotImplementedError("train_step implements the coarse + fine configuration every shipped config uses")
+    rb = pack_ray_batch(H, W, focal, batch_rays, ndc, near, far, network_fn.use_viewdirs)
+    N, dev = rb.shape[0], rb.device
+    rays_d = rb[:, 3:6].contiguous()
+    n_dep = N - n_rgb
+    rng = _rng or {}
+
+    def draw(name, kind, shape):
+        if name in rng:
+            return rng[name]
+        return (torch.rand if kind == "u" else torch.randn)(shape, device=dev)
+
+    t_rand = draw("t_rand", "u", (N, N_samples)) if perturb > 0. else None
+    z0 = ops.stratified_z(rb, N_samples, t_rand, lindisp)
+    raw0, saved0 = network_fn._run_forward("rays", rb, z0, N * N_samples, keep=True)
+    raw0 = raw0.view(N, N_samples, -1)
+    noise0 = draw("noise0", "n", (N, N_samples)) if raw_noise_std > 0. else None
+    rgb0, disp0, acc0, w0, depth0 = ops.composite(raw0, z0, rays_d, noise0, float(raw_noise_std), bool(white_bkgd))
+    u = draw("u", "u", (N, N_importance)) if perturb != 0. else None
+    z_samples, z1 = ops.importance_resample(z0, w0, N_importance, u)
+    S1 = N_samples + N_importance
+    raw1, saved1 = network_fine._run_forward("rays", rb, z1, N * S1, keep=True)
+    raw1 = raw1.view(N, S1, -1)
+    noise1 = draw("noise1", "n", (N, S1)) if raw_noise_std > 0. else None
+
+    mode = _DEPTH_MODES[depth_mode]
+    use_depth = target_depth is not None and n_dep > 0 and depth_lambda != 0.
+    depth_norm = float(target_depth.max()) if (use_depth and mode == 2) else 1.0
+    coef_rgb = 2.0 / (3.0 * max(n_rgb, 1))
+    coef_dep = 2.0 * depth_lambda * depth_importance / max(n_dep, 1) if use_depth else 0.0
+    sums = torch.zeros(4, device=dev)
+    tgt = ops._f32(target_s, "train_step")
+    tdep = ops._f32(target_depth, "train_step") if use_depth else None
+    rw = ops._f32(ray_weights, "train_step") if (use_depth and ray_weights is not None) else None
+    # fine pass: colour loss on the RGB rays, depth loss on the depth rays (run_nerf.py:1461, :1500-1524)
+    d_raw1 = ops.composite_bwd_fused_loss(raw1, z1, rays_d, noise1, raw_noise_std, white_bkgd, tgt, tdep, rw, n_rgb,
+                                          coef_rgb, coef_dep, mode, depth_norm, sums[0:2])
+    grads_f = network_fine._run_backward(d_raw1, saved1, N * S1)
+    _assign_grads(network_fine, grads_f)
+    if coarse_loss:
+        # coarse pass: colour loss only (run_nerf.py:1759-1761); depth_map0 is unsupervised
+        d_raw0 = ops.composite_bwd_fused_loss(raw0, z0, rays_d, noise0, raw_noise_std, white_bkgd, tgt, None, None,
+                                              n_rgb, coef_rgb, 0.0, 0, 1.0, sums[2:4])
+        grads_c = network_fn._run_backward(d_raw0, saved0, N * N_samples)
+        _assign_grads(network_fn, grads_c)
+    if world_size > 1:
+        allreduce_gradients(list(network_fn.parameters()) + list(network_fine.parameters()), world_size, group)
+    img_loss = sums[0] / (3.0 * max(n_rgb, 1))
+    img_loss0 = sums[2] / (3.0 * max(n_rgb, 1))
+    depth_loss = sums[1] / max(n_dep, 1)
+    loss = img_loss + depth_lambda * depth_importance * depth_loss + (img_loss0 if coarse_loss else 0.)
+    return {"loss": loss, "img_loss": img_loss, "img_loss0": img_loss0, "depth_loss": depth_loss,
+            "psnr": -10. * torch.log10(img_loss)}
+
+
+def _assign_grads(net: NeRF, grads) -> None:
+    for p, g in zip(net._ordered_params(), grads):
+        if g is not None:
+            p.grad = g

@@ -1,0 +1,77 @@
+"""CPU, world_size 2, gloo: the ray-sharded data-parallel plumbing (shard_ray_batch + allreduce_gradients).
+The per-rank loss uses the reference's normalisation (means over the local RGB rays / local depth rays);
+averaging the per-rank gradients must reproduce the single-process gradient of the full batch."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import dlnerf_b200 as dn
+
+
+def _model():
+    torch.manual_seed(0)
+    return torch.nn.Sequential(torch.nn.Linear(6, 16), torch.nn.ReLU(), torch.nn.Linear(16, 4))
+
+
+def _loss(model, rays, tgt, dep, n_rgb, lam=0.3):
+    x = torch.cat([rays[0], rays[1]], -1)            # [N, 6]
+    y = model(x)
+    return torch.mean((y[:n_rgb, :3] - tgt) ** 2) + lam * torch.mean((y[n_rgb:, 3] - dep) ** 2)
+
+
+def _batch(n_rgb=12, n_dep=8):
+    g = torch.Generator().manual_seed(1)
+    return torch.randn(2, n_rgb + n_dep, 3, generator=g), torch.rand(n_rgb, 3, generator=g), torch.rand(n_dep, generator=g)
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rays, tgt, dep = _batch()
+    n_rgb = tgt.shape[0]
+    r, t, d, _, n_loc = dn.shard_ray_batch(rays, tgt, dep, n_rgb, rank, world)
+    model = _model()
+    _loss(model, r, t, d, n_loc).backward()
+    dn.allreduce_gradients(list(model.parameters()), world)
+    if rank == 0:
+        torch.save([p.grad for p in model.parameters()], out)
+    dist.destroy_process_group()
+
+
+def test_shard_bounds_cover_everything():
+    for n in (0, 1, 7, 4096):
+        for w in (1, 2, 3, 8):
+            spans = [dn.shard_bounds(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert max(b - a for a, b in spans) - min(b - a for a, b in spans) <= 1
+
+
+def test_sharded_gradients_match_single_process(tmp_path):
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    out = str(tmp_path / "g.pt")
+    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    got = torch.load(out)
+    rays, tgt, dep = _batch()
+    model = _model()
+    _loss(model, rays, tgt, dep, tgt.shape[0]).backward()
+    for g, p in zip(got, model.parameters()):
+        torch.testing.assert_close(g, p.grad, rtol=1e-5, atol=1e-6)
+
+
+def test_shard_keeps_class_order():
+    rays, tgt, dep = _batch(n_rgb=10, n_dep=6)
+    seen_rgb, seen_dep = [], []
+    for rank in range(4):
+        r, t, d, _, n_loc = dn.shard_ray_batch(rays, tgt, dep, 10, rank, 4)
+        assert r.shape[1] == n_loc + d.shape[0] and t.shape[0] == n_loc
+        seen_rgb.append(r[:, :n_loc])
+        seen_dep.append(r[:, n_loc:])
+    assert torch.equal(torch.cat(seen_rgb, 1), rays[:, :10]) and torch.equal(torch.cat(seen_dep, 1), rays[:, 10:])
