@@ -15,9 +15,10 @@ from .run_nerf_helpers import (Embedder, NeRF, get_embedder, img2mse, mse2psnr, 
                                sample_pdf, to8b)
 from .run_nerf import (FusedQuery, batchify, batchify_rays, create_nerf, get_rays, render, render_rays,
                        run_network)
-from .train import allreduce_gradients, pack_ray_batch, shard_bounds, shard_ray_batch, train_step
+from .train import (GraphedTrainStep, allreduce_gradients, pack_ray_batch, shard_bounds, shard_ray_batch,
+                    train_step)
 
 __all__ = ["build", "lib", "ops", "Embedder", "NeRF", "get_embedder", "img2mse", "mse2psnr", "ndc_rays",
            "raw2outputs", "sample_pdf", "to8b", "FusedQuery", "batchify", "batchify_rays", "create_nerf",
            "get_rays", "render", "render_rays", "run_network", "allreduce_gradients", "pack_ray_batch",
-           "shard_bounds", "shard_ray_batch", "train_step"]
+           "shard_bounds", "shard_ray_batch", "train_step", "GraphedTrainStep"]

@@ -32,12 +32,13 @@ constexpr int kNumStages = 4;      // the ring holds one whole 256x256 layer: it
 constexpr int kStageBytes = 32768;
 constexpr int kSlab = DLN_SLAB_BYTES;
 constexpr int kNumSlabs = 5;       // 0..3 activations, 4 encoded position -> encoded direction (fwd) / d_raw (bwd)
+constexpr bool kSplitN = false;    // issue 256-wide layers as two N=128 halves (measured slower: the MMA issue cost is per instruction)
 constexpr int kMaxBiasFloats = 2432;   // 9 x 256 + 128: netdepth <= 8 with view directions, <= 9 without
 
 struct ChainSmall {
   uint64_t w_full[kNumStages], w_empty[kNumStages];
   uint64_t a_ready[kNumSlabs], s_free[kNumSlabs];
-  uint64_t acc_full[2];
+  uint64_t acc_full[2][2];         // [accumulator buffer][128-column half]
   uint64_t grp_full[kNumStages];   // weights of a group of <=4 stages have landed (helper -> MMA thread); rotating,
                                    // so a parity wait can never alias: at most kNumStages groups are ever in flight
   uint32_t tmem_base;
@@ -108,28 +109,25 @@ __device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi) {
   return r;
 }
 
-// write 32 consecutive columns [cb, cb+32) of row r into the activation slabs (optionally relu'd on the fly) and,
-// when `gslab0` is given, into the same position of the stash image in global memory (slab cb>>6 at gslab0).
-// A thread's four 16-byte chunks fill two complete 32-byte sectors of the 128-byte row.
+// 32 fp32 values -> 16 packed bf16x2 words (optionally relu'd on the fly)
 template <bool kRelu>
-__device__ __forceinline__ void store_cols32(uint8_t* act, uint8_t* gslab, int r, int cb, const float (&f)[32]) {
-  const int rowoff = (r >> 3) * 1024 + (r & 7) * 128;
-  uint8_t* row = act + (cb >> 6) * kSlab + rowoff;
+__device__ __forceinline__ void pack32(const float (&f)[32], uint32_t (&pk)[16]) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) pk[i] = kRelu ? pack_bf16_relu(f[2 * i], f[2 * i + 1]) : pack_bf16(f[2 * i], f[2 * i + 1]);
+}
+// write the 32 consecutive columns [cb, cb+32) of row r (16 packed words) into the activation slabs
+__device__ __forceinline__ void store_packed32(uint8_t* act, int r, int cb, const uint32_t (&pk)[16]) {
+  uint8_t* row = act + (cb >> 6) * kSlab + (r >> 3) * 1024 + (r & 7) * 128;
   const int ch0 = (cb & 63) >> 3;
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    uint4 v;
-    if (kRelu) {
-      v.x = pack_bf16_relu(f[8 * q + 0], f[8 * q + 1]), v.y = pack_bf16_relu(f[8 * q + 2], f[8 * q + 3]);
-      v.z = pack_bf16_relu(f[8 * q + 4], f[8 * q + 5]), v.w = pack_bf16_relu(f[8 * q + 6], f[8 * q + 7]);
-    } else {
-      v.x = pack_bf16(f[8 * q + 0], f[8 * q + 1]), v.y = pack_bf16(f[8 * q + 2], f[8 * q + 3]);
-      v.z = pack_bf16(f[8 * q + 4], f[8 * q + 5]), v.w = pack_bf16(f[8 * q + 6], f[8 * q + 7]);
-    }
-    const int off = ((ch0 + q) ^ (r & 7)) << 4;
-    *reinterpret_cast<uint4*>(row + off) = v;
-    if (gslab) *reinterpret_cast<uint4*>(gslab + rowoff + off) = v;
-  }
+  for (int q = 0; q < 4; ++q)
+    *reinterpret_cast<uint4*>(row + (((ch0 + q) ^ (r & 7)) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+}
+template <bool kRelu>
+__device__ __forceinline__ void store_cols32(uint8_t* act, uint8_t*, int r, int cb, const float (&f)[32]) {
+  uint32_t pk[16];
+  pack32<kRelu>(f, pk);
+  store_packed32(act, r, cb, pk);
 }
 
 // two fp32 adds in one instruction (FADD2)
@@ -146,12 +144,12 @@ __device__ __forceinline__ void add2(float& a0, float& a1, float b0, float b1) {
 // finish slabs 0 and 1 (the first K slabs of the next layer) together before anybody starts on slabs 2 and 3,
 // and a 128-wide output keeps all four warpgroups busy.  relu-mask word h of the thread's uint2 covers chunk h.
 //
-// One 32-column chunk of an epilogue: TMEM values -> (+bias | +dsigma*head) -> relu / mask -> bf16 slab.
+// One 32-column chunk of an epilogue: TMEM values -> (+bias | +dsigma*head) -> relu / mask -> 16 packed bf16x2 words.
 template <int EPI>
 __device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], const float* __restrict__ bias,
                                           const float* __restrict__ hw, int n_out, int nheads, float dsig,
-                                          uint32_t mw_in, uint32_t& mw_out, float (&hacc)[5], uint8_t* slabs,
-                                          uint8_t* gslab, int r, int cb) {
+                                          uint32_t mw_in, uint32_t& mw_out, float (&hacc)[5], uint32_t (&pk)[16],
+                                          int cb) {
   constexpr bool kFwd = EPI <= DLN_EPI_RELU_OUT;
   constexpr bool kRelu = EPI == DLN_EPI_RELU || EPI == DLN_EPI_RELU_SIGMA || EPI == DLN_EPI_RELU_RGB || EPI == DLN_EPI_RELU_OUT;
   float f[32];
@@ -174,10 +172,16 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], const float* 
   }
   if (kRelu) {
     // sign bits -> mask word with one funnel shift per element (bit i <-> column cb+i); relu' := (x >= +0)
-    uint32_t neg = 0;
+    // (four independent 8-long chains instead of one 32-long dependent chain)
+    uint32_t n0 = 0, n1 = 0, n2 = 0, n3 = 0;
 #pragma unroll
-    for (int i = 31; i >= 0; --i) neg = __funnelshift_l(__float_as_uint(f[i]), neg, 1);
-    mw_out = ~neg;
+    for (int i = 7; i >= 0; --i) {
+      n0 = __funnelshift_l(__float_as_uint(f[i]), n0, 1);
+      n1 = __funnelshift_l(__float_as_uint(f[8 + i]), n1, 1);
+      n2 = __funnelshift_l(__float_as_uint(f[16 + i]), n2, 1);
+      n3 = __funnelshift_l(__float_as_uint(f[24 + i]), n3, 1);
+    }
+    mw_out = ~(n0 | (n1 << 8) | (n2 << 16) | (n3 << 24));
   }
   if (EPI >= DLN_EPI_BWD_MASK) {
 #pragma unroll
@@ -200,12 +204,13 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], const float* 
         hacc[h] += a;
       }
   }
-  store_cols32<kRelu>(slabs, gslab, r, cb, f);
+  pack32<kRelu>(f, pk);
 }
 
 // debug timeline: trace[role][gstep][event] = SM clock (CTA 0 only, first 64 steps)
 __device__ __forceinline__ void trace_ev(long long* trace, int role, uint32_t gstep, int ev) {
-  if (trace != nullptr && blockIdx.x == 0 && gstep < 64) trace[(role * 64 + gstep) * 8 + ev] = clock64();
+  if (trace != nullptr && blockIdx.x == 0 && gstep < 64 && (role != 0 || (threadIdx.x & 31) == 0))
+    trace[(role * 64 + gstep) * 8 + ev] = clock64();
 }
 
 struct ProdTrack {
@@ -233,7 +238,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   if (threadIdx.x == 0) {
     for (int i = 0; i < kNumStages; ++i) mbar_init(&sm->w_full[i], 1), mbar_init(&sm->w_empty[i], 1);
     for (int i = 0; i < kNumSlabs; ++i) mbar_init(&sm->a_ready[i], i < 4 ? 256 : 128), mbar_init(&sm->s_free[i], 1);
-    mbar_init(&sm->acc_full[0], 1), mbar_init(&sm->acc_full[1], 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&sm->acc_full[i >> 1][i & 1], 1);
     for (int i = 0; i < kNumStages; ++i) mbar_init(&sm->grp_full[i], 1);
     mbar_fence_init();
   }
@@ -273,8 +278,9 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
     }
   } else if (warp == 1) {
-    // ===================================================== MMA issuer
-    if (lane == 0) {
+    // ===================================================== MMA issuer: the whole warp walks the (warp-uniform) program
+    // so that descriptors and addresses live in uniform registers; one elected lane issues tcgen05.mma / commit
+    {
       uint32_t stage = 0, gstep = 0, grp = 0;
       uint32_t par = 0;  // parity of the production count per slab
       const uint32_t pmask = prologue_mask(prog);
@@ -284,31 +290,49 @@ __global__ void __launch_bounds__(kThreads, 1)
         par ^= pmask;
         for (int s = 0; s < prog.n_steps; ++s, ++gstep) {
           const DlnChainStep& st = prog.steps[s];
-          const uint32_t d_tmem = tmem_base + (gstep & 1) * 256;
-          const uint32_t idesc = umma_idesc_bf16(128, st.n_out, 0, 0);
+          // A 256-wide layer is issued as two 128-column halves (M128 N128 K16) when its K slabs fit the ring:
+          // the first half's accumulator is committed early, so the epilogue of columns 0..127 overlaps the
+          // MMAs of columns 128..255.  (5-slab steps reuse a ring slot and are issued unsplit.)
+          const bool split = kSplitN && st.n_out == 256 && st.nk <= kNumStages;
+          const int nhalf = split ? 2 : 1;
+          const uint32_t idesc = umma_idesc_bf16(128, split ? 128 : st.n_out, 0, 0);
+          const uint32_t stage0 = stage;
           trace_ev(args.trace, 0, gstep, 0);
-          for (int j = 0; j < st.nk; ++j) {
-            const int slab = st.kslab[j];
-            mbar_wait(&sm->a_ready[slab], ((par >> slab) & 1) ^ 1);   // last production completed
-            if (j < 5) trace_ev(args.trace, 0, gstep, 1 + j);
-            if ((j & 3) == 0) {            // the helper thread has seen w_full of this group of <=4 stages
-              mbar_wait(&sm->grp_full[grp & (kNumStages - 1)], (grp / kNumStages) & 1);
-              ++grp;
+          for (int half = 0; half < nhalf; ++half) {
+            const uint32_t d_tmem = tmem_base + (gstep & 1) * 256 + half * 128;
+            stage = stage0;
+            for (int j = 0; j < st.nk; ++j) {
+              const int slab = st.kslab[j];
+              if (half == 0) {
+                mbar_wait(&sm->a_ready[slab], ((par >> slab) & 1) ^ 1);   // last production completed
+                if (j < 5) trace_ev(args.trace, 0, gstep, 1 + j);
+                if ((j & 3) == 0) {          // the helper thread has seen w_full of this group of <=4 stages
+                  mbar_wait(&sm->grp_full[grp & (kNumStages - 1)], (grp / kNumStages) & 1);
+                  ++grp;
+                }
+                tc_fence_after();
+              }
+              // descriptors differ only in the 14-bit start-address field: +2 (= 32 B) per K=16 step
+              const uint64_t ad = desc_k | (uint64_t)((slab_addr0 + slab * kSlab) >> 4);
+              const uint64_t bd = desc_k | (uint64_t)((ring_addr0 + stage * kStageBytes + half * (kStageBytes / 2)) >> 4);
+              const int kc = st.kcnt[j];
+              if (elect_one()) {
+                umma_bf16(d_tmem, ad, bd, idesc, j != 0);
+                if (kc > 1) umma_bf16(d_tmem, ad + 2, bd + 2, idesc, 1);
+                if (kc > 2) umma_bf16(d_tmem, ad + 4, bd + 4, idesc, 1);
+                if (kc > 3) umma_bf16(d_tmem, ad + 6, bd + 6, idesc, 1);
+                if (half == nhalf - 1) umma_commit(&sm->w_empty[stage]);
+              }
+              __syncwarp();
+              if (++stage == kNumStages) stage = 0;
             }
-            if (j == st.nk - 1) trace_ev(args.trace, 0, gstep, 6);
-            tc_fence_after();
-            // descriptors differ only in the 14-bit start-address field: +2 (= 32 B) per K=16 step
-            const uint64_t ad = desc_k | (uint64_t)((slab_addr0 + slab * kSlab) >> 4);
-            const uint64_t bd = desc_k | (uint64_t)((ring_addr0 + stage * kStageBytes) >> 4);
-            const int kc = st.kcnt[j];
-            umma_bf16(d_tmem, ad, bd, idesc, j != 0);
-            if (kc > 1) umma_bf16(d_tmem, ad + 2, bd + 2, idesc, 1);
-            if (kc > 2) umma_bf16(d_tmem, ad + 4, bd + 4, idesc, 1);
-            if (kc > 3) umma_bf16(d_tmem, ad + 6, bd + 6, idesc, 1);
-            umma_commit(&sm->w_empty[stage]);
-            if (++stage == kNumStages) stage = 0;
+            if (elect_one()) {
+              umma_commit(&sm->acc_full[gstep & 1][half]);
+              if (!split) umma_commit(&sm->acc_full[gstep & 1][1]);
+            }
+            __syncwarp();
+            if (half == 0) trace_ev(args.trace, 0, gstep, 6);
           }
-          umma_commit(&sm->acc_full[gstep & 1]);
           trace_ev(args.trace, 0, gstep, 7);
           par ^= step_out_mask(st);
           if (s == reload_step) par ^= 0x10u;
@@ -322,47 +346,31 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
     }
   } else if (warp == 2) {
-    // ===================================================== stash writer (training only): bulk smem -> global copies
-    // of every produced slab, two in flight (slab i is issued before slab i-1 is retired)
-    if (lane == 0 && keep) {
+    // ===================================================== stash writers (training only): lane i owns slab i and copies
+    // every production of it to the global stash with one bulk smem -> global copy; the five lanes work
+    // independently (bulk-copy groups are tracked per thread), so the copies of one layer run concurrently
+    if (lane < kNumSlabs && keep) {
+      const int slab = lane;
       uint32_t par = 0;
       const uint32_t pmask = prologue_mask(prog);
       uint8_t* stash = reinterpret_cast<uint8_t*>(args.stash);
-      int pending = -1;               // slab whose store has been issued but whose smem read is not yet retired
-      auto retire = [&](int keep_newer) {
-        if (pending >= 0) {
-          if (keep_newer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-          else bulk_wait_read0();
-          mbar_arrive(&sm->s_free[pending]);
-          pending = -1;
-        }
-      };
       for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         uint8_t* tbase = stash + (size_t)tile * prog.stash_slots * kSlab;
-        auto handle = [&](int slab, int slot) {
-          mbar_wait(&sm->a_ready[slab], (par >> slab) & 1);
-          par ^= 1u << slab;
+        auto handle = [&](int slot) {
+          mbar_wait(&sm->a_ready[slab], par);
+          par ^= 1u;
           if (slot >= 0) {
             bulk_s2g(tbase + (size_t)slot * kSlab, slabs + slab * kSlab, kSlab);
             bulk_commit();
-            const int prev = pending;
-            pending = prev;           // retire the previous store while this one is in flight
-            retire(1);
-            pending = slab;
-          } else {
-            retire(0);
-            mbar_arrive(&sm->s_free[slab]);
+            bulk_wait_read0();
           }
+          mbar_arrive(&sm->s_free[slab]);
         };
-        for (int slab = 0; slab < kNumSlabs; ++slab)
-          if ((pmask >> slab) & 1) handle(slab, slab == 4 ? 0 : prog.pro_slot + slab);
+        if ((pmask >> slab) & 1) handle(slab == 4 ? 0 : prog.pro_slot + slab);
         for (int s = 0; s < prog.n_steps; ++s) {
           const DlnChainStep& st = prog.steps[s];
-          const uint32_t om = step_out_mask(st);
-          for (int slab = 0; slab < 4; ++slab)
-            if ((om >> slab) & 1) handle(slab, st.stash_slot >= 0 ? st.stash_slot + slab : -1);
-          if (s == reload_step) handle(4, 1);        // encoded direction -> slot 1
-          retire(0);                                 // nothing stays pending across a step boundary
+          if (slab < 4 && ((step_out_mask(st) >> slab) & 1)) handle(st.stash_slot >= 0 ? st.stash_slot + slab : -1);
+          if (slab == 4 && s == reload_step) handle(1);        // encoded direction -> slot 1
         }
       }
       bulk_wait_all0();
@@ -432,7 +440,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       const long long p = tile * DLN_TILE_ROWS + r;
       const bool valid = p < args.P;
       float dsig = 0.f;
-      auto gslot = [&](int) -> uint8_t* { return nullptr; };   // the stash goes through the bulk-copy engine (warp 2)
+      auto gslot = [&](int) -> uint8_t* { return nullptr; };
       // ------------------------------------------------------------------ prologue
       if (!kBwd) {
         if (g == 0) {
@@ -503,7 +511,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         if (epi >= DLN_EPI_BWD_MASK && st.mask_slot >= 0) mw = reinterpret_cast<const uint2*>(args.masks)[mask_idx];
         const int trole = (et == 0) ? 1 : (et == 384 ? 2 : -1);
         if (trole > 0) trace_ev(args.trace, trole, gstep, 0);
-        mbar_wait(&sm->acc_full[gstep & 1], (gstep >> 1) & 1);
+        mbar_wait(&sm->acc_full[gstep & 1][0], (gstep >> 1) & 1);
         tc_fence_after();
         if (trole > 0) trace_ev(args.trace, trole, gstep, 1);
 
@@ -514,10 +522,10 @@ __global__ void __launch_bounds__(kThreads, 1)
         float hacc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
         uint32_t mo0 = 0, mo1 = 0;
         {
+          uint32_t pk[16];
           auto run = [&](auto tag, const uint32_t(&v)[32], uint32_t mi, uint32_t& mo, int cb) {
             constexpr int E = decltype(tag)::value;
-            epi_chunk<E>(v, bias, hw, st.n_out, nheads, dsig, mi, mo, hacc, slabs,
-                         gslot(st.stash_slot >= 0 ? st.stash_slot + (cb >> 6) : -1), r, cb);
+            epi_chunk<E>(v, bias, hw, st.n_out, nheads, dsig, mi, mo, hacc, pk, cb);
           };
           auto dispatch = [&](const uint32_t(&v)[32], uint32_t mi, uint32_t& mo, int cb) {
             if (!kBwd) {
@@ -530,25 +538,32 @@ __global__ void __launch_bounds__(kThreads, 1)
             }
           };
           uint32_t v[32];
-          const int cb0 = 32 * g;                    // chunk 0: slab g>>1
+          const int cb0 = 32 * g;                    // chunk 0: slab g>>1 (columns 0..127: first MMA half)
           tmem_ld32(t_acc + cb0, v);
           tmem_ld_wait();
           if (trole > 0) trace_ev(args.trace, trole, gstep, 2);
-          begin_produce(cb0 >> 6);
+          dispatch(v, mw.x, mo0, cb0);               // results stay in registers ...
           if (trole > 0) trace_ev(args.trace, trole, gstep, 3);
-          dispatch(v, mw.x, mo0, cb0);
-          end_produce(cb0 >> 6);
+          // ... until the second MMA half has completed too: the activation slabs are updated in place and every
+          // MMA of this layer reads all of them
+          mbar_wait(&sm->acc_full[gstep & 1][1], (gstep >> 1) & 1);
+          tc_fence_after();
           if (trole > 0) trace_ev(args.trace, trole, gstep, 4);
+          begin_produce(cb0 >> 6);
+          if (trole > 0) trace_ev(args.trace, trole, gstep, 5);
+          store_packed32(slabs, r, cb0, pk);
+          if (trole > 0) trace_ev(args.trace, trole, gstep, 6);
+          end_produce(cb0 >> 6);
+          if (trole > 0) trace_ev(args.trace, trole, gstep, 7);
           if (st.n_out == 256) {                     // chunk 1: slab 2 + (g>>1)
             const int cb1 = 128 + 32 * g;
             tmem_ld32(t_acc + cb1, v);
             tmem_ld_wait();
-            begin_produce(cb1 >> 6);
             dispatch(v, mw.y, mo1, cb1);
-            if (trole > 0) trace_ev(args.trace, trole, gstep, 5);
+            begin_produce(cb1 >> 6);
+            store_packed32(slabs, r, cb1, pk);
             end_produce(cb1 >> 6);
           }
-          if (trole > 0) trace_ev(args.trace, trole, gstep, 6);
           if (relu && st.mask_slot >= 0 && args.masks != nullptr)
             reinterpret_cast<uint2*>(args.masks)[mask_idx] = make_uint2(mo0, mo1);
         }

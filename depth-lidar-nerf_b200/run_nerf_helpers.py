@@ -155,10 +155,10 @@ class NeRF(nn.Module):
             self._dev_state = st
         return st
 
-    def _pack(self, st):
+    def _pack(self, st, force=False):
         params = self._ordered_params()
         ver = tuple(p._version for p in params)
-        if st["version"] == ver:
+        if st["version"] == ver and not force:
             return
         pl = self._plan
         lib, s = L.lib(), ops._stream()
@@ -169,9 +169,9 @@ class NeRF(nn.Module):
         st["version"] = ver
 
     # ------------------------------------------------------------------ kernels
-    def _run_forward(self, mode, a, b, P, keep):
+    def _run_forward(self, mode, a, b, P, keep, force_pack=False):
         st = self._state()
-        self._pack(st)
+        self._pack(st, force_pack)
         pl = self._plan
         dev = st["device"]
         n_tiles = (P + L.TILE_ROWS - 1) // L.TILE_ROWS

@@ -94,8 +94,8 @@ def train_step(H, W, focal, batch_rays: Tensor, target_s: Tensor, target_depth: 
                perturb: float = 1., raw_noise_std: float = 1., white_bkgd: bool = False, lindisp: bool = False,
                ndc: bool = True, near: float = 0., far: float = 1., depth_lambda: float = 0.,
                depth_importance: float = 1., ray_weights: Optional[Tensor] = None, depth_mode: str = "mse",
-               coarse_loss: bool = True, world_size: int = 1, group=None, _rng: Optional[Dict[str, Tensor]] = None
-               ) -> Dict[str, Tensor]:
+               coarse_loss: bool = True, world_size: int = 1, group=None, _rng: Optional[Dict[str, Tensor]] = None,
+               _force_pack: bool = False) -> Dict[str, Tensor]:
     """render + loss + backward for one ray batch; fills ``.grad`` of both networks (averaged over
     ``world_size`` ranks when > 1) and returns the loss terms as 0-d tensors (no host sync).
 
@@ -116,14 +116,14 @@ def train_step(H, W, focal, batch_rays: Tensor, target_s: Tensor, target_depth: 
 
     t_rand = draw("t_rand", "u", (N, N_samples)) if perturb > 0. else None
     z0 = ops.stratified_z(rb, N_samples, t_rand, lindisp)
-    raw0, saved0 = network_fn._run_forward("rays", rb, z0, N * N_samples, keep=True)
+    raw0, saved0 = network_fn._run_forward("rays", rb, z0, N * N_samples, keep=True, force_pack=_force_pack)
     raw0 = raw0.view(N, N_samples, -1)
     noise0 = draw("noise0", "n", (N, N_samples)) if raw_noise_std > 0. else None
     rgb0, disp0, acc0, w0, depth0 = ops.composite(raw0, z0, rays_d, noise0, float(raw_noise_std), bool(white_bkgd))
     u = draw("u", "u", (N, N_importance)) if perturb != 0. else None
     z_samples, z1 = ops.importance_resample(z0, w0, N_importance, u)
     S1 = N_samples + N_importance
-    raw1, saved1 = network_fine._run_forward("rays", rb, z1, N * S1, keep=True)
+    raw1, saved1 = network_fine._run_forward("rays", rb, z1, N * S1, keep=True, force_pack=_force_pack)
     raw1 = raw1.view(N, S1, -1)
     noise1 = draw("noise1", "n", (N, S1)) if raw_noise_std > 0. else None
 
@@ -161,3 +161,55 @@ def _assign_grads(net: NeRF, grads) -> None:
     for p, g in zip(net._ordered_params(), grads):
         if g is not None:
             p.grad = g
+
+
+class GraphedTrainStep:
+    """``train_step`` captured once into a CUDA graph and replayed per iteration (static shapes: N_rand is fixed
+    in the reference's loop).  The ~25 launches of a step (our kernels, the four torch.rand/randn draws, the
+    weight re-pack, memsets) then cost one graph launch; the fp32 -> bf16 weight re-pack is part of the graph,
+    so an ``optimizer.step()`` between replays is picked up.  The gradient all-reduce (world_size > 1) runs
+    after the replay, outside the graph.
+
+        step = GraphedTrainStep(H, W, focal, n_rays, n_rgb, net_c, net_f, depth_lambda=0.01, ...)
+        out = step(batch_rays, target_s, target_depth)        # fills .grad, returns 0-d loss tensors
+    """
+
+    def __init__(self, H, W, focal, n_rays: int, n_rgb: int, network_fn: NeRF, network_fine: NeRF,
+                 world_size: int = 1, group=None, warmup: int = 3, **kw):
+        if kw.get("depth_mode") == "weighted_norm":
+            raise NotImplementedError("weighted_norm needs max(target_depth) on the host; use train_step")
+        dev = next(network_fn.parameters()).device
+        self.world_size, self.group = world_size, group
+        self.nets = (network_fn, network_fine)
+        self.rays = torch.zeros(2, n_rays, 3, device=dev)
+        self.rays[1, :, 2] = -1.0                                  # any valid direction for the warm-up passes
+        self.target_s = torch.zeros(n_rgb, 3, device=dev)
+        self.target_depth = torch.zeros(n_rays - n_rgb, device=dev)
+        self.ray_weights = torch.ones(n_rays - n_rgb, device=dev) if kw.pop("use_ray_weights", False) else None
+        args = (H, W, focal, self.rays, self.target_s, self.target_depth, n_rgb, network_fn, network_fine)
+        kw = dict(kw, ray_weights=self.ray_weights, world_size=1, _force_pack=True)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(max(warmup, 1)):
+                train_step(*args, **kw)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = train_step(*args, **kw)
+        self._grads = [(p, p.grad) for net in self.nets for p in net.parameters()]
+
+    def __call__(self, batch_rays: Tensor, target_s: Tensor, target_depth: Optional[Tensor] = None,
+                 ray_weights: Optional[Tensor] = None) -> Dict[str, Tensor]:
+        self.rays.copy_(batch_rays, non_blocking=True)
+        self.target_s.copy_(target_s, non_blocking=True)
+        if target_depth is not None:
+            self.target_depth.copy_(target_depth, non_blocking=True)
+        if ray_weights is not None and self.ray_weights is not None:
+            self.ray_weights.copy_(ray_weights, non_blocking=True)
+        self.graph.replay()
+        for p, g in self._grads:          # survive optimizer.zero_grad(set_to_none=True)
+            p.grad = g
+        if self.world_size > 1:
+            allreduce_gradients([p for p, _ in self._grads], self.world_size, self.group)
+        return self.out

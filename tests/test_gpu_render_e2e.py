@@ -194,3 +194,30 @@ def test_fused_train_step_matches_drop_in_route(mode):
             worst = max(worst, rel_l2(p.grad, ref[(tag, n)]))
     print("  worst per-tensor rel-L2 between the two routes: %.3e" % worst)
     assert worst <= 2e-3      # identical kernels; only fp32 atomics ordering and loss-scalar rounding differ
+
+
+def test_graphed_train_step_matches_eager_and_tracks_weight_updates():
+    """CUDA-graph replay of train_step: same gradients as the eager call on the same inputs (injected draws are
+    not possible inside a graph, so perturb = noise = 0), and a weight update between replays is picked up."""
+    n_rgb, n_dep = 128, 128
+    net_c, pc, spec_c, net_f, pf, spec_f, ro, rd, rng, tgt, dep = _case(n_rgb, n_dep, 41, False, False)
+    d = dn()
+    rays = torch.stack([ro, rd], 0).to(DEV)
+    kw = dict(N_samples=64, N_importance=64, perturb=0., raw_noise_std=0., depth_lambda=0.01, depth_importance=1.)
+    out = d.train_step(H, W, FOCAL, rays, tgt.to(DEV), dep.to(DEV), n_rgb, net_c, net_f, **kw)
+    ref = [p.grad.clone() for p in list(net_c.parameters()) + list(net_f.parameters())]
+    ref_loss = out["loss"].item()
+    step = d.GraphedTrainStep(H, W, FOCAL, n_rgb + n_dep, n_rgb, net_c, net_f, **kw)
+    for rep in range(2):
+        res = step(rays, tgt.to(DEV), dep.to(DEV))
+        assert abs(res["loss"].item() - ref_loss) <= 1e-5 * abs(ref_loss)
+        worst = max(rel_l2(p.grad, g) for p, g in zip(list(net_c.parameters()) + list(net_f.parameters()), ref))
+        print("  replay %d: worst per-tensor rel-L2 vs eager %.3e" % (rep, worst))
+        assert worst <= 2e-3
+    with torch.no_grad():
+        for p in net_f.parameters():
+            p.mul_(1.05)
+    res2 = step(rays, tgt.to(DEV), dep.to(DEV))
+    out2 = d.train_step(H, W, FOCAL, rays, tgt.to(DEV), dep.to(DEV), n_rgb, net_c, net_f, **kw)
+    assert abs(res2["loss"].item() - out2["loss"].item()) <= 1e-5 * abs(out2["loss"].item())
+    assert abs(res2["loss"].item() - ref_loss) > 1e-7

@@ -30,6 +30,6 @@ torch.cuda.synchronize()
 t = trace.cpu().view(4, 64, 8)
 t0 = int(t[0, 0, 0])
 rel = lambda x: int(x) - t0 if int(x) else -1
-print("keep=%d; per step (gstep): MMA[start, a_ready j0..j4, w_full(last), commit]  EPI_WG0[wait0, acc_full, ld, begin, chunk0, chunk1, arrive]  EPI_WG3[...]" % keep)
+print("keep=%d; per step (gstep): MMA[start, a_ready j0..j4, w_full(last), commit]  EPI_WG0[wait0, acc_full0, ld, computed, acc_full1, s_free, stored, arrived]  EPI_WG3[...]" % keep)
 for gs in range(24):
-    print("g%02d MMA %s | WG0 %s | WG3 %s" % (gs, [rel(x) for x in t[0, gs]], [rel(x) for x in t[1, gs, :7]], [rel(x) for x in t[2, gs, :7]]))
+    print("g%02d MMA %s | WG0 %s | WG3 %s" % (gs, [rel(x) for x in t[0, gs]], [rel(x) for x in t[1, gs, :8]], [rel(x) for x in t[2, gs, :8]]))
