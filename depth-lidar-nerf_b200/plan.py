@@ -38,7 +38,7 @@ class NetShape:
                                       % (8 if self.use_viewdirs else 9))
         if self.input_ch > 64 or self.input_ch_views > 64:
             raise NotImplementedError("encoded inputs wider than 64 channels are not supported")
-        if (self.input_ch - 3) % 6 or (self.input_ch_views - 3) % 6:
+        if (self.input_ch - 3) % 6 or (self.use_viewdirs and (self.input_ch_views - 3) % 6):
             raise NotImplementedError("input widths must be 3+6L (get_embedder)")
         for s in self.skips:
             if s == self.D - 1:
@@ -53,7 +53,7 @@ class NetShape:
 
     @property
     def L_dir(self) -> int:
-        return (self.input_ch_views - 3) // 6
+        return (self.input_ch_views - 3) // 6 if self.use_viewdirs else 0
 
     @property
     def out_ch(self) -> int:

@@ -164,12 +164,13 @@ def compare_grads(named_got, ref_emul, ref_fp32, tag=""):
     return stats
 
 
-def make_net(D, use_viewdirs=True, seed=0, device="cuda", sigma_bias=0.0):
+def make_net(D, use_viewdirs=True, seed=0, device="cuda", sigma_bias=0.0, input_ch_views=27):
     """(package NeRF on device, oracle params dict on CPU, MLPSpec) with identical parameters."""
-    spec = O.MLPSpec(D=D, use_viewdirs=use_viewdirs)
+    spec = O.MLPSpec(D=D, use_viewdirs=use_viewdirs, input_ch_views=input_ch_views)
     p = O.init_params(spec, seed=3407 + D + seed)
     if sigma_bias and use_viewdirs:
         p = O.trained_like(p, sigma_bias)
-    net = dn().NeRF(D=D, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=use_viewdirs)
+    net = dn().NeRF(D=D, W=256, input_ch=63, input_ch_views=input_ch_views, output_ch=5, skips=[4],
+                    use_viewdirs=use_viewdirs)
     net.load_state_dict(p)
     return net.to(device), p, spec

@@ -221,3 +221,77 @@ def test_graphed_train_step_matches_eager_and_tracks_weight_updates():
     out2 = d.train_step(H, W, FOCAL, rays, tgt.to(DEV), dep.to(DEV), n_rgb, net_c, net_f, **kw)
     assert abs(res2["loss"].item() - out2["loss"].item()) <= 1e-5 * abs(out2["loss"].item())
     assert abs(res2["loss"].item() - ref_loss) > 1e-7
+
+
+def _oracle_generic(pc, spec_c, pf, spec_f, rb, rng, std, n_imp=64, white=False, lindisp=False, n_samples=64):
+    return O.render_rays(rb, pc, spec_c, pf, spec_f, n_samples, n_imp, rng, raw_noise_std=std, white_bkgd=white,
+                         lindisp=lindisp)
+
+
+@pytest.mark.parametrize("case", ["white_bkgd", "lindisp_no_ndc", "coarse_only", "odd_sizes", "kitti360_shape"])
+def test_render_variants_against_oracle(case):
+    """Edge / variant configurations of render(): white background, lindisp sampling without NDC (general near/far),
+    N_importance = 0 (coarse pass only), ragged sizes (rays not a multiple of anything, 40 + 24 samples), and
+    KITTI-360-shaped rays (94x352, focal 138.14, fractional pixel coordinates, 'sky' depth targets at 1-1e-7)."""
+    d = dn()
+    n = 96 if case != "odd_sizes" else 77
+    Hh, Ww, foc = (94, 352, 138.14) if case == "kitti360_shape" else (H, W, FOCAL)
+    ns, ni = (40, 24) if case == "odd_sizes" else (64, 64)
+    if case == "coarse_only":
+        ni = 0
+    net_c, pc, spec_c = make_net(4, seed=51, sigma_bias=1.0)
+    net_f, pf, spec_f = make_net(8, seed=52, sigma_bias=1.0)
+    ro, rd = O.synth_rays(n, seed=13, H=Hh, W=Ww, focal=foc)
+    ndc = case != "lindisp_no_ndc"
+    near, far = (0., 1.) if ndc else (2., 6.)
+    rng = O.synth_rng(n, ns, ni, seed=13)
+    white, lind = case == "white_bkgd", case == "lindisp_no_ndc"
+    rb = O.pack_rays(Hh, Ww, foc, ro, rd, ndc=ndc, near=near, far=far)
+    ref = _oracle_generic(pc, spec_c, pf if ni else None, spec_f, rb, rng, 1.0, ni, white, lind, ns)
+    q = d.FusedQuery(d.get_embedder(10, 0)[0], d.get_embedder(4, 0)[0], 1 << 16, 10, 4, 0)
+    inj = {k: getattr(rng, k).to(DEV) for k in ("t_rand", "noise0", "u", "noise1") if getattr(rng, k) is not None}
+    with torch.no_grad():
+        out = d.render(Hh, Ww, foc, chunk=1 << 20, rays=torch.stack([ro, rd], 0).to(DEV), retraw=True, near=near,
+                       far=far, network_query_fn=q, perturb=1.0, N_importance=ni, network_fine=net_f if ni else None,
+                       N_samples=ns, network_fn=net_c, use_viewdirs=True, white_bkgd=white, raw_noise_std=1.0,
+                       ndc=ndc, lindisp=lind, _rng=inj)
+    rgb, disp, acc, depth, extras = out
+    report(case + " rgb_map", rgb, ref["rgb_map"], atol=2e-2)
+    report(case + " depth_map", depth, ref["depth_map"], atol=2e-2 * max(1.0, far))
+    report(case + " acc_map", acc, ref["acc_map"], atol=2e-2)
+    assert extras["raw"].shape == (n, ns + ni, 4)
+    if ni:
+        report(case + " rgb0", extras["rgb0"], ref["rgb0"], atol=2e-2)
+        assert set(extras) == {"raw", "rgb0", "disp0", "acc0", "depth_map0", "z_std"}
+    else:
+        assert set(extras) == {"raw"}
+    if case == "kitti360_shape":
+        # depth loss on sky targets (1 - 1e-7), all three variants of run_nerf.py:1503-1524 stay finite
+        tgt, dep = O.synth_targets(n // 2, n - n // 2, seed=2)
+        dep[:8] = 1.0 - 1e-7
+        for mode in ("mse", "weighted", "relative"):
+            res = d.train_step(Hh, Ww, foc, torch.stack([ro, rd], 0).to(DEV), tgt.to(DEV), dep.to(DEV), n // 2, net_c,
+                               net_f, depth_lambda=0.01, depth_mode=mode,
+                               ray_weights=torch.ones(n - n // 2, device=DEV) if mode == "weighted" else None, _rng=inj)
+            assert torch.isfinite(res["loss"]) and all(torch.isfinite(p.grad).all() for p in net_f.parameters())
+
+
+def test_render_without_viewdirs_against_oracle():
+    d = dn()
+    n = 64
+    # create_nerf passes input_ch_views = 0 when use_viewdirs is off (run_nerf.py:394-397)
+    net_c, pc, spec_c = make_net(4, use_viewdirs=False, seed=61, input_ch_views=0)
+    net_f, pf, spec_f = make_net(8, use_viewdirs=False, seed=62, input_ch_views=0)
+    ro, rd = O.synth_rays(n, seed=14)
+    rng = O.synth_rng(n, 64, 64, seed=14, perturb=False, noise=False)
+    rb = O.pack_rays(H, W, FOCAL, ro, rd, use_viewdirs=False)
+    ref = O.render_rays(rb, pc, spec_c, pf, spec_f, 64, 64, rng, raw_noise_std=0.0)
+    q = d.FusedQuery(d.get_embedder(10, 0)[0], None, 1 << 16, 10, 0, 0)
+    with torch.no_grad():
+        rgb, disp, acc, depth, extras = d.render(H, W, FOCAL, chunk=1 << 20, rays=torch.stack([ro, rd], 0).to(DEV),
+                                                 retraw=True, near=0., far=1., network_query_fn=q, perturb=0.,
+                                                 N_importance=64, network_fine=net_f, N_samples=64, network_fn=net_c,
+                                                 use_viewdirs=False, white_bkgd=False, raw_noise_std=0., ndc=True)
+    report("no-viewdirs rgb_map", rgb, ref["rgb_map"], atol=2e-2)
+    report("no-viewdirs depth_map", depth, ref["depth_map"], atol=2e-2)
+    assert extras["raw"].shape == (n, 128, 5)

@@ -13,7 +13,7 @@ run() { # name, pytest args...
 run render tests/test_gpu_render_kernels.py -m gpu
 run mlp_fwd tests/test_gpu_mlp.py -m gpu -k "forward"
 run mlp_bwd_dz tests/test_gpu_mlp.py -m gpu -k "dz_per_layer"
-run mlp_bwd tests/test_gpu_mlp.py -m gpu -k "backward_gradients"
+run mlp_bwd tests/test_gpu_mlp.py -m gpu -k "backward_gradients or full_size"
 run mlp_misc tests/test_gpu_mlp.py -m gpu -k "repacked or unsupported"
 run e2e tests/test_gpu_render_e2e.py -m gpu
 timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke exit=$?" | tee -a gpurun_out/summary.txt
