@@ -358,18 +358,35 @@ def run_ours(args):
                 "flops_basis": "algorithmic unpadded MACs/point (SURVEY §8d) x points per launch"}
 
     # ---- end to end from pinned host memory ------------------------------------------------------------
-    def e2e_step():
+    # The drop-in route keeps every chunk's activations alive for autograd (as the reference does), so above the
+    # ray-chunk size it cannot hold the batch; there the end-to-end number goes through train_step (ray-chunked).
+    big = args.n_rand > dn.default_ray_chunk(net_c, net_f, N_SAMPLES, N_IMPORTANCE)
+    e2e_fn = fused_step if big else step
+    e2e_api = ("dlnerf_b200.train_step(...) (ray-chunked; the drop-in autograd route cannot hold %d rays)" % args.n_rand
+               if big else "dlnerf_b200.render(...) + img2mse + loss.backward() (drop-in path)")
+
+    def e2e_step(fn=None):
         r = host_rays.to(dev, non_blocking=True)
         t1 = host_tgt.to(dev, non_blocking=True)
         t2 = host_dep.to(dev, non_blocking=True)
-        return float(step(r, t1, t2).item())
+        return float((fn or e2e_fn)(r, t1, t2).item())
 
+    h2d = int(host_rays.numel() + host_tgt.numel() + host_dep.numel()) * 4
     for _ in range(3):
         e2e_step()
     ms_e2e = timed(e2e_step, args.steps)
     e2e = {"value": args.n_rand * world / (ms_e2e * 1e-3), "unit": "rays/s", "ms_per_step": ms_e2e,
-           "h2d_bytes_per_step": int(host_rays.numel() + host_tgt.numel() + host_dep.numel()) * 4,
-           "d2h_bytes_per_step": 4, "api": "dlnerf_b200.render(...) + img2mse + loss.backward() (drop-in path)"}
+           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "api": e2e_api}
+    if graphed is not None:
+        # same host-buffer protocol through the CUDA-graph step (pinned host tensors are copied straight into the
+        # graph's static inputs, loss read back with .item())
+        def e2e_graph_step():
+            return float(graphed(host_rays, host_tgt, host_dep)["loss"].item())
+        for _ in range(3):
+            e2e_graph_step()
+        ms_g = timed(e2e_graph_step, args.steps)
+        e2e["graph_route"] = {"value": args.n_rand * world / (ms_g * 1e-3), "unit": "rays/s", "ms_per_step": ms_g,
+                              "api": "dlnerf_b200.GraphedTrainStep(...)(host_rays, host_target_s, host_target_depth)"}
 
     cb = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

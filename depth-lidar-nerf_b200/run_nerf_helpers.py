@@ -193,7 +193,9 @@ class NeRF(nn.Module):
         L.call("dln_mlp_chain", C.byref(pl.fwd), C.byref(args), st["sms"], ops._stream(), tag="mlp_fwd D=%d" % self.D)
         return out, saved
 
-    def _run_backward(self, d_out, saved, P):
+    def _run_backward(self, d_out, saved, P, gflat=None):
+        """dgrad chain + wgrad.  ``gflat`` (flat fp32 [n_params]) accumulates across calls when given (ray-chunked
+        steps); otherwise a zeroed buffer is allocated."""
         st = self._state()
         pl = self._plan
         dev = st["device"]
@@ -208,7 +210,8 @@ class NeRF(nn.Module):
         args.d_out, args.stash, args.masks = d.data_ptr(), stash_b.data_ptr(), masks.data_ptr()
         lib, s = L.lib(), ops._stream()
         L.call("dln_mlp_chain", C.byref(pl.bwd), C.byref(args), st["sms"], s, tag="mlp_dgrad D=%d" % self.D)
-        gflat = torch.zeros(pl.n_params, device=dev, dtype=torch.float32)
+        if gflat is None:
+            gflat = torch.zeros(pl.n_params, device=dev, dtype=torch.float32)
         n_items = len(pl.wgrad)
         splits = int(max(1, min(n_tiles, (2 * st["sms"]) // n_items)))
         L.call("dln_mlp_wgrad", st["items"].data_ptr(), n_items, splits, stash_f.data_ptr(), pl.fwd_slots,

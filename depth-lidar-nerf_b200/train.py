@@ -18,6 +18,7 @@ from typing import Dict, Optional, Sequence
 
 import torch
 
+from . import _lib as L
 from . import ops
 from .run_nerf import FusedQuery
 from .run_nerf_helpers import NeRF, ndc_rays
@@ -88,16 +89,35 @@ def pack_ray_batch(H: int, W: int, focal: float, batch_rays: Tensor, ndc: bool =
     return torch.cat(cols, -1).float().contiguous()
 
 
+def _stash_bytes_per_ray(net: NeRF, n_samples: int) -> int:
+    """HBM a ray needs between forward and backward of `net` (activation stashes of both chains + masks)."""
+    st = net._state()
+    pl = net._plan
+    return n_samples * (pl.fwd_slots + pl.bwd_slots) * (L.SLAB_BYTES // L.TILE_ROWS) + n_samples * pl.mask_slots * 32
+
+
+def default_ray_chunk(network_fn: NeRF, network_fine: NeRF, N_samples: int, N_importance: int,
+                      budget_bytes: int = 48 << 30) -> int:
+    """Largest multiple of 1024 rays whose stashes fit `budget_bytes` (both nets are live at the same time)."""
+    per_ray = _stash_bytes_per_ray(network_fn, N_samples) + _stash_bytes_per_ray(network_fine, N_samples + N_importance)
+    return max(1024, (budget_bytes // per_ray) // 1024 * 1024)
+
+
 @torch.no_grad()
 def train_step(H, W, focal, batch_rays: Tensor, target_s: Tensor, target_depth: Optional[Tensor], n_rgb: int,
                network_fn: NeRF, network_fine: NeRF, N_samples: int = 64, N_importance: int = 64,
                perturb: float = 1., raw_noise_std: float = 1., white_bkgd: bool = False, lindisp: bool = False,
                ndc: bool = True, near: float = 0., far: float = 1., depth_lambda: float = 0.,
                depth_importance: float = 1., ray_weights: Optional[Tensor] = None, depth_mode: str = "mse",
-               coarse_loss: bool = True, world_size: int = 1, group=None, _rng: Optional[Dict[str, Tensor]] = None,
-               _force_pack: bool = False) -> Dict[str, Tensor]:
+               coarse_loss: bool = True, world_size: int = 1, group=None, ray_chunk: Optional[int] = None,
+               _rng: Optional[Dict[str, Tensor]] = None, _force_pack: bool = False) -> Dict[str, Tensor]:
     """render + loss + backward for one ray batch; fills ``.grad`` of both networks (averaged over
     ``world_size`` ranks when > 1) and returns the loss terms as 0-d tensors (no host sync).
+
+    Batches larger than ``ray_chunk`` rays (default: what fits 48 GB of activation stash, ~28 k rays for the
+    D=4/D=8 pair) are processed chunk by chunk -- each chunk a slice of the RGB rays plus the matching slice of
+    the depth rays, full forward + backward, gradients accumulated in the same flat fp32 buffers -- which is
+    the same sum as the unchunked step (config E: N_rand 16 k ... 256 k).
 
     Random draws follow the reference's order (rand jitter, randn coarse noise, rand u, randn fine noise);
     ``_rng`` (tests) injects them."""
@@ -105,28 +125,8 @@ def train_step(H, W, focal, batch_rays: Tensor, target_s: Tensor, target_depth: 
         raise NotImplementedError("train_step implements the coarse + fine configuration every shipped config uses")
     rb = pack_ray_batch(H, W, focal, batch_rays, ndc, near, far, network_fn.use_viewdirs)
     N, dev = rb.shape[0], rb.device
-    rays_d = rb[:, 3:6].contiguous()
+    network_fn._state(), network_fine._state()          # builds the plans / flat parameter buffers
     n_dep = N - n_rgb
-    rng = _rng or {}
-
-    def draw(name, kind, shape):
-        if name in rng:
-            return rng[name]
-        return (torch.rand if kind == "u" else torch.randn)(shape, device=dev)
-
-    t_rand = draw("t_rand", "u", (N, N_samples)) if perturb > 0. else None
-    z0 = ops.stratified_z(rb, N_samples, t_rand, lindisp)
-    raw0, saved0 = network_fn._run_forward("rays", rb, z0, N * N_samples, keep=True, force_pack=_force_pack)
-    raw0 = raw0.view(N, N_samples, -1)
-    noise0 = draw("noise0", "n", (N, N_samples)) if raw_noise_std > 0. else None
-    rgb0, disp0, acc0, w0, depth0 = ops.composite(raw0, z0, rays_d, noise0, float(raw_noise_std), bool(white_bkgd))
-    u = draw("u", "u", (N, N_importance)) if perturb != 0. else None
-    z_samples, z1 = ops.importance_resample(z0, w0, N_importance, u)
-    S1 = N_samples + N_importance
-    raw1, saved1 = network_fine._run_forward("rays", rb, z1, N * S1, keep=True, force_pack=_force_pack)
-    raw1 = raw1.view(N, S1, -1)
-    noise1 = draw("noise1", "n", (N, S1)) if raw_noise_std > 0. else None
-
     mode = _DEPTH_MODES[depth_mode]
     use_depth = target_depth is not None and n_dep > 0 and depth_lambda != 0.
     depth_norm = float(target_depth.max()) if (use_depth and mode == 2) else 1.0
@@ -136,16 +136,60 @@ def train_step(H, W, focal, batch_rays: Tensor, target_s: Tensor, target_depth: 
     tgt = ops._f32(target_s, "train_step")
     tdep = ops._f32(target_depth, "train_step") if use_depth else None
     rw = ops._f32(ray_weights, "train_step") if (use_depth and ray_weights is not None) else None
-    # fine pass: colour loss on the RGB rays, depth loss on the depth rays (run_nerf.py:1461, :1500-1524)
-    d_raw1 = ops.composite_bwd_fused_loss(raw1, z1, rays_d, noise1, raw_noise_std, white_bkgd, tgt, tdep, rw, n_rgb,
-                                          coef_rgb, coef_dep, mode, depth_norm, sums[0:2])
-    grads_f = network_fine._run_backward(d_raw1, saved1, N * S1)
+    S1 = N_samples + N_importance
+    if ray_chunk is None:
+        ray_chunk = default_ray_chunk(network_fn, network_fine, N_samples, N_importance)
+    n_chunks = max(1, -(-N // max(int(ray_chunk), 1)))
+    gacc = [torch.zeros(net._plan.n_params, device=dev, dtype=torch.float32) for net in (network_fn, network_fine)]
+
+    for c in range(n_chunks):
+        if n_chunks == 1:
+            rb_c, tgt_c, tdep_c, rw_c, nr_c, rng = rb, tgt, tdep, rw, n_rgb, (_rng or {})
+        else:
+            r0, r1 = shard_bounds(n_rgb, c, n_chunks)
+            d0, d1 = shard_bounds(n_dep, c, n_chunks)
+            pick = lambda t: torch.cat([t[r0:r1], t[n_rgb + d0:n_rgb + d1]], 0)     # noqa: E731
+            rb_c, tgt_c, nr_c = pick(rb), tgt[r0:r1], r1 - r0
+            tdep_c = tdep[d0:d1] if tdep is not None else None
+            rw_c = rw[d0:d1] if rw is not None else None
+            rng = {k: pick(v) for k, v in (_rng or {}).items()}
+            if rb_c.shape[0] == 0:
+                continue
+        Nc = rb_c.shape[0]
+        rays_d = rb_c[:, 3:6].contiguous()
+
+        def draw(name, kind, shape):
+            if name in rng:
+                return rng[name]
+            return (torch.rand if kind == "u" else torch.randn)(shape, device=dev)
+
+        t_rand = draw("t_rand", "u", (Nc, N_samples)) if perturb > 0. else None
+        z0 = ops.stratified_z(rb_c, N_samples, t_rand, lindisp)
+        raw0, saved0 = network_fn._run_forward("rays", rb_c, z0, Nc * N_samples, keep=True,
+                                               force_pack=_force_pack and c == 0)
+        raw0 = raw0.view(Nc, N_samples, -1)
+        noise0 = draw("noise0", "n", (Nc, N_samples)) if raw_noise_std > 0. else None
+        rgb0, disp0, acc0, w0, depth0 = ops.composite(raw0, z0, rays_d, noise0, float(raw_noise_std),
+                                                      bool(white_bkgd))
+        u = draw("u", "u", (Nc, N_importance)) if perturb != 0. else None
+        z_samples, z1 = ops.importance_resample(z0, w0, N_importance, u)
+        raw1, saved1 = network_fine._run_forward("rays", rb_c, z1, Nc * S1, keep=True,
+                                                 force_pack=_force_pack and c == 0)
+        raw1 = raw1.view(Nc, S1, -1)
+        noise1 = draw("noise1", "n", (Nc, S1)) if raw_noise_std > 0. else None
+        # fine pass: colour loss on the RGB rays, depth loss on the depth rays (run_nerf.py:1461, :1500-1524)
+        d_raw1 = ops.composite_bwd_fused_loss(raw1, z1, rays_d, noise1, raw_noise_std, white_bkgd, tgt_c, tdep_c,
+                                              rw_c, nr_c, coef_rgb, coef_dep, mode, depth_norm, sums[0:2])
+        grads_f = network_fine._run_backward(d_raw1, saved1, Nc * S1, gflat=gacc[1])
+        del saved1, d_raw1, raw1
+        if coarse_loss:
+            # coarse pass: colour loss only (run_nerf.py:1759-1761); depth_map0 is unsupervised
+            d_raw0 = ops.composite_bwd_fused_loss(raw0, z0, rays_d, noise0, raw_noise_std, white_bkgd, tgt_c, None,
+                                                  None, nr_c, coef_rgb, 0.0, 0, 1.0, sums[2:4])
+            grads_c = network_fn._run_backward(d_raw0, saved0, Nc * N_samples, gflat=gacc[0])
+        del saved0
     _assign_grads(network_fine, grads_f)
     if coarse_loss:
-        # coarse pass: colour loss only (run_nerf.py:1759-1761); depth_map0 is unsupervised
-        d_raw0 = ops.composite_bwd_fused_loss(raw0, z0, rays_d, noise0, raw_noise_std, white_bkgd, tgt, None, None,
-                                              n_rgb, coef_rgb, 0.0, 0, 1.0, sums[2:4])
-        grads_c = network_fn._run_backward(d_raw0, saved0, N * N_samples)
         _assign_grads(network_fn, grads_c)
     if world_size > 1:
         allreduce_gradients(list(network_fn.parameters()) + list(network_fine.parameters()), world_size, group)
