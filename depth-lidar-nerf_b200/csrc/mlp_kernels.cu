@@ -45,6 +45,8 @@ struct ChainSmall {
   uint32_t pad_;
   alignas(16) float bias[kMaxBiasFloats];   // bias vectors of all steps, packed back to back (forward only)
   float part[4][4][128];                    // per-warpgroup partial head sums: rgb 0..2 (or out 0..3), sigma 3
+  uint64_t ld_done;                         // all 16 epilogue warps have read accumulator columns 0..127 of this step
+  uint32_t tr[48];                          // debug timeline (see trace_ev)
 };
 
 constexpr size_t kChainSmemBytes = (size_t)kNumSlabs * kSlab + (size_t)kNumStages * kStageBytes + sizeof(ChainSmall) + 1024;
@@ -207,10 +209,16 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], const float* 
   pack32<kRelu>(f, pk);
 }
 
-// debug timeline: trace[role][gstep][event] = SM clock (CTA 0 only, first 64 steps)
-__device__ __forceinline__ void trace_ev(long long* trace, int role, uint32_t gstep, int ev) {
-  if (trace != nullptr && blockIdx.x == 0 && gstep < 64 && (role != 0 || (threadIdx.x & 31) == 0))
-    trace[(role * 64 + gstep) * 8 + ev] = clock64();
+// debug timeline of CTA 0: %clock at up to 8 events of 3 roles (0 MMA warp, 1 / 2 one epilogue thread of
+// warpgroup 0 / 3) for the two steps gstep = kTraceStep0, +1, kept in shared memory (a clock read + one st.shared
+// per event, so the traced schedule is the real one) and copied to args.trace when the kernel ends.
+constexpr uint32_t kTraceStep0 = 12;
+__device__ __forceinline__ void trace_ev(ChainSmall* sm, const long long* trace, int role, uint32_t gstep, int ev) {
+  if (trace != nullptr && blockIdx.x == 0 && gstep - kTraceStep0 < 2u && (role != 0 || (threadIdx.x & 31) == 0)) {
+    uint32_t c;
+    asm volatile("mov.u32 %0, %%clock;" : "=r"(c));
+    sm->tr[role * 16 + (gstep - kTraceStep0) * 8 + ev] = c;
+  }
 }
 
 struct ProdTrack {
@@ -237,7 +245,8 @@ __global__ void __launch_bounds__(kThreads, 1)
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kNumStages; ++i) mbar_init(&sm->w_full[i], 1), mbar_init(&sm->w_empty[i], 1);
-    for (int i = 0; i < kNumSlabs; ++i) mbar_init(&sm->a_ready[i], i < 4 ? 256 : 128), mbar_init(&sm->s_free[i], 1);
+    for (int i = 0; i < kNumSlabs; ++i) mbar_init(&sm->a_ready[i], i < 4 ? 8 : 4), mbar_init(&sm->s_free[i], 1);   // one arrival per producing warp
+    mbar_init(&sm->ld_done, 16);
     for (int i = 0; i < 4; ++i) mbar_init(&sm->acc_full[i >> 1][i & 1], 1);
     for (int i = 0; i < kNumStages; ++i) mbar_init(&sm->grp_full[i], 1);
     mbar_fence_init();
@@ -297,7 +306,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           const int nhalf = split ? 2 : 1;
           const uint32_t idesc = umma_idesc_bf16(128, split ? 128 : st.n_out, 0, 0);
           const uint32_t stage0 = stage;
-          trace_ev(args.trace, 0, gstep, 0);
+          trace_ev(sm, args.trace, 0, gstep, 0);
           for (int half = 0; half < nhalf; ++half) {
             const uint32_t d_tmem = tmem_base + (gstep & 1) * 256 + half * 128;
             stage = stage0;
@@ -305,7 +314,7 @@ __global__ void __launch_bounds__(kThreads, 1)
               const int slab = st.kslab[j];
               if (half == 0) {
                 mbar_wait(&sm->a_ready[slab], ((par >> slab) & 1) ^ 1);   // last production completed
-                if (j < 5) trace_ev(args.trace, 0, gstep, 1 + j);
+                if (j < 5) trace_ev(sm, args.trace, 0, gstep, 1 + j);
                 if ((j & 3) == 0) {          // the helper thread has seen w_full of this group of <=4 stages
                   mbar_wait(&sm->grp_full[grp & (kNumStages - 1)], (grp / kNumStages) & 1);
                   ++grp;
@@ -313,15 +322,29 @@ __global__ void __launch_bounds__(kThreads, 1)
                 tc_fence_after();
               }
               // descriptors differ only in the 14-bit start-address field: +2 (= 32 B) per K=16 step
-              const uint64_t ad = desc_k | (uint64_t)((slab_addr0 + slab * kSlab) >> 4);
               const uint64_t bd = desc_k | (uint64_t)((ring_addr0 + stage * kStageBytes + half * (kStageBytes / 2)) >> 4);
               const int kc = st.kcnt[j];
-              if (elect_one()) {
-                umma_bf16(d_tmem, ad, bd, idesc, j != 0);
-                if (kc > 1) umma_bf16(d_tmem, ad + 2, bd + 2, idesc, 1);
-                if (kc > 2) umma_bf16(d_tmem, ad + 4, bd + 4, idesc, 1);
-                if (kc > 3) umma_bf16(d_tmem, ad + 6, bd + 6, idesc, 1);
-                if (half == nhalf - 1) umma_commit(&sm->w_empty[stage]);
+              if (slab < 4) {
+                // activations of the previous step: bf16 pairs in tensor memory, written in place over the low
+                // columns of the accumulator buffer the previous step used (K slab j = columns [32 slab, +32))
+                const uint32_t at = tmem_base + ((gstep + 1) & 1) * 256 + slab * 32;
+                if (elect_one()) {
+                  umma_bf16_ts(d_tmem, at, bd, idesc, j != 0);
+                  if (kc > 1) umma_bf16_ts(d_tmem, at + 8, bd + 2, idesc, 1);
+                  if (kc > 2) umma_bf16_ts(d_tmem, at + 16, bd + 4, idesc, 1);
+                  if (kc > 3) umma_bf16_ts(d_tmem, at + 24, bd + 6, idesc, 1);
+                  if (half == nhalf - 1) umma_commit(&sm->w_empty[stage]);
+                }
+              } else {
+                // encoded position / direction (fwd) or d_raw (bwd): a shared-memory slab
+                const uint64_t ad = desc_k | (uint64_t)((slab_addr0 + slab * kSlab) >> 4);
+                if (elect_one()) {
+                  umma_bf16(d_tmem, ad, bd, idesc, j != 0);
+                  if (kc > 1) umma_bf16(d_tmem, ad + 2, bd + 2, idesc, 1);
+                  if (kc > 2) umma_bf16(d_tmem, ad + 4, bd + 4, idesc, 1);
+                  if (kc > 3) umma_bf16(d_tmem, ad + 6, bd + 6, idesc, 1);
+                  if (half == nhalf - 1) umma_commit(&sm->w_empty[stage]);
+                }
               }
               __syncwarp();
               if (++stage == kNumStages) stage = 0;
@@ -331,9 +354,9 @@ __global__ void __launch_bounds__(kThreads, 1)
               if (!split) umma_commit(&sm->acc_full[gstep & 1][1]);
             }
             __syncwarp();
-            if (half == 0) trace_ev(args.trace, 0, gstep, 6);
+            if (half == 0) trace_ev(sm, args.trace, 0, gstep, 6);
           }
-          trace_ev(args.trace, 0, gstep, 7);
+          trace_ev(sm, args.trace, 0, gstep, 7);
           par ^= step_out_mask(st);
           if (s == reload_step) par ^= 0x10u;
         }
@@ -346,32 +369,52 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
     }
   } else if (warp == 2) {
-    // ===================================================== stash writers (training only): lane i owns slab i and copies
-    // every production of it to the global stash with one bulk smem -> global copy; the five lanes work
-    // independently (bulk-copy groups are tracked per thread), so the copies of one layer run concurrently
-    if (lane < kNumSlabs && keep) {
-      const int slab = lane;
+    // ===================================================== stash writer (training only): ONE lane walks the slab
+    // productions in program order and copies each to the global stash with a bulk smem -> global copy.  (Five
+    // lanes spinning on five different barriers in one warp serialise each other: the divergent paths are only
+    // switched every few hundred cycles, which showed up as late s_free arrivals in the epilogue.)  The copies
+    // still overlap: slab X is released (s_free) once the NEXT copy has been issued and X's group has finished
+    // reading shared memory; the tail of a tile is flushed so the next tile's prologue never waits on it.
+    if (lane == 0 && keep) {
       uint32_t par = 0;
+      int pending = -1;
       const uint32_t pmask = prologue_mask(prog);
       uint8_t* stash = reinterpret_cast<uint8_t*>(args.stash);
       for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         uint8_t* tbase = stash + (size_t)tile * prog.stash_slots * kSlab;
-        auto handle = [&](int slot) {
-          mbar_wait(&sm->a_ready[slab], par);
-          par ^= 1u;
+        auto flush = [&]() {
+          if (pending >= 0) {
+            bulk_wait_read0();
+            mbar_arrive(&sm->s_free[pending]);
+            pending = -1;
+          }
+        };
+        auto handle = [&](int slab, int slot) {
+          if (pending == slab) flush();
+          mbar_wait(&sm->a_ready[slab], (par >> slab) & 1u);
+          par ^= 1u << slab;
           if (slot >= 0) {
             bulk_s2g(tbase + (size_t)slot * kSlab, slabs + slab * kSlab, kSlab);
             bulk_commit();
-            bulk_wait_read0();
+            if (pending >= 0) {
+              bulk_wait_read1();
+              mbar_arrive(&sm->s_free[pending]);
+            }
+            pending = slab;
+          } else {
+            mbar_arrive(&sm->s_free[slab]);
           }
-          mbar_arrive(&sm->s_free[slab]);
         };
-        if ((pmask >> slab) & 1) handle(slab == 4 ? 0 : prog.pro_slot + slab);
+        for (int slab = 0; slab < kNumSlabs; ++slab)
+          if ((pmask >> slab) & 1) handle(slab, slab == 4 ? 0 : prog.pro_slot + slab);
         for (int s = 0; s < prog.n_steps; ++s) {
           const DlnChainStep& st = prog.steps[s];
-          if (slab < 4 && ((step_out_mask(st) >> slab) & 1)) handle(st.stash_slot >= 0 ? st.stash_slot + slab : -1);
-          if (slab == 4 && s == reload_step) handle(1);        // encoded direction -> slot 1
+          const uint32_t om = step_out_mask(st);
+          for (int slab = 0; slab < 4; ++slab)
+            if ((om >> slab) & 1) handle(slab, st.stash_slot >= 0 ? st.stash_slot + slab : -1);
+          if (s == reload_step) handle(4, 1);                    // encoded direction -> slot 1
         }
+        flush();
       }
       bulk_wait_all0();
     }
@@ -400,13 +443,17 @@ __global__ void __launch_bounds__(kThreads, 1)
     ProdTrack pt;
     const uint32_t pmask = prologue_mask(prog);
     uint32_t gstep = 0;
+    // Activation slabs 0..3 live in TENSOR MEMORY for the next layer's MMAs; their shared-memory images exist only
+    // as the staging buffer of the stash copies (training), so without a stash they are not written at all.
     auto begin_produce = [&](int slab) {
       if (keep && ((pt.any >> slab) & 1)) mbar_wait(&sm->s_free[slab], ((pt.par >> slab) & 1) ^ 1);
     };
-    auto end_produce = [&](int slab) {
-      fence_async_smem();
+    auto end_produce = [&](int slab) {   // one arrival per warp
+      if (slab < 4) tmem_st_wait();
+      if (slab == 4 || keep) fence_async_smem();
       tc_fence_before();
-      mbar_arrive(&sm->a_ready[slab]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm->a_ready[slab]);
     };
     // one encoded row (position g==0 / direction g==1) for tile row r, fused (rays, z) or pre-encoded (x) input
     auto encoded_row = [&](long long p, bool valid, int which, float (&e)[64]) {
@@ -481,7 +528,13 @@ __global__ void __launch_bounds__(kThreads, 1)
                 }
 #pragma unroll
               for (int i = 0; i < 32; ++i) f[i] = (mk & (1u << i)) ? f[i] : 0.f;
-              store_cols32<false>(slabs, gslot(prog.pro_slot + (cb >> 6)), r, cb, f);
+              uint32_t pk[16];
+              pack32<false>(f, pk);
+              // dZ of the first backward layer -> tensor memory, in the buffer the previous step (last step of the
+              // previous tile) accumulated in; every warp has finished reading its columns 0..127 (ld_done was
+              // waited for by this thread in that step)
+              tmem_st16(tmem_base + ((gstep + 1) & 1) * 256 + lane_addr + 64 * h + 16 * g, pk);
+              if (keep) store_packed32(slabs, r, cb, pk);
               end_produce(cb >> 6);
             }
           }
@@ -510,10 +563,10 @@ __global__ void __launch_bounds__(kThreads, 1)
         const size_t mask_idx = (((size_t)(st.mask_slot < 0 ? 0 : st.mask_slot) * n_tiles + tile) * 4 + g) * 128 + r;
         if (epi >= DLN_EPI_BWD_MASK && st.mask_slot >= 0) mw = reinterpret_cast<const uint2*>(args.masks)[mask_idx];
         const int trole = (et == 0) ? 1 : (et == 384 ? 2 : -1);
-        if (trole > 0) trace_ev(args.trace, trole, gstep, 0);
+        if (trole > 0) trace_ev(sm, args.trace, trole, gstep, 0);
         mbar_wait(&sm->acc_full[gstep & 1][0], (gstep >> 1) & 1);
         tc_fence_after();
-        if (trole > 0) trace_ev(args.trace, trole, gstep, 1);
+        if (trole > 0) trace_ev(sm, args.trace, trole, gstep, 1);
 
         const uint32_t t_acc = tmem_base + (gstep & 1) * 256 + lane_addr;
         const bool relu = (epi == DLN_EPI_RELU || epi == DLN_EPI_RELU_SIGMA || epi == DLN_EPI_RELU_RGB || epi == DLN_EPI_RELU_OUT);
@@ -538,31 +591,41 @@ __global__ void __launch_bounds__(kThreads, 1)
             }
           };
           uint32_t v[32];
-          const int cb0 = 32 * g;                    // chunk 0: slab g>>1 (columns 0..127: first MMA half)
+          const int cb0 = 32 * g;                    // chunk 0: features [32g, +32) of columns 0..127
           tmem_ld32(t_acc + cb0, v);
           tmem_ld_wait();
-          if (trole > 0) trace_ev(args.trace, trole, gstep, 2);
-          dispatch(v, mw.x, mo0, cb0);               // results stay in registers ...
-          if (trole > 0) trace_ev(args.trace, trole, gstep, 3);
-          // ... until the second MMA half has completed too: the activation slabs are updated in place and every
-          // MMA of this layer reads all of them
-          mbar_wait(&sm->acc_full[gstep & 1][1], (gstep >> 1) & 1);
+          // The bf16 outputs are written back IN PLACE over accumulator columns 0..127 (features [128h+32g, +32) ->
+          // columns [64h+16g, +16)), which other warpgroups read in this first chunk: announce our read ...
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sm->ld_done);
+          if (trole > 0) trace_ev(sm, args.trace, trole, gstep, 2);
+          dispatch(v, mw.x, mo0, cb0);
+          if (trole > 0) trace_ev(sm, args.trace, trole, gstep, 3);
+          // ... and wait for everybody else's before the first store
+          mbar_wait(&sm->ld_done, gstep & 1);
           tc_fence_after();
-          if (trole > 0) trace_ev(args.trace, trole, gstep, 4);
-          begin_produce(cb0 >> 6);
-          if (trole > 0) trace_ev(args.trace, trole, gstep, 5);
-          store_packed32(slabs, r, cb0, pk);
-          if (trole > 0) trace_ev(args.trace, trole, gstep, 6);
+          if (trole > 0) trace_ev(sm, args.trace, trole, gstep, 4);
+          tmem_st16(t_acc + 16 * g, pk);
+          if (keep) {
+            begin_produce(cb0 >> 6);
+            if (trole > 0) trace_ev(sm, args.trace, trole, gstep, 5);
+            store_packed32(slabs, r, cb0, pk);
+          }
           end_produce(cb0 >> 6);
-          if (trole > 0) trace_ev(args.trace, trole, gstep, 7);
-          if (st.n_out == 256) {                     // chunk 1: slab 2 + (g>>1)
+          if (trole > 0) trace_ev(sm, args.trace, trole, gstep, 6);
+          if (st.n_out == 256) {                     // chunk 1: features [128 + 32g, +32)
             const int cb1 = 128 + 32 * g;
             tmem_ld32(t_acc + cb1, v);
             tmem_ld_wait();
             dispatch(v, mw.y, mo1, cb1);
-            begin_produce(cb1 >> 6);
-            store_packed32(slabs, r, cb1, pk);
+            tmem_st16(t_acc + 64 + 16 * g, pk);
+            if (keep) {
+              begin_produce(cb1 >> 6);
+              store_packed32(slabs, r, cb1, pk);
+            }
             end_produce(cb1 >> 6);
+            if (trole > 0) trace_ev(sm, args.trace, trole, gstep, 7);
           }
           if (relu && st.mask_slot >= 0 && args.masks != nullptr)
             reinterpret_cast<uint2*>(args.masks)[mask_idx] = make_uint2(mo0, mo1);
@@ -622,6 +685,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, 512);
+  if (args.trace != nullptr && blockIdx.x == 0 && threadIdx.x < 48) args.trace[threadIdx.x] = sm->tr[threadIdx.x];
 }
 
 // ---------------------------------------------------------------------------------------------
