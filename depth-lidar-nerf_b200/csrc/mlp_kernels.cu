@@ -33,6 +33,8 @@ constexpr int kStageBytes = 32768;
 constexpr int kSlab = DLN_SLAB_BYTES;
 constexpr int kNumSlabs = 5;       // 0..3 activations, 4 encoded position -> encoded direction (fwd) / d_raw (bwd)
 constexpr bool kSplitN = false;    // issue 256-wide layers as two N=128 halves (measured slower: the MMA issue cost is per instruction)
+constexpr bool kDirectStash = false;  // epilogue threads write the stash images straight to global memory instead of
+                                      // staging them in smem for bulk copies: parity-green but 50% slower (scattered 16-byte stores)
 constexpr int kMaxBiasFloats = 2432;   // 9 x 256 + 128: netdepth <= 8 with view directions, <= 9 without
 
 struct ChainSmall {
@@ -45,8 +47,7 @@ struct ChainSmall {
   uint32_t pad_;
   alignas(16) float bias[kMaxBiasFloats];   // bias vectors of all steps, packed back to back (forward only)
   float part[4][4][128];                    // per-warpgroup partial head sums: rgb 0..2 (or out 0..3), sigma 3
-  uint64_t ld_done;                         // all 16 epilogue warps have read accumulator columns 0..127 of this step
-  uint32_t tr[48];                          // debug timeline (see trace_ev)
+  uint32_t tr[64];                          // debug timeline (see trace_ev)
 };
 
 constexpr size_t kChainSmemBytes = (size_t)kNumSlabs * kSlab + (size_t)kNumStages * kStageBytes + sizeof(ChainSmall) + 1024;
@@ -246,7 +247,6 @@ __global__ void __launch_bounds__(kThreads, 1)
   if (threadIdx.x == 0) {
     for (int i = 0; i < kNumStages; ++i) mbar_init(&sm->w_full[i], 1), mbar_init(&sm->w_empty[i], 1);
     for (int i = 0; i < kNumSlabs; ++i) mbar_init(&sm->a_ready[i], i < 4 ? 8 : 4), mbar_init(&sm->s_free[i], 1);   // one arrival per producing warp
-    mbar_init(&sm->ld_done, 16);
     for (int i = 0; i < 4; ++i) mbar_init(&sm->acc_full[i >> 1][i & 1], 1);
     for (int i = 0; i < kNumStages; ++i) mbar_init(&sm->grp_full[i], 1);
     mbar_fence_init();
@@ -325,14 +325,16 @@ __global__ void __launch_bounds__(kThreads, 1)
               const uint64_t bd = desc_k | (uint64_t)((ring_addr0 + stage * kStageBytes + half * (kStageBytes / 2)) >> 4);
               const int kc = st.kcnt[j];
               if (slab < 4) {
-                // activations of the previous step: bf16 pairs in tensor memory, written in place over the low
-                // columns of the accumulator buffer the previous step used (K slab j = columns [32 slab, +32))
-                const uint32_t at = tmem_base + ((gstep + 1) & 1) * 256 + slab * 32;
+                // activations of the previous step: bf16 pairs in tensor memory, written in place over the
+                // accumulator buffer the previous step used -- each 32-feature group [32q, +32) packed into the
+                // first 16 of its own 32 accumulator columns, so K step kk of slab j starts at column
+                // 64 j + 32 (kk >> 1) + 8 (kk & 1)
+                const uint32_t at = tmem_base + ((gstep + 1) & 1) * 256 + slab * 64;
                 if (elect_one()) {
                   umma_bf16_ts(d_tmem, at, bd, idesc, j != 0);
                   if (kc > 1) umma_bf16_ts(d_tmem, at + 8, bd + 2, idesc, 1);
-                  if (kc > 2) umma_bf16_ts(d_tmem, at + 16, bd + 4, idesc, 1);
-                  if (kc > 3) umma_bf16_ts(d_tmem, at + 24, bd + 6, idesc, 1);
+                  if (kc > 2) umma_bf16_ts(d_tmem, at + 32, bd + 4, idesc, 1);
+                  if (kc > 3) umma_bf16_ts(d_tmem, at + 40, bd + 6, idesc, 1);
                   if (half == nhalf - 1) umma_commit(&sm->w_empty[stage]);
                 }
               } else {
@@ -375,8 +377,8 @@ __global__ void __launch_bounds__(kThreads, 1)
     // switched every few hundred cycles, which showed up as late s_free arrivals in the epilogue.)  The copies
     // still overlap: slab X is released (s_free) once the NEXT copy has been issued and X's group has finished
     // reading shared memory; the tail of a tile is flushed so the next tile's prologue never waits on it.
-    if (lane == 0 && keep) {
-      uint32_t par = 0;
+    if (lane == 0 && keep && !kDirectStash) {
+      uint32_t par = 0, sgstep = 0, pending_step = 0;
       int pending = -1;
       const uint32_t pmask = prologue_mask(prog);
       uint8_t* stash = reinterpret_cast<uint8_t*>(args.stash);
@@ -393,21 +395,24 @@ __global__ void __launch_bounds__(kThreads, 1)
           if (pending == slab) flush();
           mbar_wait(&sm->a_ready[slab], (par >> slab) & 1u);
           par ^= 1u << slab;
+          if (slab < 4) trace_ev(sm, args.trace, 3, sgstep, slab);
           if (slot >= 0) {
             bulk_s2g(tbase + (size_t)slot * kSlab, slabs + slab * kSlab, kSlab);
             bulk_commit();
             if (pending >= 0) {
               bulk_wait_read1();
               mbar_arrive(&sm->s_free[pending]);
+              if (pending < 4) trace_ev(sm, args.trace, 3, pending_step, 4 + pending);
             }
             pending = slab;
+            pending_step = sgstep;
           } else {
             mbar_arrive(&sm->s_free[slab]);
           }
         };
         for (int slab = 0; slab < kNumSlabs; ++slab)
           if ((pmask >> slab) & 1) handle(slab, slab == 4 ? 0 : prog.pro_slot + slab);
-        for (int s = 0; s < prog.n_steps; ++s) {
+        for (int s = 0; s < prog.n_steps; ++s, ++sgstep) {
           const DlnChainStep& st = prog.steps[s];
           const uint32_t om = step_out_mask(st);
           for (int slab = 0; slab < 4; ++slab)
@@ -446,11 +451,11 @@ __global__ void __launch_bounds__(kThreads, 1)
     // Activation slabs 0..3 live in TENSOR MEMORY for the next layer's MMAs; their shared-memory images exist only
     // as the staging buffer of the stash copies (training), so without a stash they are not written at all.
     auto begin_produce = [&](int slab) {
-      if (keep && ((pt.any >> slab) & 1)) mbar_wait(&sm->s_free[slab], ((pt.par >> slab) & 1) ^ 1);
+      if (!kDirectStash && keep && ((pt.any >> slab) & 1)) mbar_wait(&sm->s_free[slab], ((pt.par >> slab) & 1) ^ 1);
     };
     auto end_produce = [&](int slab) {   // one arrival per warp
       if (slab < 4) tmem_st_wait();
-      if (slab == 4 || keep) fence_async_smem();
+      if (slab == 4 || (keep && !kDirectStash)) fence_async_smem();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm->a_ready[slab]);
@@ -487,7 +492,8 @@ __global__ void __launch_bounds__(kThreads, 1)
       const long long p = tile * DLN_TILE_ROWS + r;
       const bool valid = p < args.P;
       float dsig = 0.f;
-      auto gslot = [&](int) -> uint8_t* { return nullptr; };
+      uint8_t* const gtile = keep ? reinterpret_cast<uint8_t*>(args.stash) + (size_t)tile * prog.stash_slots * kSlab : nullptr;
+      auto gslot = [&](int slot) -> uint8_t* { return (kDirectStash && keep) ? gtile + (size_t)slot * kSlab : nullptr; };
       // ------------------------------------------------------------------ prologue
       if (!kBwd) {
         if (g == 0) {
@@ -531,10 +537,9 @@ __global__ void __launch_bounds__(kThreads, 1)
               uint32_t pk[16];
               pack32<false>(f, pk);
               // dZ of the first backward layer -> tensor memory, in the buffer the previous step (last step of the
-              // previous tile) accumulated in; every warp has finished reading its columns 0..127 (ld_done was
-              // waited for by this thread in that step)
-              tmem_st16(tmem_base + ((gstep + 1) & 1) * 256 + lane_addr + 64 * h + 16 * g, pk);
-              if (keep) store_packed32(slabs, r, cb, pk);
+              // previous tile) accumulated in, over columns only this thread reads
+              tmem_st16(tmem_base + ((gstep + 1) & 1) * 256 + lane_addr + cb, pk);
+              if (keep) store_packed32(kDirectStash ? gtile + (size_t)prog.pro_slot * kSlab : slabs, r, cb, pk);
               end_produce(cb >> 6);
             }
           }
@@ -563,7 +568,6 @@ __global__ void __launch_bounds__(kThreads, 1)
         const size_t mask_idx = (((size_t)(st.mask_slot < 0 ? 0 : st.mask_slot) * n_tiles + tile) * 4 + g) * 128 + r;
         if (epi >= DLN_EPI_BWD_MASK && st.mask_slot >= 0) mw = reinterpret_cast<const uint2*>(args.masks)[mask_idx];
         const int trole = (et == 0) ? 1 : (et == 384 ? 2 : -1);
-        if (trole > 0) trace_ev(sm, args.trace, trole, gstep, 0);
         mbar_wait(&sm->acc_full[gstep & 1][0], (gstep >> 1) & 1);
         tc_fence_after();
         if (trole > 0) trace_ev(sm, args.trace, trole, gstep, 1);
@@ -594,24 +598,20 @@ __global__ void __launch_bounds__(kThreads, 1)
           const int cb0 = 32 * g;                    // chunk 0: features [32g, +32) of columns 0..127
           tmem_ld32(t_acc + cb0, v);
           tmem_ld_wait();
-          // The bf16 outputs are written back IN PLACE over accumulator columns 0..127 (features [128h+32g, +32) ->
-          // columns [64h+16g, +16)), which other warpgroups read in this first chunk: announce our read ...
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&sm->ld_done);
+          // The bf16 outputs go back IN PLACE into tensor memory for the next layer's MMAs: features [cb, cb+32) are
+          // packed into columns [cb, cb+16) of this thread's lane -- columns nobody else reads, so no cross-warp
+          // ordering is needed.
           if (trole > 0) trace_ev(sm, args.trace, trole, gstep, 2);
           dispatch(v, mw.x, mo0, cb0);
           if (trole > 0) trace_ev(sm, args.trace, trole, gstep, 3);
-          // ... and wait for everybody else's before the first store
-          mbar_wait(&sm->ld_done, gstep & 1);
-          tc_fence_after();
-          if (trole > 0) trace_ev(sm, args.trace, trole, gstep, 4);
-          tmem_st16(t_acc + 16 * g, pk);
           if (keep) {
             begin_produce(cb0 >> 6);
             if (trole > 0) trace_ev(sm, args.trace, trole, gstep, 5);
-            store_packed32(slabs, r, cb0, pk);
+            if (!kDirectStash) store_packed32(slabs, r, cb0, pk);
+            else if (st.stash_slot >= 0) store_packed32(gtile + (size_t)st.stash_slot * kSlab, r, cb0, pk);
           }
+          if (trole > 0) trace_ev(sm, args.trace, trole, gstep, 0);
+          tmem_st16(t_acc + cb0, pk);
           end_produce(cb0 >> 6);
           if (trole > 0) trace_ev(sm, args.trace, trole, gstep, 6);
           if (st.n_out == 256) {                     // chunk 1: features [128 + 32g, +32)
@@ -619,10 +619,11 @@ __global__ void __launch_bounds__(kThreads, 1)
             tmem_ld32(t_acc + cb1, v);
             tmem_ld_wait();
             dispatch(v, mw.y, mo1, cb1);
-            tmem_st16(t_acc + 64 + 16 * g, pk);
+            tmem_st16(t_acc + cb1, pk);
             if (keep) {
               begin_produce(cb1 >> 6);
-              store_packed32(slabs, r, cb1, pk);
+              if (!kDirectStash) store_packed32(slabs, r, cb1, pk);
+              else if (st.stash_slot >= 0) store_packed32(gtile + (size_t)st.stash_slot * kSlab, r, cb1, pk);
             }
             end_produce(cb1 >> 6);
             if (trole > 0) trace_ev(sm, args.trace, trole, gstep, 7);
@@ -685,7 +686,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, 512);
-  if (args.trace != nullptr && blockIdx.x == 0 && threadIdx.x < 48) args.trace[threadIdx.x] = sm->tr[threadIdx.x];
+  if (args.trace != nullptr && blockIdx.x == 0 && threadIdx.x < 64) args.trace[threadIdx.x] = sm->tr[threadIdx.x];
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -27,11 +27,11 @@ for it in range(3):
     args.trace = trace.data_ptr() if it == 2 else None
     L.check(L.lib().dln_mlp_chain(C.byref(pl.fwd), C.byref(args), st["sms"], dn.ops._stream()), "fwd")
 torch.cuda.synchronize()
-t = trace.cpu()[:48].view(3, 2, 8) & 0xFFFFFFFF
+t = trace.cpu()[:64].view(4, 2, 8) & 0xFFFFFFFF
 t0 = int(t[0, 0, 0])
 rel = lambda x: (int(x) - t0) & 0xFFFFFFFF if int(x) else -1
 print("keep=%d; gsteps 12,13 of CTA 0 (SM clocks, smem trace)" % keep)
 print("MMA  [start, a_ready j0, j1, j2, j3, j4, commit0, end]")
 print("EPI  [before wait, acc_full seen, ld0 done, computed c0, ld_done passed, s_free passed, arrived c0, arrived c1]")
 for gs in range(2):
-    print("g%02d MMA %s\n    WG0 %s\n    WG3 %s" % (12 + gs, [rel(x) for x in t[0, gs]], [rel(x) for x in t[1, gs]], [rel(x) for x in t[2, gs]]))
+    print("g%02d MMA %s\n    WG0 %s\n    WG3 %s\n    STASH[a_ready seen slab0..3 | s_free arrived slab0..3] %s" % (12 + gs, [rel(x) for x in t[0, gs]], [rel(x) for x in t[1, gs]], [rel(x) for x in t[2, gs]], [rel(x) for x in t[3, gs]]))
