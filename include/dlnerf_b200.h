@@ -151,7 +151,7 @@ typedef struct {
   const float* d_out;      /* bwd: d raw[P,out_ch]                                                     */
   void* stash;             /* [tiles][stash_slots][DLN_SLAB_BYTES] or null                             */
   uint32_t* masks;         /* [mask_slots][tiles][4][128][2] relu bit masks                            */
-  long long* trace;        /* optional debug timeline [4 roles][64 steps][8 events] of SM clocks, CTA 0 only */
+  long long* trace;        /* optional debug timeline: 64 entries [4 roles][2 steps][8 events] of %clock, CTA 0 only */
 } DlnChainArgs;
 
 /* Fused MLP chain (forward or dgrad).  prog_host / args_host are HOST structs passed by value to the

@@ -16,6 +16,7 @@ run mlp_bwd_dz tests/test_gpu_mlp.py -m gpu -k "dz_per_layer"
 run mlp_bwd tests/test_gpu_mlp.py -m gpu -k "backward_gradients or full_size"
 run mlp_misc tests/test_gpu_mlp.py -m gpu -k "repacked or unsupported"
 run e2e tests/test_gpu_render_e2e.py -m gpu
+run fullsize tests/test_gpu_fullsize_properties.py -m gpu
 timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke exit=$?" | tee -a gpurun_out/summary.txt
 tail -2 gpurun_out/smoke.log | tee -a gpurun_out/summary.txt
 timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit=$?" | tee -a gpurun_out/summary.txt
