@@ -60,11 +60,12 @@ class PackJob(C.Structure):
                 ("n_rows", C.c_int32), ("dst_off", C.c_uint32)]
 
 
-_P, _I, _F, _LL = C.c_void_p, C.c_int, C.c_float, C.c_longlong
+_P, _I, _F, _LL, _D = C.c_void_p, C.c_int, C.c_float, C.c_longlong, C.c_double
 
 # name -> argtypes; every function returns int.  Must list EVERY symbol include/dlnerf_b200.h declares
 # (tests/test_abi.py parses the header and compares).
 SIGNATURES = {
+    "dln_pack_rays": [_P, _P, _I, _I, _I, _I, _D, _F, _F, _F, _I, _P, _P],
     "dln_stratified_z": [_P, _I, _P, _P, _I, _I, _I, _P],
     "dln_posenc": [_P, _P, _LL, _I, _P],
     "dln_composite_fwd": [_P, _I, _P, _P, _P, _F, _I, _P, _P, _P, _P, _P, _I, _I, _P],

@@ -32,6 +32,21 @@ def _ptr(t: Optional[Tensor]) -> Optional[int]:
 
 
 # ------------------------------------------------------------------------------------------------
+def pack_rays(H: int, W: int, focal: float, rays_o: Tensor, rays_d: Tensor, ndc: bool, near: float, far: float,
+              use_viewdirs: bool) -> Tensor:
+    """render()'s ray packing in one launch (run_nerf.py:145-183 with ndc_rays, helpers:320-337, near plane 1):
+    [..., 3] origins / directions -> ray_batch[N, 8 | 11] = [o, d, near, far, (unit viewdirs of the pre-warp d)]."""
+    o = _f32(rays_o, "pack_rays").reshape(-1, 3)
+    d = _f32(rays_d, "pack_rays").reshape(-1, 3)
+    if o.shape != d.shape:
+        raise ValueError("rays_o and rays_d must have the same shape")
+    N = o.shape[0]
+    out = torch.empty(N, 11 if use_viewdirs else 8, device=o.device, dtype=torch.float32)
+    L.call("dln_pack_rays", o.data_ptr(), d.data_ptr(), N, int(bool(ndc)), int(H), int(W), float(focal), 1.0,
+           float(near), float(far), int(bool(use_viewdirs)), out.data_ptr(), _stream(), tag="pack_rays")
+    return out
+
+
 def stratified_z(ray_batch: Tensor, n_samples: int, t_rand: Optional[Tensor] = None, lindisp: bool = False) -> Tensor:
     """run_nerf.py:571-593.  ray_batch[N, >=8] with near/far at columns 6/7."""
     rb = _f32(ray_batch, "stratified_z")

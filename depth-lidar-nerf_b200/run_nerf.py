@@ -82,6 +82,16 @@ def render(H, W, focal, chunk=1024 * 32, rays=None, c2w=None, ndc=True, near=0.,
         rays_o, rays_d = get_rays(H, W, focal, c2w)
     else:
         rays_o, rays_d = rays
+    if (c2w_staticcam is None and depths is None and torch.is_tensor(rays_d) and rays_d.is_cuda
+            and not isinstance(near, torch.Tensor) and not isinstance(far, torch.Tensor)):
+        # the training-loop case: one kernel instead of the ~15 element-wise launches below (same operation order)
+        sh = rays_d.shape
+        packed = ops.pack_rays(H, W, focal, rays_o, rays_d, ndc, near, far, use_viewdirs)
+        all_ret = batchify_rays(packed, chunk, **kwargs)
+        for k in all_ret:
+            all_ret[k] = torch.reshape(all_ret[k], list(sh[:-1]) + list(all_ret[k].shape[1:]))
+        k_extract = ['rgb_map', 'disp_map', 'acc_map', 'depth_map']
+        return [all_ret[k] for k in k_extract] + [{k: all_ret[k] for k in all_ret if k not in k_extract}]
     viewdirs = None
     if use_viewdirs:
         viewdirs = rays_d

@@ -120,8 +120,14 @@ class NeRF(nn.Module):
 
     # ------------------------------------------------------------------ device-side state
     def _ordered_params(self) -> List[nn.Parameter]:
-        d = dict(self.named_parameters())
-        return [d[name] for name, _ in self._shape.param_shapes()]
+        # called several times per training step: resolve the names once (load_state_dict copies in place and
+        # .to()/.cuda() swap .data, so the Parameter objects stay the same)
+        cache = self.__dict__.get("_ordered_cache")
+        if cache is None:
+            d = dict(self.named_parameters())
+            cache = [d[name] for name, _ in self._shape.param_shapes()]
+            self.__dict__["_ordered_cache"] = cache
+        return cache
 
     def _state(self):
         """Flat fp32 parameter buffer (each nn.Parameter is re-pointed to a view of it), packed bf16

@@ -77,6 +77,8 @@ def pack_ray_batch(H: int, W: int, focal: float, batch_rays: Tensor, ndc: bool =
     """The [N, 8|11] ray_batch of render() (run_nerf.py:145-183): unit view directions from the PRE-warp
     directions, NDC warp with near plane 1, [o, d, near, far, viewdirs]."""
     rays_o, rays_d = batch_rays[0], batch_rays[1]
+    if rays_d.is_cuda:
+        return ops.pack_rays(H, W, focal, rays_o, rays_d, ndc, near, far, use_viewdirs)
     viewdirs = None
     if use_viewdirs:
         viewdirs = rays_d / torch.norm(rays_d, dim=-1, keepdim=True)

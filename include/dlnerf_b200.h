@@ -22,6 +22,12 @@ extern "C" {
  * Sampling / encoding
  * -------------------------------------------------------------------------------------------- */
 
+/* The packed ray batch of render(): replaces run_nerf.py:145-183 (unit view directions from the pre-warp
+ * directions :147-152, ndc_rays run_nerf_helpers.py:320-337 with near plane `near_plane`, near/far columns,
+ * concatenation :178-183).  rays_o / rays_d are [N,3] contiguous fp32; ray_batch is [N, use_viewdirs ? 11 : 8]. */
+int dln_pack_rays(const float* rays_o, const float* rays_d, int N, int ndc, int H, int W, double focal,
+                  float near_plane, float near, float far, int use_viewdirs, float* ray_batch, void* stream);
+
 /* Stratified depths along each ray.  Replaces run_nerf.py:571-593 (t_vals linspace, near/far lerp or
  * lindisp, mids/upper/lower jitter).  rays[N, ray_stride] holds near at column 6 and far at column 7
  * (the packed ray_batch of run_nerf.py:178-183).  t_rand[N,S] may be null (perturb == 0). */

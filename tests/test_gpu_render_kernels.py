@@ -55,6 +55,27 @@ def test_posenc_against_golden(golden_dir):
     assert e.shape == (0, 63)
 
 
+# ---------------------------------------------------------------------------------------- ray packing
+@pytest.mark.parametrize("ndc,vd,near,far", [(True, True, 0., 1.), (False, True, 2., 6.), (True, False, 0., 1.)])
+def test_pack_rays_matches_reference_packing(ndc, vd, near, far):
+    """dln_pack_rays == render()'s packing (run_nerf.py:145-183 + ndc_rays) as restated by the pinned oracle:
+    the kernel performs the reference's operations in the reference's order, each rounded separately, so the NDC
+    origins / directions and the near / far columns are bit-exact; the unit view directions may differ in the last
+    ulp (torch reduces the norm in a different association)."""
+    Hh, Ww, foc = 378, 504, 407.6
+    ro, rd = O.synth_rays(1000, seed=11)
+    ref = O.pack_rays(Hh, Ww, foc, ro, rd, ndc=ndc, near=near, far=far, use_viewdirs=vd)
+    got = dn().ops.pack_rays(Hh, Ww, foc, ro.to(DEV), rd.to(DEV), ndc, near, far, vd)
+    assert got.shape == ref.shape
+    assert torch.equal(got[:, :8].cpu(), ref[:, :8]), "o', d', near, far must be bit-exact"
+    if vd:
+        report("unit viewdirs", got[:, 8:], ref[:, 8:], atol=1.2e-7)
+    # [2, N, 3] stacked input of the training loop and an empty batch
+    rb = dn().pack_ray_batch(Hh, Ww, foc, torch.stack([ro, rd], 0).to(DEV), ndc, near, far, vd)
+    assert torch.equal(rb, got)
+    assert dn().ops.pack_rays(Hh, Ww, foc, ro[:0].to(DEV), rd[:0].to(DEV), ndc, near, far, vd).shape == (0, ref.shape[1])
+
+
 # ---------------------------------------------------------------------------------------- compositing
 def _composite_inputs(N, S, seed, C=4):
     g = torch.Generator().manual_seed(seed)
