@@ -15,6 +15,7 @@ from .run_nerf_helpers import (Embedder, NeRF, get_embedder, img2mse, mse2psnr, 
                                sample_pdf, to8b)
 from .run_nerf import (FusedQuery, batchify, batchify_rays, create_nerf, get_rays, render, render_rays,
                        run_network)
+from .optim import FlatAdam
 from .train import (GraphedTrainStep, allreduce_gradients, default_ray_chunk, pack_ray_batch, shard_bounds, shard_ray_batch,
                     train_step)
 

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
 CSRC = os.path.join(_HERE, "csrc")
 SO_PATH = os.path.join(_HERE, "libdlnerf_b200.so")
-SOURCES = ["render_kernels.cu", "mlp_kernels.cu"]
+SOURCES = ["render_kernels.cu", "mlp_kernels.cu", "optim_kernels.cu"]
 
 MAX_STEPS = 12
 MAX_KSLABS = 6
@@ -76,6 +76,7 @@ SIGNATURES = {
     "dln_mlp_chain": [C.POINTER(ChainProgram), C.POINTER(ChainArgs), _I, _P],
     "dln_mlp_wgrad": [_P, _I, _I, _P, _I, _P, _I, _LL, _P, _P],
     "dln_mlp_pack_weights": [_P, _P, _I, _P, _P],
+    "dln_adam_step": [_P, _P, _P, _P, _LL, _D, _D, _D, _D, _I, _F, _P],
     "dln_abi_sizes": [C.POINTER(C.c_int)],
 }
 

@@ -205,6 +205,17 @@ int dln_mlp_pack_weights(const float* params_flat, const DlnPackJob* jobs_dev, i
 /* Library / build information (arch string, e.g. "sm_100a"). */
 const char* dln_build_info(void);
 
+/* ----------------------------------------------------------------------------------------------
+ * Optimiser
+ * -------------------------------------------------------------------------------------------- */
+
+/* One Adam step on a flat fp32 buffer: replaces optimizer.step() of run_nerf.py:440 / :1774 (torch.optim.Adam,
+ * no weight decay, no amsgrad) for all parameters of a network at once.  `step` is the 1-based step count used in
+ * the bias corrections, `grad_scale` multiplies the gradient first (1/world after a summing all-reduce).  All four
+ * buffers hold n floats and are 16-byte aligned. */
+int dln_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, double lr,
+                  double beta1, double beta2, double eps, int step, float grad_scale, void* stream);
+
 /* Host-only: sizeof of the five ABI structs, in the order ChainStep, ChainProgram, ChainArgs, WgradItem,
  * PackJob, so a binding can verify its mirror of this header without touching a GPU. */
 int dln_abi_sizes(int* out5_host);
