@@ -130,6 +130,11 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm is rank 0 alone on the box's host cores
+    try:
+        torch.set_num_threads(len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        torch.set_num_threads(os.cpu_count() or 1)
     torch.manual_seed(3407)
     total = args.steps + args.warmup
     n_sample = int(max(128, min(1024, (60000 // max(total, 1)) // 64 * 64)))
