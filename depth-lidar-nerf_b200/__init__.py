@@ -6,15 +6,16 @@ root) or ``importlib.import_module("depth-lidar-nerf_b200")``.
 
 Layout:  csrc/ (CUDA kernels + C ABI, include/dlnerf_b200.h)  ·  _lib.py (loader)  ·  plan.py (static MLP
 plans)  ·  ops.py (torch wrappers)  ·  run_nerf_helpers.py / run_nerf.py (mirrors of the reference modules)
-·  train.py (fused train step, ray-sharded data parallel).
+·  train.py (fused train step, ray-sharded data parallel)  ·  optim.py (flat Adam)  ·  data.py (device ray bank).
 """
 from . import _lib
 from ._lib import build, lib
 from . import ops
 from .run_nerf_helpers import (Embedder, NeRF, get_embedder, img2mse, mse2psnr, ndc_rays, raw2outputs,
                                sample_pdf, to8b)
-from .run_nerf import (FusedQuery, batchify, batchify_rays, create_nerf, get_rays, render, render_rays,
-                       run_network)
+from .run_nerf import (FusedQuery, batchify, batchify_rays, create_nerf, get_rays, render, render_path,
+                       render_rays, run_network)
+from .data import DeviceRayLoader, RayDataset
 from .optim import FlatAdam
 from .train import (GraphedTrainStep, allreduce_gradients, default_ray_chunk, pack_ray_batch, shard_bounds, shard_ray_batch,
                     train_step)
@@ -22,4 +23,5 @@ from .train import (GraphedTrainStep, allreduce_gradients, default_ray_chunk, pa
 __all__ = ["build", "lib", "ops", "Embedder", "NeRF", "get_embedder", "img2mse", "mse2psnr", "ndc_rays",
            "raw2outputs", "sample_pdf", "to8b", "FusedQuery", "batchify", "batchify_rays", "create_nerf",
            "get_rays", "render", "render_rays", "run_network", "allreduce_gradients", "pack_ray_batch",
-           "shard_bounds", "shard_ray_batch", "train_step", "GraphedTrainStep"]
+           "shard_bounds", "shard_ray_batch", "train_step", "GraphedTrainStep", "default_ray_chunk", "FlatAdam",
+           "render_path", "DeviceRayLoader", "RayDataset"]

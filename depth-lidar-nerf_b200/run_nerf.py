@@ -13,10 +13,11 @@ from __future__ import annotations
 import os
 from typing import Dict, Optional
 
+import numpy as np
 import torch
 
 from . import ops
-from .run_nerf_helpers import NeRF, get_embedder, ndc_rays, raw2outputs, sample_pdf
+from .run_nerf_helpers import NeRF, get_embedder, ndc_rays, raw2outputs, sample_pdf, to8b
 
 Tensor = torch.Tensor
 
@@ -116,6 +117,36 @@ def render(H, W, focal, chunk=1024 * 32, rays=None, c2w=None, ndc=True, near=0.,
         all_ret[k] = torch.reshape(all_ret[k], list(sh[:-1]) + list(all_ret[k].shape[1:]))
     k_extract = ['rgb_map', 'disp_map', 'acc_map', 'depth_map']
     return [all_ret[k] for k in k_extract] + [{k: all_ret[k] for k in all_ret if k not in k_extract}]
+
+
+def render_path(render_poses, hwf, chunk, render_kwargs, gt_imgs=None, savedir=None, render_factor=0, iteration=0,
+                writer=None, coords=None):
+    """run_nerf.py:268-359: full-image renders for a list of poses (evaluation / video), no autograd graph and
+    therefore no activation stash.  Returns (rgbs[P,H,W,3], disps[P,H,W]) as numpy like the reference; with
+    ``savedir`` each view's maps go to ``{i:03d}.npz`` (+ an 8-bit PNG when cv2 is importable -- imageio, the
+    reference's writer, is not a dependency here).  Tensorboard ``writer`` images and the semantic-map video are
+    the caller's visualisation code and are not reproduced."""
+    H, W, focal = hwf
+    if render_factor != 0:
+        H, W, focal = H // render_factor, W // render_factor, focal / render_factor
+    H, W = int(H), int(W)
+    rgbs, disps = [], []
+    for i, c2w in enumerate(render_poses):
+        with torch.no_grad():
+            rgb, disp, acc, depth, extras = render(H, W, focal, chunk=chunk, c2w=c2w[:3, :4], retraw=True,
+                                                   **render_kwargs)
+        rgbs.append(rgb.cpu().numpy())
+        disps.append(disp.cpu().numpy())
+        if savedir is not None:
+            rgb8 = to8b(np.nan_to_num(rgbs[-1]))
+            np.savez(os.path.join(savedir, '{:03d}.npz'.format(i)), rgb=rgbs[-1], disp=disps[-1],
+                     acc=acc.cpu().numpy(), depth=depth.cpu().numpy())
+            try:
+                import cv2
+                cv2.imwrite(os.path.join(savedir, '{:03d}.png'.format(i)), rgb8[..., ::-1])
+            except ImportError:
+                pass
+    return np.stack(rgbs, 0), np.stack(disps, 0)
 
 
 def get_rays(H, W, focal, c2w):

@@ -322,3 +322,34 @@ def test_render_without_viewdirs_against_oracle():
     report("no-viewdirs rgb_map", rgb, ref["rgb_map"], atol=2e-2)
     report("no-viewdirs depth_map", depth, ref["depth_map"], atol=2e-2)
     assert extras["raw"].shape == (n, 128, 5)
+
+
+def test_render_path_full_images_match_per_ray_render(tmp_path):
+    """render_path (run_nerf.py:268-359): full-image evaluation renders through c2w -> get_rays, chunked, without
+    autograd; equal to rendering the same rays in one call, deterministic (perturb = noise = 0 as in
+    render_kwargs_test), and against the oracle on the same rays."""
+    import numpy as np
+    d = dn()
+    net_c, pc, spec_c = make_net(4, seed=61, sigma_bias=1.0)
+    net_f, pf, spec_f = make_net(8, seed=62, sigma_bias=1.0)
+    Hh, Ww, foc = 12, 20, 18.0
+    q = d.FusedQuery(d.get_embedder(10, 0)[0], d.get_embedder(4, 0)[0], 1 << 16, 10, 4, 0)
+    kw = dict(network_query_fn=q, perturb=0., N_importance=64, network_fine=net_f, N_samples=64, network_fn=net_c,
+              use_viewdirs=True, white_bkgd=False, raw_noise_std=0., ndc=True, near=0., far=1.)
+    poses = torch.eye(4, device=DEV)[None, :3, :4].repeat(2, 1, 1).contiguous()
+    poses[1, :3, 3] = torch.tensor([0.1, -0.05, 0.02], device=DEV)
+    rgbs, disps = d.render_path(poses, (Hh, Ww, foc), 64, kw, savedir=str(tmp_path))      # 240 rays in chunks of 64
+    assert rgbs.shape == (2, Hh, Ww, 3) and disps.shape == (2, Hh, Ww)
+    assert (tmp_path / "000.npz").exists() and (tmp_path / "001.npz").exists()
+    for i in range(2):
+        ro, rd = d.get_rays(Hh, Ww, foc, poses[i])
+        with torch.no_grad():
+            rgb, disp, acc, depth, extras = d.render(Hh, Ww, foc, chunk=1 << 20, rays=(ro, rd), **kw)
+        assert np.array_equal(rgbs[i], rgb.cpu().numpy()), "chunked c2w route must equal the one-call ray route"
+        rb = O.pack_rays(Hh, Ww, foc, ro.reshape(-1, 3).cpu(), rd.reshape(-1, 3).cpu())
+        ref = O.render_rays(rb, pc, spec_c, pf, spec_f, 64, 64, O.RenderRNG(), raw_noise_std=0.0)
+        report("render_path rgb (pose %d)" % i, torch.from_numpy(rgbs[i]).reshape(-1, 3), ref["rgb_map"], atol=2e-2)
+        saved = np.load(tmp_path / ("%03d.npz" % i))
+        report("saved depth (pose %d)" % i, torch.from_numpy(saved["depth"]).reshape(-1), ref["depth_map"], atol=2e-2)
+    rgbs_half, _ = d.render_path(poses[:1], (Hh, Ww, foc), 1 << 20, kw, render_factor=2)
+    assert rgbs_half.shape == (1, Hh // 2, Ww // 2, 3)
