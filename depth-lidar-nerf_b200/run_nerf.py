@@ -119,6 +119,54 @@ def render(H, W, focal, chunk=1024 * 32, rays=None, c2w=None, ndc=True, near=0.,
     return [all_ret[k] for k in k_extract] + [{k: all_ret[k] for k in all_ret if k not in k_extract}]
 
 
+def batchify_rays_feature_loss(rays_flat, chunk=1024 * 32, keep_keys=None, **kwargs):
+    """run_nerf.py:90-108: batchify_rays that only keeps the entries named in ``keep_keys`` (patch renders)."""
+    all_ret = {}
+    for i in range(0, rays_flat.shape[0], chunk):
+        ret = render_rays(rays_flat[i:i + chunk], **kwargs)
+        for k in ret:
+            if keep_keys and k not in keep_keys:
+                continue
+            all_ret.setdefault(k, []).append(ret[k])
+    return {k: torch.cat(all_ret[k], 0) for k in all_ret}
+
+
+def render_feature_loss(H, W, focal, chunk=1024 * 32, rays=None, c2w=None, ndc=True, near=0., far=1.,
+                        use_viewdirs=False, c2w_staticcam=None, keep_keys=None, **kwargs):
+    """run_nerf.py:197-265: the patch render of the feature / GAN / inverse-depth losses (:1552-1647).  The caller
+    renders the few gradient-carrying rays of a patch normally and the rest under ``torch.no_grad()``; without an
+    autograd graph the MLP kernels run in their forward-only form (no activation stash, no ReLU masks).  Returns
+    ``[rgb_map, disp_map, acc_map (those kept)] + [dict of every kept entry]``."""
+    if c2w is not None:
+        rays_o, rays_d = get_rays(H, W, focal, c2w)
+    else:
+        rays_o, rays_d = rays
+    sh = rays_d.shape
+    if c2w_staticcam is None and torch.is_tensor(rays_d) and rays_d.is_cuda:
+        packed = ops.pack_rays(H, W, focal, rays_o, rays_d, ndc, near, far, use_viewdirs)
+    else:
+        viewdirs = None
+        if use_viewdirs:
+            viewdirs = rays_d
+            if c2w_staticcam is not None:
+                rays_o, rays_d = get_rays(H, W, focal, c2w_staticcam)
+            viewdirs = torch.reshape(viewdirs / torch.norm(viewdirs, dim=-1, keepdim=True), [-1, 3]).float()
+        if ndc:
+            rays_o, rays_d = ndc_rays(H, W, focal, 1., rays_o, rays_d)
+        rays_o, rays_d = torch.reshape(rays_o, [-1, 3]).float(), torch.reshape(rays_d, [-1, 3]).float()
+        cols = [rays_o, rays_d, near * torch.ones_like(rays_d[..., :1]), far * torch.ones_like(rays_d[..., :1])]
+        if use_viewdirs:
+            cols.append(viewdirs)
+        packed = torch.cat(cols, -1)
+    all_ret = batchify_rays_feature_loss(packed, chunk, keep_keys=keep_keys, **kwargs)
+    for k in all_ret:
+        all_ret[k] = torch.reshape(all_ret[k], list(sh[:-1]) + list(all_ret[k].shape[1:]))
+    k_extract = ['rgb_map', 'disp_map', 'acc_map']
+    if keep_keys:
+        k_extract = [k for k in k_extract if k in keep_keys]
+    return [all_ret[k] for k in k_extract] + [{k: all_ret[k] for k in all_ret}]
+
+
 def render_path(render_poses, hwf, chunk, render_kwargs, gt_imgs=None, savedir=None, render_factor=0, iteration=0,
                 writer=None, coords=None):
     """run_nerf.py:268-359: full-image renders for a list of poses (evaluation / video), no autograd graph and

@@ -353,3 +353,39 @@ def test_render_path_full_images_match_per_ray_render(tmp_path):
         report("saved depth (pose %d)" % i, torch.from_numpy(saved["depth"]).reshape(-1), ref["depth_map"], atol=2e-2)
     rgbs_half, _ = d.render_path(poses[:1], (Hh, Ww, foc), 1 << 20, kw, render_factor=2)
     assert rgbs_half.shape == (1, Hh // 2, Ww // 2, 3)
+
+
+def test_patch_render_grad_and_no_grad_split():
+    """render_feature_loss (run_nerf.py:197-265) as the patch losses use it (:1552-1647): a few rays of a patch
+    carry gradients, the rest are rendered under no_grad (forward-only kernels, no stash); keep_keys filters the
+    returned entries; the rendered values equal render() on the same rays and the parameter gradients equal
+    those of a render() + backward over the gradient rays alone."""
+    d = dn()
+    n_grad, n_nograd = 96, 160
+    net_c, pc, spec_c, net_f, pf, spec_f, ro, rd, rng, tgt, dep = _case(n_grad, n_nograd, 71, False, False)
+    q = d.FusedQuery(d.get_embedder(10, 0)[0], d.get_embedder(4, 0)[0], 1 << 16, 10, 4, 0)
+    kw = dict(network_query_fn=q, perturb=0., N_importance=64, network_fine=net_f, N_samples=64, network_fn=net_c,
+              use_viewdirs=True, white_bkgd=False, raw_noise_std=0., ndc=True, near=0., far=1.)
+    keep = ['rgb_map', 'rgb0', 'depth_map', 'depth_map0']
+    ro, rd = ro.to(DEV), rd.to(DEV)
+    out_g = d.render_feature_loss(H, W, FOCAL, chunk=64, rays=(ro[:n_grad], rd[:n_grad]), keep_keys=keep, **kw)
+    assert len(out_g) == 2 and set(out_g[-1]) == set(keep)                      # only rgb_map of the 3 extracts kept
+    with torch.no_grad():
+        out_n = d.render_feature_loss(H, W, FOCAL, chunk=64, rays=(ro[n_grad:], rd[n_grad:]), keep_keys=keep, **kw)[-1]
+    assert not out_n['rgb_map'].requires_grad and out_g[-1]['rgb_map'].requires_grad
+    full = d.render(H, W, FOCAL, chunk=1 << 20, rays=(ro, rd), **kw)
+    report("patch rgb (grad rays)", out_g[-1]['rgb_map'], full[0][:n_grad], atol=1e-6)
+    report("patch rgb (no-grad rays)", out_n['rgb_map'], full[0][n_grad:], atol=1e-6)
+    report("patch depth0 (no-grad rays)", out_n['depth_map0'], full[4]['depth_map0'][n_grad:], atol=1e-6)
+    nets = list(net_c.parameters()) + list(net_f.parameters())
+    for p in nets:
+        p.grad = None
+    (out_g[-1]['rgb_map'].square().mean() + out_g[-1]['depth_map0'].mean()).backward()
+    got = [p.grad.clone() for p in nets]
+    for p in nets:
+        p.grad = None
+    ref = d.render(H, W, FOCAL, chunk=1 << 20, rays=(ro[:n_grad], rd[:n_grad]), **kw)
+    (ref[0].square().mean() + ref[4]['depth_map0'].mean()).backward()
+    worst = max(rel_l2(a, p.grad) for a, p in zip(got, nets))
+    print("  patch gradients vs render() on the gradient rays: worst per-tensor rel-L2 %.3e" % worst)
+    assert worst <= 2e-3
