@@ -272,14 +272,16 @@ class NeRF(nn.Module):
 # Ray helpers (run_nerf_helpers.py:320-337)
 # --------------------------------------------------------------------------------------------------
 def ndc_rays(H, W, focal, near, rays_o, rays_d):
-    """Near-plane shift + projective warp.  A dozen element-wise ops on [N,3]; negligible,
-    left to torch on the device."""
+    """Near-plane shift + projective warp (run_nerf_helpers.py:320-337) with torch ops; render() uses the
+    one-launch `ops.pack_rays` for device tensors, this function keeps the reference's name and signature."""
     t = -(near + rays_o[..., 2]) / rays_d[..., 2]
     rays_o = rays_o + t[..., None] * rays_d
     sx, sy = -1. / (W / (2. * focal)), -1. / (H / (2. * focal))
-    ox, oy = rays_o[..., 0] / rays_o[..., 2], rays_o[..., 1] / rays_o[..., 2]
-    o = torch.stack([sx * ox, sy * oy, 1. + 2. * near / rays_o[..., 2]], -1)
-    d = torch.stack([sx * (rays_d[..., 0] / rays_d[..., 2] - ox), sy * (rays_d[..., 1] / rays_d[..., 2] - oy),
+    # the reference's operation order, (sx * o_x) / o_z, so the results are bit-identical to it (:326-333)
+    o = torch.stack([sx * rays_o[..., 0] / rays_o[..., 2], sy * rays_o[..., 1] / rays_o[..., 2],
+                     1. + 2. * near / rays_o[..., 2]], -1)
+    d = torch.stack([sx * (rays_d[..., 0] / rays_d[..., 2] - rays_o[..., 0] / rays_o[..., 2]),
+                     sy * (rays_d[..., 1] / rays_d[..., 2] - rays_o[..., 1] / rays_o[..., 2]),
                      -2. * near / rays_o[..., 2]], -1)
     return o, d
 

@@ -105,6 +105,16 @@ def default_ray_chunk(network_fn: NeRF, network_fine: NeRF, N_samples: int, N_im
     return max(1024, (budget_bytes // per_ray) // 1024 * 1024)
 
 
+_SIDE_STREAMS: Dict[torch.device, "torch.cuda.Stream"] = {}
+
+
+def _side_stream(dev) -> "torch.cuda.Stream":
+    dev = torch.device(dev)
+    if dev not in _SIDE_STREAMS:
+        _SIDE_STREAMS[dev] = torch.cuda.Stream(device=dev)
+    return _SIDE_STREAMS[dev]
+
+
 @torch.no_grad()
 def train_step(H, W, focal, batch_rays: Tensor, target_s: Tensor, target_depth: Optional[Tensor], n_rgb: int,
                network_fn: NeRF, network_fine: NeRF, N_samples: int = 64, N_importance: int = 64,
@@ -112,7 +122,7 @@ def train_step(H, W, focal, batch_rays: Tensor, target_s: Tensor, target_depth: 
                ndc: bool = True, near: float = 0., far: float = 1., depth_lambda: float = 0.,
                depth_importance: float = 1., ray_weights: Optional[Tensor] = None, depth_mode: str = "mse",
                coarse_loss: bool = True, world_size: int = 1, group=None, ray_chunk: Optional[int] = None,
-               _rng: Optional[Dict[str, Tensor]] = None, _force_pack: bool = False) -> Dict[str, Tensor]:
+               overlap_coarse_backward: bool = True, _rng: Optional[Dict[str, Tensor]] = None, _force_pack: bool = False) -> Dict[str, Tensor]:
     """render + loss + backward for one ray batch; fills ``.grad`` of both networks (averaged over
     ``world_size`` ranks when > 1) and returns the loss terms as 0-d tensors (no host sync).
 
@@ -182,14 +192,23 @@ def train_step(H, W, focal, batch_rays: Tensor, target_s: Tensor, target_depth: 
         # fine pass: colour loss on the RGB rays, depth loss on the depth rays (run_nerf.py:1461, :1500-1524)
         d_raw1 = ops.composite_bwd_fused_loss(raw1, z1, rays_d, noise1, raw_noise_std, white_bkgd, tgt_c, tdep_c,
                                               rw_c, nr_c, coef_rgb, coef_dep, mode, depth_norm, sums[0:2])
-        grads_f = network_fine._run_backward(d_raw1, saved1, Nc * S1, gflat=gacc[1])
-        del saved1, d_raw1, raw1
+        side = None
         if coarse_loss:
-            # coarse pass: colour loss only (run_nerf.py:1759-1761); depth_map0 is unsupervised
-            d_raw0 = ops.composite_bwd_fused_loss(raw0, z0, rays_d, noise0, raw_noise_std, white_bkgd, tgt_c, None,
-                                                  None, nr_c, coef_rgb, 0.0, 0, 1.0, sums[2:4])
-            grads_c = network_fn._run_backward(d_raw0, saved0, Nc * N_samples, gflat=gacc[0])
-        del saved0
+            # coarse pass: colour loss only (run_nerf.py:1759-1761); depth_map0 is unsupervised.  It depends on the
+            # coarse forward alone, so it runs on a second stream next to the fine backward: its CTAs fill the SMs
+            # the persistent fine-net kernels leave idle at their tails and under the HBM-bound wgrad.
+            main = torch.cuda.current_stream(dev)
+            side = _side_stream(dev) if overlap_coarse_backward else main
+            if side is not main:
+                side.wait_stream(main)
+            with torch.cuda.stream(side):
+                d_raw0 = ops.composite_bwd_fused_loss(raw0, z0, rays_d, noise0, raw_noise_std, white_bkgd, tgt_c,
+                                                      None, None, nr_c, coef_rgb, 0.0, 0, 1.0, sums[2:4])
+                grads_c = network_fn._run_backward(d_raw0, saved0, Nc * N_samples, gflat=gacc[0])
+        grads_f = network_fine._run_backward(d_raw1, saved1, Nc * S1, gflat=gacc[1])
+        if side is not None and side is not torch.cuda.current_stream(dev):
+            torch.cuda.current_stream(dev).wait_stream(side)
+        del saved1, d_raw1, raw1, saved0
     _assign_grads(network_fine, grads_f)
     if coarse_loss:
         _assign_grads(network_fn, grads_c)

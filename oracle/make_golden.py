@@ -245,8 +245,8 @@ def main():
     ro, rdw = O.synth_rays(n_rgb + n_dep, seed=5)
     o_ref, d_ref = H.ndc_rays(Hh, Ww, focal, 1.0, ro, rdw)
     o_m, d_m = O.ndc_rays(Hh, Ww, focal, 1.0, ro, rdw)
-    close(o_m, o_ref, 1e-6, "ndc o")
-    close(d_m, d_ref, 1e-6, "ndc d")
+    close(o_m, o_ref, 0.0, "ndc o")          # same operations in the same order: bit-exact
+    close(d_m, d_ref, 0.0, "ndc d")
     fix = dict(rays_o=np_(ro), rays_d=np_(rdw), ndc_o=np_(o_ref), ndc_d=np_(d_ref))
 
     if R is not None:

@@ -241,11 +241,10 @@ def ndc_rays(H: int, W: int, focal: float, near: float, rays_o: Tensor, rays_d: 
     o = rays_o + t[..., None] * rays_d
     sx = -1.0 / (W / (2.0 * focal))
     sy = -1.0 / (H / (2.0 * focal))
-    ox_oz = o[..., 0] / o[..., 2]
-    oy_oz = o[..., 1] / o[..., 2]
-    o_ndc = torch.stack([sx * ox_oz, sy * oy_oz, 1.0 + 2.0 * near / o[..., 2]], dim=-1)
-    d_ndc = torch.stack([sx * (rays_d[..., 0] / rays_d[..., 2] - ox_oz),
-                         sy * (rays_d[..., 1] / rays_d[..., 2] - oy_oz),
+    # operation order of :326-333 kept literally ((sx * o_x) / o_z, not sx * (o_x / o_z)): bit-exact with the reference
+    o_ndc = torch.stack([sx * o[..., 0] / o[..., 2], sy * o[..., 1] / o[..., 2], 1.0 + 2.0 * near / o[..., 2]], dim=-1)
+    d_ndc = torch.stack([sx * (rays_d[..., 0] / rays_d[..., 2] - o[..., 0] / o[..., 2]),
+                         sy * (rays_d[..., 1] / rays_d[..., 2] - o[..., 1] / o[..., 2]),
                          -2.0 * near / o[..., 2]], dim=-1)
     return o_ndc, d_ndc
 
