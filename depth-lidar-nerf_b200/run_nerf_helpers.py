@@ -199,7 +199,7 @@ class NeRF(nn.Module):
         L.call("dln_mlp_chain", C.byref(pl.fwd), C.byref(args), st["sms"], ops._stream(), tag="mlp_fwd D=%d" % self.D)
         return out, saved
 
-    def _run_backward(self, d_out, saved, P, gflat=None):
+    def _run_backward(self, d_out, saved, P, gflat=None, sms=None):
         """dgrad chain + wgrad.  ``gflat`` (flat fp32 [n_params]) accumulates across calls when given (ray-chunked
         steps); otherwise a zeroed buffer is allocated."""
         st = self._state()
@@ -215,7 +215,9 @@ class NeRF(nn.Module):
         args.wblob, args.fblob = st["wb"].data_ptr(), st["flat"].data_ptr()
         args.d_out, args.stash, args.masks = d.data_ptr(), stash_b.data_ptr(), masks.data_ptr()
         lib, s = L.lib(), ops._stream()
-        L.call("dln_mlp_chain", C.byref(pl.bwd), C.byref(args), st["sms"], s, tag="mlp_dgrad D=%d" % self.D)
+        # `sms` caps the persistent dgrad grid so that a concurrent kernel on another stream keeps some SMs
+        L.call("dln_mlp_chain", C.byref(pl.bwd), C.byref(args), min(st["sms"], sms) if sms else st["sms"], s,
+               tag="mlp_dgrad D=%d" % self.D)
         if gflat is None:
             gflat = torch.zeros(pl.n_params, device=dev, dtype=torch.float32)
         n_items = len(pl.wgrad)

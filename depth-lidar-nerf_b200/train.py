@@ -122,7 +122,8 @@ def train_step(H, W, focal, batch_rays: Tensor, target_s: Tensor, target_depth: 
                ndc: bool = True, near: float = 0., far: float = 1., depth_lambda: float = 0.,
                depth_importance: float = 1., ray_weights: Optional[Tensor] = None, depth_mode: str = "mse",
                coarse_loss: bool = True, world_size: int = 1, group=None, ray_chunk: Optional[int] = None,
-               overlap_coarse_backward: bool = True, _rng: Optional[Dict[str, Tensor]] = None, _force_pack: bool = False) -> Dict[str, Tensor]:
+               overlap_coarse_backward: bool = True, coarse_sms: Optional[int] = None,
+               _rng: Optional[Dict[str, Tensor]] = None, _force_pack: bool = False) -> Dict[str, Tensor]:
     """render + loss + backward for one ray batch; fills ``.grad`` of both networks (averaged over
     ``world_size`` ranks when > 1) and returns the loss terms as 0-d tensors (no host sync).
 
@@ -204,7 +205,8 @@ def train_step(H, W, focal, batch_rays: Tensor, target_s: Tensor, target_depth: 
             with torch.cuda.stream(side):
                 d_raw0 = ops.composite_bwd_fused_loss(raw0, z0, rays_d, noise0, raw_noise_std, white_bkgd, tgt_c,
                                                       None, None, nr_c, coef_rgb, 0.0, 0, 1.0, sums[2:4])
-                grads_c = network_fn._run_backward(d_raw0, saved0, Nc * N_samples, gflat=gacc[0])
+                grads_c = network_fn._run_backward(d_raw0, saved0, Nc * N_samples, gflat=gacc[0],
+                                                   sms=coarse_sms if side is not main else None)
         grads_f = network_fine._run_backward(d_raw1, saved1, Nc * S1, gflat=gacc[1])
         if side is not None and side is not torch.cuda.current_stream(dev):
             torch.cuda.current_stream(dev).wait_stream(side)
