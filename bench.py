@@ -370,7 +370,10 @@ def run_ours(args):
                 "all_mlp_kernels": {"tflops": mlp_tflops, "frac": mlp_tflops / pk["tf_sust"],
                                     "ms_per_step": mlp_ms, "share_of_step": mlp_ms / ms_share},
                 "share_basis_ms_per_step": ms_share,
-                "flops_basis": "algorithmic unpadded MACs/point (SURVEY §8d) x points per launch"}
+                "flops_basis": "algorithmic unpadded MACs/point of the reference's layer structure (SURVEY §8d) x points "
+                               "per launch; the kernels fold feature_linear into views_linears (no activation between "
+                               "them) and so execute 65 536 MACs/point fewer per pass (89 % of the algorithmic count "
+                               "for D=8, 79 % for D=4) for the same result"}
 
     # ---- end to end from pinned host memory ------------------------------------------------------------
     # The drop-in route keeps every chunk's activations alive for autograd (as the reference does), so above the

@@ -33,7 +33,94 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// feature_linear folded into views_linears (plan.py build_plan, fold_feature): W = 256, W/2 = 128.
+//   fold   : M[i][j] = sum_k Wv[i][k] Wf[k][j],  b'[i] = sum_k Wv[i][k] bf[k] + bv[i]      (after every weight update)
+//   unfold : dWv[i][k] += sum_j dM[i][j] Wf[k][j] + db'[i] bf[k];  dWf[k][j] += sum_i Wv[i][k] dM[i][j];
+//            dbf[k] += sum_i Wv[i][k] db'[i];  dbv[i] += db'[i]                               (after every wgrad)
+// 8 M multiply-adds each, once per step and network: CUDA cores, fp32.
+// ------------------------------------------------------------------------------------------------
+struct FoldOffsets {
+  long long wv, wf, bf, bv, M, bM;
+  int ldv;
+};
+
+__global__ void __launch_bounds__(256) fold_kernel(float* __restrict__ flat, FoldOffsets o) {
+  __shared__ float wrow[256];
+  __shared__ float red[8];
+  const int i = blockIdx.x, j = threadIdx.x;
+  wrow[j] = flat[o.wv + (long long)i * o.ldv + j];
+  __syncthreads();
+  const float* wf = flat + o.wf;
+  float acc = 0.f;
+#pragma unroll 8
+  for (int k = 0; k < 256; ++k) acc = fmaf(wrow[k], wf[k * 256 + j], acc);
+  flat[o.M + i * 256 + j] = acc;
+  float b = dln::warp_sum(wrow[j] * flat[o.bf + j]);
+  if ((j & 31) == 0) red[j >> 5] = b;
+  __syncthreads();
+  if (j == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    flat[o.bM + i] = t + flat[o.bv + i];
+  }
+}
+
+__global__ void __launch_bounds__(256) unfold_kernel(const float* __restrict__ flat, float* __restrict__ g, FoldOffsets o) {
+  __shared__ float sh[256];
+  const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  if (b < 128) {                 // row i of dW_v1: (W_f dM_i)[k] + db'_i b_f[k]; a warp per k, lanes over j
+    const int i = b;
+    sh[t] = g[o.M + i * 256 + t];
+    __syncthreads();
+    const float dbi = g[o.bM + i];
+    for (int k = warp; k < 256; k += 8) {
+      const float* wf = flat + o.wf + k * 256;
+      float acc = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc = fmaf(sh[q * 32 + lane], wf[q * 32 + lane], acc);
+      acc = dln::warp_sum(acc);
+      if (lane == 0) g[o.wv + (long long)i * o.ldv + k] += acc + dbi * flat[o.bf + k];
+    }
+  } else if (b < 384) {          // row k of dW_f: sum_i Wv[i][k] dM[i][:]
+    const int k = b - 128;
+    if (t < 128) sh[t] = flat[o.wv + (long long)t * o.ldv + k];
+    __syncthreads();
+    float acc = 0.f;
+#pragma unroll 8
+    for (int i = 0; i < 128; ++i) acc = fmaf(sh[i], g[o.M + i * 256 + t], acc);
+    g[o.wf + k * 256 + t] += acc;
+  } else {                       // biases
+    if (t < 128) sh[t] = g[o.bM + t];
+    __syncthreads();
+    float acc = 0.f;
+    for (int i = 0; i < 128; ++i) acc = fmaf(flat[o.wv + (long long)i * o.ldv + t], sh[i], acc);
+    g[o.bf + t] += acc;
+    if (t < 128) g[o.bv + t] += sh[t];
+  }
+}
+
 }  // namespace
+
+extern "C" int dln_mlp_fold(float* params_flat, long long off_views_w, int ld_views, long long off_feature_w,
+                            long long off_feature_b, long long off_views_b, long long off_M, long long off_bM,
+                            void* stream) {
+  DLN_CHECK_ARG(params_flat && ld_views >= 256 && off_views_w >= 0 && off_feature_w >= 0 && off_feature_b >= 0 &&
+                off_views_b >= 0 && off_M >= 0 && off_bM >= 0);
+  const FoldOffsets o{off_views_w, off_feature_w, off_feature_b, off_views_b, off_M, off_bM, ld_views};
+  fold_kernel<<<128, 256, 0, (cudaStream_t)stream>>>(params_flat, o);
+  return dln_launch_status();
+}
+
+extern "C" int dln_mlp_unfold_grads(const float* params_flat, float* grads_flat, long long off_views_w, int ld_views,
+                                    long long off_feature_w, long long off_feature_b, long long off_views_b,
+                                    long long off_M, long long off_bM, void* stream) {
+  DLN_CHECK_ARG(params_flat && grads_flat && ld_views >= 256 && off_views_w >= 0 && off_feature_w >= 0 &&
+                off_feature_b >= 0 && off_views_b >= 0 && off_M >= 0 && off_bM >= 0);
+  const FoldOffsets o{off_views_w, off_feature_w, off_feature_b, off_views_b, off_M, off_bM, ld_views};
+  unfold_kernel<<<385, 256, 0, (cudaStream_t)stream>>>(params_flat, grads_flat, o);
+  return dln_launch_status();
+}
 
 extern "C" int dln_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n,
                              double lr, double beta1, double beta2, double eps, int step, float grad_scale,

@@ -97,6 +97,13 @@ class Plan:
     fwd_slots: int = 0
     bwd_slots: int = 0
     mask_slots: int = 0
+    # feature_linear folded into views_linears (see build_plan): derived operands live behind the parameters in the
+    # flat buffer ([0, n_params) parameters | M [W/2 x W] | b' [W/2]); the flat gradient buffer has the same layout,
+    # its tail being per-call scratch (dM, db') that dln_mlp_unfold_grads turns into the real gradients
+    fold: bool = False
+    n_flat: int = 0
+    off_M: int = -1
+    off_bM: int = -1
 
 
 def _set_k(step: L.ChainStep, slabs: List[int], cnts: List[int]) -> None:
@@ -106,7 +113,15 @@ def _set_k(step: L.ChainStep, slabs: List[int], cnts: List[int]) -> None:
         step.kcnt[j] = c
 
 
-def build_plan(shape: NetShape) -> Plan:
+def build_plan(shape: NetShape, fold_feature: bool = True) -> Plan:
+    """Static execution plan of one network.
+
+    ``fold_feature`` (view-direction nets only): ``feature_linear`` has no activation (run_nerf_helpers.py:126), so
+    views(feature(h)) = relu([W_v1 W_f] h + W_vd dir + [W_v1 b_f + b_v]) with W_v1 = views weight[:, :W].  The chain
+    then skips the 256x256 feature step in the forward pass, one of the two dgrad steps behind it and one 256x256
+    wgrad item (with 4 + 4 slabs of stash per tile): M = W_v1 W_f and b' are rebuilt by ``dln_mlp_fold`` whenever
+    the weights change, and the gradient of M is unfolded into dW_v1 = dM W_f^T + db' b_f^T, dW_f = W_v1^T dM, db_f = W_v1^T db'
+    by ``dln_mlp_unfold_grads`` -- identical in exact arithmetic, one bf16 rounding fewer in practice."""
     shape.validate()
     D, W = shape.D, shape.W
     pl = Plan(shape=shape)
@@ -118,6 +133,11 @@ def build_plan(shape: NetShape) -> Plan:
             n *= d
         off += (n + 3) // 4 * 4      # keep every tensor 16-byte aligned inside the flat buffer
     pl.n_params = off
+    pl.fold = bool(fold_feature and shape.use_viewdirs)
+    pl.n_flat = off
+    if pl.fold:
+        pl.off_M, pl.off_bM = off, off + (W // 2) * W
+        pl.n_flat = pl.off_bM + W // 2
     O = pl.offsets
     kc_pts = _ceil_div(shape.input_ch, 16)
     kc_dir = _ceil_div(shape.input_ch_views, 16)
@@ -130,7 +150,8 @@ def build_plan(shape: NetShape) -> Plan:
     steps = 0
 
     def add_job(jobs, name, ld, row0, col0, n_valid, k_valid, transposed, n_rows, dst):
-        jobs.append(L.PackJob(O[name], ld, row0, col0, n_valid, k_valid, transposed, n_rows, dst))
+        src = O[name] if isinstance(name, str) else int(name)          # parameter name or raw float offset
+        jobs.append(L.PackJob(src, ld, row0, col0, n_valid, k_valid, transposed, n_rows, dst))
 
     H_slot = lambda i: 2 + 4 * i          # forward stash slot of the output of pts layer i
     for i in range(D):
@@ -161,22 +182,27 @@ def build_plan(shape: NetShape) -> Plan:
                 st.head_off, st.head_bias_off = O["output_linear.weight"], O["output_linear.bias"]
         steps += 1
     feat_slot = H_slot(D)
-    hv_slot = feat_slot + 4
+    hv_slot = feat_slot + (0 if pl.fold else 4)
     if shape.use_viewdirs:
+        if not pl.fold:
+            st = fwd.steps[steps]
+            st.w_off, st.bias_off, st.n_out, st.epi = blob, O["feature_linear.bias"], 256, L.EPI_LINEAR
+            _set_k(st, [0, 1, 2, 3], [4, 4, 4, 4])
+            for j in range(4):
+                add_job(pl.fwd_jobs, "feature_linear.weight", W, 0, 64 * j, 256, 64, 0, 256, blob)
+                blob += 256 * 128
+            st.stash_slot, st.mask_slot = feat_slot, -1
+            steps += 1
         st = fwd.steps[steps]
-        st.w_off, st.bias_off, st.n_out, st.epi = blob, O["feature_linear.bias"], 256, L.EPI_LINEAR
-        _set_k(st, [0, 1, 2, 3], [4, 4, 4, 4])
-        for j in range(4):
-            add_job(pl.fwd_jobs, "feature_linear.weight", W, 0, 64 * j, 256, 64, 0, 256, blob)
-            blob += 256 * 128
-        st.stash_slot, st.mask_slot = feat_slot, -1
-        steps += 1
-        st = fwd.steps[steps]
-        st.w_off, st.bias_off, st.n_out, st.epi = blob, O["views_linears.0.bias"], 128, L.EPI_RELU_RGB
+        st.w_off, st.n_out, st.epi = blob, 128, L.EPI_RELU_RGB
+        st.bias_off = pl.off_bM if pl.fold else O["views_linears.0.bias"]
         _set_k(st, [0, 1, 2, 3, 4], [4, 4, 4, 4, kc_dir])     # slab 4 holds the encoded direction by now
         ldv = W + shape.input_ch_views
         for j in range(4):
-            add_job(pl.fwd_jobs, "views_linears.0.weight", ldv, 0, 64 * j, 128, 64, 0, 128, blob)
+            if pl.fold:      # K slabs of M = W_v1 W_f act directly on the last hidden layer
+                add_job(pl.fwd_jobs, pl.off_M, W, 0, 64 * j, 128, 64, 0, 128, blob)
+            else:
+                add_job(pl.fwd_jobs, "views_linears.0.weight", ldv, 0, 64 * j, 128, 64, 0, 128, blob)
             blob += 128 * 128
         add_job(pl.fwd_jobs, "views_linears.0.weight", ldv, 0, W, 128, shape.input_ch_views, 0, 128, blob)
         blob += 128 * 128
@@ -204,25 +230,37 @@ def build_plan(shape: NetShape) -> Plan:
     if shape.use_viewdirs:
         bwd.pro_head_off, bwd.pro_mask_slot = O["rgb_linear.weight"], D
         dzv_slot, dzf_slot = 1, 3
-        dz_slot = lambda l: 7 + 4 * (D - 1 - l)
+        first_dz = 3 if pl.fold else 7
+        dz_slot = lambda l: first_dz + 4 * (D - 1 - l)
         ldv = W + shape.input_ch_views
-        st = bwd.steps[steps]            # d feature = dZ_v * W_views[:, :W]
-        st.w_off, st.n_out, st.epi = blob, 256, L.EPI_BWD_COPY
-        _set_k(st, [0, 1], [4, 4])
-        for j in range(2):
-            add_job(pl.bwd_jobs, "views_linears.0.weight", ldv, 64 * j, 0, 256, 64, 1, 256, blob)
-            blob += 256 * 128
-        st.stash_slot, st.mask_slot = dzf_slot, -1
-        steps += 1
-        st = bwd.steps[steps]            # dH_{D-1} = d feature * W_feature + d sigma * w_alpha ; mask
-        st.w_off, st.n_out, st.epi = blob, 256, L.EPI_BWD_MASK_SIGMA
-        _set_k(st, [0, 1, 2, 3], [4, 4, 4, 4])
-        for j in range(4):
-            add_job(pl.bwd_jobs, "feature_linear.weight", W, 64 * j, 0, 256, 64, 1, 256, blob)
-            blob += 256 * 128
-        st.n_heads, st.head_off = 1, O["alpha_linear.weight"]
-        st.stash_slot, st.mask_slot = dz_slot(D - 1), D - 1
-        steps += 1
+        if pl.fold:
+            st = bwd.steps[steps]        # dH_{D-1} = dZ_v * M + d sigma * w_alpha ; mask
+            st.w_off, st.n_out, st.epi = blob, 256, L.EPI_BWD_MASK_SIGMA
+            _set_k(st, [0, 1], [4, 4])
+            for j in range(2):
+                add_job(pl.bwd_jobs, pl.off_M, W, 64 * j, 0, 256, 64, 1, 256, blob)
+                blob += 256 * 128
+            st.n_heads, st.head_off = 1, O["alpha_linear.weight"]
+            st.stash_slot, st.mask_slot = dz_slot(D - 1), D - 1
+            steps += 1
+        else:
+            st = bwd.steps[steps]            # d feature = dZ_v * W_views[:, :W]
+            st.w_off, st.n_out, st.epi = blob, 256, L.EPI_BWD_COPY
+            _set_k(st, [0, 1], [4, 4])
+            for j in range(2):
+                add_job(pl.bwd_jobs, "views_linears.0.weight", ldv, 64 * j, 0, 256, 64, 1, 256, blob)
+                blob += 256 * 128
+            st.stash_slot, st.mask_slot = dzf_slot, -1
+            steps += 1
+            st = bwd.steps[steps]            # dH_{D-1} = d feature * W_feature + d sigma * w_alpha ; mask
+            st.w_off, st.n_out, st.epi = blob, 256, L.EPI_BWD_MASK_SIGMA
+            _set_k(st, [0, 1, 2, 3], [4, 4, 4, 4])
+            for j in range(4):
+                add_job(pl.bwd_jobs, "feature_linear.weight", W, 64 * j, 0, 256, 64, 1, 256, blob)
+                blob += 256 * 128
+            st.n_heads, st.head_off = 1, O["alpha_linear.weight"]
+            st.stash_slot, st.mask_slot = dz_slot(D - 1), D - 1
+            steps += 1
     else:
         bwd.pro_head_off, bwd.pro_mask_slot = O["output_linear.weight"], D - 1
         dz_slot = lambda l: 1 + 4 * (D - 1 - l)
@@ -247,9 +285,9 @@ def build_plan(shape: NetShape) -> Plan:
         it = L.WgradItem()
         it.a_bwd_stash, it.a_slot, it.a_nslab = 1, a_slot, a_n
         it.b_from_bwd, it.b_slot, it.b_nslab = 0, b_slot, b_n
-        it.dw_off, it.ld, it.col_off, it.n_cols = O[wname], ld, col_off, n_cols
+        it.dw_off, it.ld, it.col_off, it.n_cols = (O[wname] if isinstance(wname, str) else int(wname)), ld, col_off, n_cols
         it.row_off, it.n_rows = row_off, n_rows
-        it.db_off = O[bname] if bname else -1
+        it.db_off = -1 if bname is None else (O[bname] if isinstance(bname, str) else int(bname))
         it.db_col_off, it.db_n = db_col, db_n
         pl.wgrad.append(it)
 
@@ -263,10 +301,14 @@ def build_plan(shape: NetShape) -> Plan:
         else:
             item(dz_slot(l), 4, H_slot(l - 1), 4, wn, ld, 0, 256, 0, 256, bn, 0, 256)
     if shape.use_viewdirs:
-        item(dzf_slot, 4, H_slot(D - 1), 4, "feature_linear.weight", W, 0, 256, 0, 256, "feature_linear.bias", 0, 256)
+        if not pl.fold:
+            item(dzf_slot, 4, H_slot(D - 1), 4, "feature_linear.weight", W, 0, 256, 0, 256, "feature_linear.bias", 0, 256)
         item(0, 1, H_slot(D - 1), 4, "alpha_linear.weight", W, 0, 256, 3, 1, "alpha_linear.bias", 3, 1)
         ldv = W + shape.input_ch_views
-        item(dzv_slot, 2, feat_slot, 4, "views_linears.0.weight", ldv, 0, 256, 0, 128, "views_linears.0.bias", 0, 128)
+        if pl.fold:      # dM = dZ_v^T H_{D-1} and db' = colsum(dZ_v) into the scratch tail of the gradient buffer
+            item(dzv_slot, 2, H_slot(D - 1), 4, pl.off_M, W, 0, 256, 0, 128, pl.off_bM, 0, 128)
+        else:
+            item(dzv_slot, 2, feat_slot, 4, "views_linears.0.weight", ldv, 0, 256, 0, 128, "views_linears.0.bias", 0, 128)
         item(dzv_slot, 2, 1, 1, "views_linears.0.weight", ldv, W, shape.input_ch_views, 0, 128)
         item(0, 1, hv_slot, 2, "rgb_linear.weight", W // 2, 0, 128, 0, 3, "rgb_linear.bias", 0, 3)
     else:

@@ -144,7 +144,7 @@ class NeRF(nn.Module):
         stale = st is None or st["device"] != dev or any(
             p.data_ptr() != st["flat"].data_ptr() + 4 * pl.offsets[n] for p, n in zip(params, names))
         if stale:
-            flat = torch.zeros(pl.n_params, device=dev, dtype=torch.float32)
+            flat = torch.zeros(pl.n_flat, device=dev, dtype=torch.float32)     # parameters (+ folded operands M, b')
             for p, n in zip(params, names):
                 view = flat[pl.offsets[n]: pl.offsets[n] + p.numel()].view(p.shape)
                 view.copy_(p.data)
@@ -168,11 +168,18 @@ class NeRF(nn.Module):
             return
         pl = self._plan
         lib, s = L.lib(), ops._stream()
+        if pl.fold:
+            L.call("dln_mlp_fold", st["flat"].data_ptr(), *self._fold_args(), s, tag="fold_feature")
         L.call("dln_mlp_pack_weights", st["flat"].data_ptr(), st["fwd_jobs"].data_ptr(), len(pl.fwd_jobs),
                                          st["wf"].data_ptr(), s, tag="pack_weights(fwd)")
         L.call("dln_mlp_pack_weights", st["flat"].data_ptr(), st["bwd_jobs"].data_ptr(), len(pl.bwd_jobs),
                                          st["wb"].data_ptr(), s, tag="pack_weights(bwd)")
         st["version"] = ver
+
+    def _fold_args(self):
+        pl, O = self._plan, self._plan.offsets
+        return (O["views_linears.0.weight"], self.W + self.input_ch_views, O["feature_linear.weight"],
+                O["feature_linear.bias"], O["views_linears.0.bias"], pl.off_M, pl.off_bM)
 
     # ------------------------------------------------------------------ kernels
     def _run_forward(self, mode, a, b, P, keep, force_pack=False):
@@ -219,11 +226,16 @@ class NeRF(nn.Module):
         L.call("dln_mlp_chain", C.byref(pl.bwd), C.byref(args), min(st["sms"], sms) if sms else st["sms"], s,
                tag="mlp_dgrad D=%d" % self.D)
         if gflat is None:
-            gflat = torch.zeros(pl.n_params, device=dev, dtype=torch.float32)
+            gflat = torch.zeros(pl.n_flat, device=dev, dtype=torch.float32)
+        elif pl.fold:
+            gflat[pl.n_params:].zero_()        # dM / db' scratch of THIS call (the buffer accumulates across calls)
         n_items = len(pl.wgrad)
         splits = int(max(1, min(n_tiles, (2 * st["sms"]) // n_items)))
         L.call("dln_mlp_wgrad", st["items"].data_ptr(), n_items, splits, stash_f.data_ptr(), pl.fwd_slots,
                                   stash_b.data_ptr(), pl.bwd_slots, n_tiles, gflat.data_ptr(), s, tag="mlp_wgrad D=%d" % self.D)
+        if pl.fold:
+            L.call("dln_mlp_unfold_grads", st["flat"].data_ptr(), gflat.data_ptr(), *self._fold_args(), s,
+                   tag="unfold_grads")
         grads = []
         for (name, shp), p in zip(self._shape.param_shapes(), self._ordered_params()):
             o = pl.offsets[name]

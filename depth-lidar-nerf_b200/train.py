@@ -153,7 +153,7 @@ def train_step(H, W, focal, batch_rays: Tensor, target_s: Tensor, target_depth: 
     if ray_chunk is None:
         ray_chunk = default_ray_chunk(network_fn, network_fine, N_samples, N_importance)
     n_chunks = max(1, -(-N // max(int(ray_chunk), 1)))
-    gacc = [torch.zeros(net._plan.n_params, device=dev, dtype=torch.float32) for net in (network_fn, network_fine)]
+    gacc = [torch.zeros(net._plan.n_flat, device=dev, dtype=torch.float32) for net in (network_fn, network_fine)]
 
     for c in range(n_chunks):
         if n_chunks == 1:

@@ -205,6 +205,19 @@ int dln_mlp_pack_weights(const float* params_flat, const DlnPackJob* jobs_dev, i
 /* Library / build information (arch string, e.g. "sm_100a"). */
 const char* dln_build_info(void);
 
+/* feature_linear folded into views_linears (run_nerf_helpers.py:126-131: the feature layer has no activation, so
+ * relu(W_v [W_f h + b_f ; dir] + b_v) = relu([W_v1 W_f] h + W_vd dir + [W_v1 b_f + b_v]); the chain then skips one
+ * 256x256 layer in the forward pass, one dgrad step and one wgrad item).  All offsets are float offsets into the flat
+ * buffers; `off_M` ([128 x 256]) and `off_bM` ([128]) are the derived operands behind the parameters.
+ *   dln_mlp_fold         : M = W_v1 W_f, b' = W_v1 b_f + b_v            (after every weight update, before packing)
+ *   dln_mlp_unfold_grads : grads_flat[off_M / off_bM] hold dM / db' of ONE wgrad call; adds dW_v1 += dM W_f^T + db' b_f^T,
+ *                          dW_f += W_v1^T dM, db_f += W_v1^T db', db_v += db' to the parameters' gradient regions. */
+int dln_mlp_fold(float* params_flat, long long off_views_w, int ld_views, long long off_feature_w,
+                 long long off_feature_b, long long off_views_b, long long off_M, long long off_bM, void* stream);
+int dln_mlp_unfold_grads(const float* params_flat, float* grads_flat, long long off_views_w, int ld_views,
+                         long long off_feature_w, long long off_feature_b, long long off_views_b, long long off_M,
+                         long long off_bM, void* stream);
+
 /* ----------------------------------------------------------------------------------------------
  * Optimiser
  * -------------------------------------------------------------------------------------------- */

@@ -106,10 +106,12 @@ def mlp_reference(params, x, spec: O.MLPSpec, emulate_bf16=True):
         out["raw"] = h32 @ params["output_linear.weight"].T + params["output_linear.bias"]
         return out
     sigma = h32 @ params["alpha_linear.weight"].T + params["alpha_linear.bias"]
-    feat32 = h_q @ q(params["feature_linear.weight"]).T + params["feature_linear.bias"]
-    out["feat"] = q(feat32)
-    hv32 = torch.relu(torch.cat([q(feat32), xd_q], -1) @ q(params["views_linears.0.weight"]).T
-                      + params["views_linears.0.bias"])
+    # feature_linear folded into views_linears (plan.build_plan, fold_feature): M = W_v1 W_f formed in fp32 and
+    # rounded to bf16 once, b' = W_v1 b_f + b_v in fp32; the feature vector itself is never materialised
+    Wv, W = params["views_linears.0.weight"], spec.W
+    M = Wv[:, :W] @ params["feature_linear.weight"]
+    b2 = Wv[:, :W] @ params["feature_linear.bias"] + params["views_linears.0.bias"]
+    hv32 = torch.relu(h_q @ q(M).T + xd_q @ q(Wv[:, W:]).T + b2)
     out["HV"] = q(hv32)
     rgb = hv32 @ params["rgb_linear.weight"].T + params["rgb_linear.bias"]
     out["raw"] = torch.cat([rgb, sigma], -1)
@@ -136,9 +138,13 @@ def mlp_forward_emulated(params, x, spec: O.MLPSpec):
     if not spec.use_viewdirs:
         return h32 @ params["output_linear.weight"].T + params["output_linear.bias"]
     sigma = h32 @ params["alpha_linear.weight"].T + params["alpha_linear.bias"]
-    feat = _ste(h_q @ _ste(params["feature_linear.weight"]).T + params["feature_linear.bias"])
-    hv32 = torch.relu(torch.cat([feat, xd_q], -1) @ _ste(params["views_linears.0.weight"]).T
-                      + params["views_linears.0.bias"])
+    # feature_linear is folded into views_linears by the kernels' plan (plan.build_plan, fold_feature): the bf16
+    # operand is M = W_v1 W_f (formed in fp32, rounded once), the bias b' = W_v1 b_f + b_v stays fp32
+    Wv = params["views_linears.0.weight"]
+    W = spec.W
+    M = Wv[:, :W] @ params["feature_linear.weight"]
+    b2 = Wv[:, :W] @ params["feature_linear.bias"] + params["views_linears.0.bias"]
+    hv32 = torch.relu(h_q @ _ste(M).T + xd_q @ _ste(Wv[:, W:]).T + b2)
     rgb = hv32 @ params["rgb_linear.weight"].T + params["rgb_linear.bias"]
     return torch.cat([rgb, sigma], -1)
 

@@ -43,6 +43,42 @@ def _stages_by_offset(flat, jobs):
     return {j.dst_off: _stage_matrix_fast(flat, j) for j in jobs}
 
 
+def extend_flat(plan, flat):
+    """[parameters | M = W_v1 W_f | b' = W_v1 b_f + b_v]: what dln_mlp_fold appends behind the parameters."""
+    out = np.zeros(plan.n_flat)
+    out[:plan.n_params] = flat[:plan.n_params]
+    if plan.fold:
+        O, W = plan.offsets, plan.shape.W
+        ldv = W + plan.shape.input_ch_views
+        Wv1 = flat[O["views_linears.0.weight"]: O["views_linears.0.weight"] + (W // 2) * ldv].reshape(W // 2, ldv)[:, :W]
+        Wf = flat[O["feature_linear.weight"]: O["feature_linear.weight"] + W * W].reshape(W, W)
+        bf = flat[O["feature_linear.bias"]: O["feature_linear.bias"] + W]
+        bv = flat[O["views_linears.0.bias"]: O["views_linears.0.bias"] + W // 2]
+        out[plan.off_M: plan.off_M + (W // 2) * W] = (Wv1 @ Wf).reshape(-1)
+        out[plan.off_bM: plan.off_bM + W // 2] = Wv1 @ bf + bv
+    return out
+
+
+def unfold_grads(plan, flat, g):
+    """dln_mlp_unfold_grads: scratch (dM, db') -> dW_v1 += dM W_f^T + db' b_f^T (feature = W_f h + b_f),
+    dW_f += W_v1^T dM, db_f += W_v1^T db', db_v += db'."""
+    if not plan.fold:
+        return g
+    O, W = plan.offsets, plan.shape.W
+    ldv = W + plan.shape.input_ch_views
+    Wv = flat[O["views_linears.0.weight"]: O["views_linears.0.weight"] + (W // 2) * ldv].reshape(W // 2, ldv)
+    Wf = flat[O["feature_linear.weight"]: O["feature_linear.weight"] + W * W].reshape(W, W)
+    dM = g[plan.off_M: plan.off_M + (W // 2) * W].reshape(W // 2, W)
+    db = g[plan.off_bM: plan.off_bM + W // 2]
+    gWv = g[O["views_linears.0.weight"]: O["views_linears.0.weight"] + (W // 2) * ldv].reshape(W // 2, ldv)
+    bf = flat[O["feature_linear.bias"]: O["feature_linear.bias"] + W]
+    gWv[:, :W] += dM @ Wf.T + np.outer(db, bf)
+    g[O["feature_linear.weight"]: O["feature_linear.weight"] + W * W] += (Wv[:, :W].T @ dM).reshape(-1)
+    g[O["feature_linear.bias"]: O["feature_linear.bias"] + W] += Wv[:, :W].T @ db
+    g[O["views_linears.0.bias"]: O["views_linears.0.bias"] + W // 2] += db
+    return g
+
+
 def run_forward(plan, flat, enc_pts, enc_dir):
     """enc_pts [P, <=64], enc_dir [P, <=64] (already encoded rows).  Returns (out [P,out_ch], stash dict
     slot -> [P,64], masks dict slot -> bool [P, n_out])."""
@@ -125,7 +161,7 @@ def run_backward(plan, flat, d_out, masks):
 
 
 def run_wgrad(plan, stash_f, stash_b):
-    g = np.zeros(plan.n_params)
+    g = np.zeros(plan.n_flat)
     for it in plan.wgrad:
         A = np.concatenate([stash_b[it.a_slot + i] for i in range(it.a_nslab)], 1)        # [P, 64*a_nslab]
         src = stash_b if it.b_from_bwd else stash_f

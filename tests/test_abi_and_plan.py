@@ -96,13 +96,15 @@ def _flat_from(params, plan):
     return flat
 
 
-@pytest.mark.parametrize("D,vd", [(8, True), (4, True), (6, True), (8, False), (3, False)])
-def test_plan_reproduces_oracle_forward_and_gradients(D, vd):
+@pytest.mark.parametrize("D,vd,fold", [(8, True, True), (4, True, True), (6, True, True), (8, True, False),
+                                       (4, True, False), (8, False, True), (3, False, True)])
+def test_plan_reproduces_oracle_forward_and_gradients(D, vd, fold):
     spec = O.MLPSpec(D=D, use_viewdirs=vd)
     params = {k: v.double() for k, v in O.init_params(spec, seed=D).items()}
     shape = plan_mod.NetShape(D=D, input_ch=63, input_ch_views=27, output_ch=5, use_viewdirs=vd)
-    plan = plan_mod.build_plan(shape)
-    flat = _flat_from(params, plan)
+    plan = plan_mod.build_plan(shape, fold_feature=fold)
+    assert plan.fold == (fold and vd)
+    flat = plan_sim.extend_flat(plan, _flat_from(params, plan))      # what dln_mlp_fold appends (M, b')
     g = torch.Generator().manual_seed(D)
     P = 37
     x = torch.randn(P, 90, generator=g, dtype=torch.float64)
@@ -114,7 +116,7 @@ def test_plan_reproduces_oracle_forward_and_gradients(D, vd):
     out, stash_f, masks = plan_sim.run_forward(plan, flat, x[:, :63].numpy(), x[:, 63:].numpy())
     np.testing.assert_allclose(out, y.detach().numpy(), atol=1e-10)
     stash_b = plan_sim.run_backward(plan, flat, cot.numpy(), masks)
-    gflat = plan_sim.run_wgrad(plan, stash_f, stash_b)
+    gflat = plan_sim.unfold_grads(plan, flat, plan_sim.run_wgrad(plan, stash_f, stash_b))
     for name, _ in shape.param_shapes():
         ref = pl[name].grad
         got = gflat[plan.offsets[name]: plan.offsets[name] + params[name].numel()].reshape(params[name].shape)

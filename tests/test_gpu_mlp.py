@@ -49,10 +49,9 @@ def test_forward_layers_against_emulated_reference(D, P):
     for i in range(D):
         r = ref["H%d" % i]
         report("layer %d activations" % i, stash_rows(st, 2 + 4 * i, 4, P), r, atol=2e-2 * r.abs().max().item() + 1e-3)
-    r = ref["feat"]
-    report("feature", stash_rows(st, 2 + 4 * D, 4, P), r, atol=2e-2 * r.abs().max().item() + 1e-3)
+    assert net._plan.fold           # feature_linear is folded into the views layer: no feature slabs in the stash
     r = ref["HV"]
-    report("views hidden", stash_rows(st, 6 + 4 * D, 2, P), r, atol=2e-2 * r.abs().max().item() + 1e-3)
+    report("views hidden", stash_rows(st, 2 + 4 * D, 2, P), r, atol=2e-2 * r.abs().max().item() + 1e-3)
     r = ref["raw"]
     report("raw vs emulated", out, r, atol=5e-3 * r.abs().max().item() + 1e-3)
     full = O.mlp_forward(params, x, spec)
@@ -148,9 +147,9 @@ def test_backward_dz_per_layer():
         if i in spec.skips:
             h = torch.cat([xp, h], -1)
     sigma = h32 @ pl["alpha_linear.weight"].T + pl["alpha_linear.bias"]
-    feat = h @ _ste(pl["feature_linear.weight"]).T + pl["feature_linear.bias"]
-    feat.retain_grad()
-    zv = torch.cat([_ste(feat), xd], -1) @ _ste(pl["views_linears.0.weight"]).T + pl["views_linears.0.bias"]
+    Wv = pl["views_linears.0.weight"]
+    M = Wv[:, :256] @ pl["feature_linear.weight"]              # folded feature_linear (plan.build_plan)
+    zv = h @ _ste(M).T + xd @ _ste(Wv[:, 256:]).T + (Wv[:, :256] @ pl["feature_linear.bias"] + pl["views_linears.0.bias"])
     zv.retain_grad()
     rgb = torch.relu(zv) @ pl["rgb_linear.weight"].T + pl["rgb_linear.bias"]
     (torch.cat([rgb, sigma], -1) * cot).sum().backward()
@@ -173,8 +172,8 @@ def test_backward_dz_per_layer():
     torch.cuda.synchronize()
     sb = read_stash(stash_b, n_tiles, plan.bwd_slots)
     report("d_raw slab", stash_rows(sb, 0, 1, P)[:, :4], bf16r(cot), atol=0)
-    for name, slot, n, refg in [("dZ views", 1, 2, zv.grad), ("d feature", 3, 4, feat.grad)] + \
-            [("dZ layer %d" % l, 7 + 4 * (D - 1 - l), 4, zs[l].grad) for l in range(D - 1, -1, -1)]:
+    for name, slot, n, refg in [("dZ views", 1, 2, zv.grad)] + \
+            [("dZ layer %d" % l, 3 + 4 * (D - 1 - l), 4, zs[l].grad) for l in range(D - 1, -1, -1)]:
         got = stash_rows(sb, slot, n, P)
         print("  %-12s cosine %.5f rel-L2 %.3e" % (name, cosine(got, refg), rel_l2(got, refg)))
         assert cosine(got, refg) >= 0.999 and rel_l2(got, refg) <= 3e-2, name
