@@ -68,33 +68,38 @@ __global__ void __launch_bounds__(256) fold_kernel(float* __restrict__ flat, Fol
 
 __global__ void __launch_bounds__(256) unfold_kernel(const float* __restrict__ flat, float* __restrict__ g, FoldOffsets o) {
   __shared__ float sh[256];
+  __shared__ float out[256];
   const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
   if (b < 128) {                 // row i of dW_v1: (W_f dM_i)[k] + db'_i b_f[k]; a warp per k, lanes over j
     const int i = b;
     sh[t] = g[o.M + i * 256 + t];
     __syncthreads();
     const float dbi = g[o.bM + i];
-    for (int k = warp; k < 256; k += 8) {
+#pragma unroll 4
+    for (int k = warp; k < 256; k += 8) {      // 4 rows of W_f in flight per warp
       const float* wf = flat + o.wf + k * 256;
       float acc = 0.f;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) acc = fmaf(sh[q * 32 + lane], wf[q * 32 + lane], acc);
+      for (int q = 0; q < 8; ++q) acc = fmaf(sh[q * 32 + lane], __ldg(wf + q * 32 + lane), acc);
       acc = dln::warp_sum(acc);
-      if (lane == 0) g[o.wv + (long long)i * o.ldv + k] += acc + dbi * flat[o.bf + k];
+      if (lane == 0) out[k] = acc;
     }
+    __syncthreads();           // one coalesced read-modify-write of the gradient row instead of 256 dependent ones
+    g[o.wv + (long long)i * o.ldv + t] += out[t] + dbi * __ldg(flat + o.bf + t);
   } else if (b < 384) {          // row k of dW_f: sum_i Wv[i][k] dM[i][:]
     const int k = b - 128;
     if (t < 128) sh[t] = flat[o.wv + (long long)t * o.ldv + k];
     __syncthreads();
     float acc = 0.f;
-#pragma unroll 8
+#pragma unroll 16
     for (int i = 0; i < 128; ++i) acc = fmaf(sh[i], g[o.M + i * 256 + t], acc);
     g[o.wf + k * 256 + t] += acc;
   } else {                       // biases
     if (t < 128) sh[t] = g[o.bM + t];
     __syncthreads();
     float acc = 0.f;
-    for (int i = 0; i < 128; ++i) acc = fmaf(flat[o.wv + (long long)i * o.ldv + t], sh[i], acc);
+#pragma unroll 16
+    for (int i = 0; i < 128; ++i) acc = fmaf(__ldg(flat + o.wv + (long long)i * o.ldv + t), sh[i], acc);
     g[o.bf + t] += acc;
     if (t < 128) g[o.bv + t] += sh[t];
   }
