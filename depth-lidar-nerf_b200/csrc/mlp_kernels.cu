@@ -27,12 +27,12 @@ namespace {
 
 constexpr int kThreads = 640;
 constexpr int kEpiWarp0 = 4;
-constexpr int kEpiThreads = 512;   // 16 epilogue warps: 4 per scheduler, one warpgroup per 64-column slab
 constexpr int kNumStages = 4;      // the ring holds one whole 256x256 layer: it is refilled during the epilogue
 constexpr int kStageBytes = 32768;
 constexpr int kSlab = DLN_SLAB_BYTES;
 constexpr int kNumSlabs = 5;       // 0..3 activations, 4 encoded position -> encoded direction (fwd) / d_raw (bwd)
 constexpr bool kSplitN = false;    // issue 256-wide layers as two N=128 halves (measured slower: the MMA issue cost is per instruction)
+constexpr bool kEarlyPrologue = true;  // forward: encode the next tile's positions under the last layer's MMAs
 constexpr bool kDirectStash = false;  // epilogue threads write the stash images straight to global memory instead of
                                       // staging them in smem for bulk copies: parity-green but 50% slower (scattered 16-byte stores)
 constexpr int kMaxBiasFloats = 2432;   // 9 x 256 + 128: netdepth <= 8 with view directions, <= 9 without
@@ -65,29 +65,54 @@ __device__ __forceinline__ uint32_t step_out_mask(const DlnChainStep& s) { retur
 // ---------------------------------------------------------------------------------------------
 // row helpers
 // ---------------------------------------------------------------------------------------------
-// gamma(v) for one 3-vector into e[0..63]; entries past 3+6L are zero.  sincosf once per coordinate,
-// higher octaves by the double-angle recurrence (abs. error <= 2^L * 1e-7, far below bf16 resolution).
-__device__ __forceinline__ void encode_row(float x, float y, float z, int L, float (&e)[64]) {
-#pragma unroll
-  for (int i = 0; i < 64; ++i) e[i] = 0.f;
-  e[0] = x, e[1] = y, e[2] = z;
+// Columns [16q, 16q+16) of gamma(v) = [v, sin(2^f v), cos(2^f v)]_f (entries past 3+6L are zero): the four
+// epilogue warpgroups encode one quarter of a row each.  A quarter touches at most 4 frequencies; sincosf is
+// evaluated once per coordinate at the lowest of them and the higher octaves follow by the double-angle recurrence
+// (at most 3 steps, abs. error < 1e-6).
+template <int q>
+__device__ __forceinline__ void encode_quarter_t(float x, float y, float z, int L, float (&e)[16]) {
+  constexpr int c0 = 16 * q;
+  constexpr int f0 = c0 >= 3 ? (c0 - 3) / 6 : 0;        // lowest frequency index with a column in the quarter
+  const float sc = exp2f((float)f0);
   float s[3], c[3];
-  sincosf(x, &s[0], &c[0]);
-  sincosf(y, &s[1], &c[1]);
-  sincosf(z, &s[2], &c[2]);
+  sincosf(x * sc, &s[0], &c[0]);
+  sincosf(y * sc, &s[1], &c[1]);
+  sincosf(z * sc, &s[2], &c[2]);
+  const float v[3] = {x, y, z};
+  const int ncol = 3 + 6 * L;
 #pragma unroll
-  for (int f = 0; f < 10; ++f) {
-    if (f < L) {
+  for (int i = 0; i < 16; ++i) e[i] = 0.f;
 #pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        e[3 + 6 * f + k] = s[k];
-        e[3 + 6 * f + 3 + k] = c[k];
-        const float s2 = 2.f * s[k] * c[k];
-        const float c2 = 1.f - 2.f * s[k] * s[k];
-        s[k] = s2, c[k] = c2;
+  for (int df = 0; df < 4; ++df) {                       // frequencies f0 .. f0+3 cover any 16-column window
+    const int base = 3 + 6 * (f0 + df) - c0;             // column (relative to the quarter) of sin(2^f x); compile-time
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        if (i == base + k && c0 + i < ncol) e[i] = s[k];
+        if (i == base + 3 + k && c0 + i < ncol) e[i] = c[k];
       }
+      const float s2 = 2.f * s[k] * c[k], c2 = 1.f - 2.f * s[k] * s[k];
+      s[k] = s2, c[k] = c2;
     }
   }
+  if (q == 0) e[0] = x, e[1] = y, e[2] = z;
+  (void)v;
+}
+__device__ __forceinline__ void encode_quarter(float x, float y, float z, int L, int q, float (&e)[16]) {
+  switch (q) {      // q is warpgroup-uniform: the column positions inside a quarter become compile-time constants
+    case 0: encode_quarter_t<0>(x, y, z, L, e); break;
+    case 1: encode_quarter_t<1>(x, y, z, L, e); break;
+    case 2: encode_quarter_t<2>(x, y, z, L, e); break;
+    default: encode_quarter_t<3>(x, y, z, L, e); break;
+  }
+}
+// write columns [16q, 16q+16) of row r (two 16-byte swizzle chunks)
+__device__ __forceinline__ void store_quarter(uint8_t* slab, int r, int q, const uint32_t (&pk)[8]) {
+  uint8_t* row = slab + (r >> 3) * 1024 + (r & 7) * 128;
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+    *reinterpret_cast<uint4*>(row + (((2 * q + h) ^ (r & 7)) << 4)) = make_uint4(pk[4 * h], pk[4 * h + 1], pk[4 * h + 2], pk[4 * h + 3]);
 }
 
 // write one 64-wide row (bf16) of a slab; `gslab` (optional) is the same slab image in the global stash
@@ -246,7 +271,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kNumStages; ++i) mbar_init(&sm->w_full[i], 1), mbar_init(&sm->w_empty[i], 1);
-    for (int i = 0; i < kNumSlabs; ++i) mbar_init(&sm->a_ready[i], i < 4 ? 8 : 4), mbar_init(&sm->s_free[i], 1);   // one arrival per producing warp
+    for (int i = 0; i < kNumSlabs; ++i) mbar_init(&sm->a_ready[i], i < 4 ? 8 : (kBwd ? 4 : 16)), mbar_init(&sm->s_free[i], 1);   // one arrival per producing warp
     for (int i = 0; i < 4; ++i) mbar_init(&sm->acc_full[i >> 1][i & 1], 1);
     for (int i = 0; i < kNumStages; ++i) mbar_init(&sm->grp_full[i], 1);
     mbar_fence_init();
@@ -292,6 +317,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     {
       uint32_t stage = 0, gstep = 0, grp = 0;
       uint32_t par = 0;  // parity of the production count per slab
+      uint32_t catch_mask = 0, catch_par = 0;
       const uint32_t pmask = prologue_mask(prog);
       const uint64_t desc_k = umma_desc_sw128(0, 16, 1024);      // K-major SWIZZLE_128B, SBO 1024 B
       const uint32_t slab_addr0 = smem_u32(slabs), ring_addr0 = smem_u32(wring);
@@ -299,6 +325,11 @@ __global__ void __launch_bounds__(kThreads, 1)
         par ^= pmask;
         for (int s = 0; s < prog.n_steps; ++s, ++gstep) {
           const DlnChainStep& st = prog.steps[s];
+          if (s == 1 && catch_mask) {      // deferred observation of the previous tile's last productions
+            for (int slab = 0; slab < 4; ++slab)
+              if ((catch_mask >> slab) & 1) mbar_wait(&sm->a_ready[slab], ((catch_par >> slab) & 1) ^ 1);
+            catch_mask = 0;
+          }
           // A 256-wide layer is issued as two 128-column halves (M128 N128 K16) when its K slabs fit the ring:
           // the first half's accumulator is committed early, so the epilogue of columns 0..127 overlaps the
           // MMAs of columns 128..255.  (5-slab steps reuse a ring slot and are issued unsplit.)
@@ -365,9 +396,16 @@ __global__ void __launch_bounds__(kThreads, 1)
         // Parity waits are only sound while a waiter is never two phases ahead of the barrier.  No MMA
         // consumes the slabs the LAST step produces (they only go to the stash), so observe them here
         // before waiting for the next tile's productions of the same slabs.
+        // Forward chain: the next tile's first layer reads the encoded position only (slab 4, produced early by
+        // warpgroup 0 while this tile's last MMAs ran), so it is issued BEFORE these waits and overlaps the last
+        // epilogue; the waits then happen ahead of the next tile's step 1 with the parities captured here.
         const uint32_t om = step_out_mask(prog.steps[prog.n_steps - 1]);
-        for (int slab = 0; slab < 4; ++slab)
-          if ((om >> slab) & 1) mbar_wait(&sm->a_ready[slab], ((par >> slab) & 1) ^ 1);
+        if (kEarlyPrologue && !kBwd) {
+          catch_mask = om, catch_par = par;
+        } else {
+          for (int slab = 0; slab < 4; ++slab)
+            if ((om >> slab) & 1) mbar_wait(&sm->a_ready[slab], ((par >> slab) & 1) ^ 1);
+        }
       }
     }
   } else if (warp == 2) {
@@ -448,6 +486,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     ProdTrack pt;
     const uint32_t pmask = prologue_mask(prog);
     uint32_t gstep = 0;
+    bool enc_done = false;      // the encoded positions of the current tile were produced during the previous tile
     // Activation slabs 0..3 live in TENSOR MEMORY for the next layer's MMAs; their shared-memory images exist only
     // as the staging buffer of the stash copies (training), so without a stash they are not written at all.
     auto begin_produce = [&](int slab) {
@@ -460,8 +499,10 @@ __global__ void __launch_bounds__(kThreads, 1)
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm->a_ready[slab]);
     };
-    // one encoded row (position g==0 / direction g==1) for tile row r, fused (rays, z) or pre-encoded (x) input
-    auto encoded_row = [&](long long p, bool valid, int which, float (&e)[64]) {
+    // columns [16g, 16g+16) of one encoded row (which = 0 position / 1 direction) of point p, packed to bf16 pairs;
+    // fused (rays, z) or pre-encoded (x) input.  All four warpgroups take part: a quarter of the row each.
+    auto encoded_quarter = [&](long long p, bool valid, int which, uint32_t (&pk)[8]) {
+      float e[16];
       if (args.x == nullptr) {
         float vx = 0.f, vy = 0.f, vz = 0.f;
         if (valid) {
@@ -474,18 +515,25 @@ __global__ void __launch_bounds__(kThreads, 1)
             vx = rp[args.vd_col], vy = rp[args.vd_col + 1], vz = rp[args.vd_col + 2];
           }
         }
-        encode_row(vx, vy, vz, which == 0 ? prog.L_pts : prog.L_dir, e);
+        encode_quarter(vx, vy, vz, which == 0 ? prog.L_pts : prog.L_dir, g, e);
         if (!valid) {
 #pragma unroll
-          for (int i = 0; i < 64; ++i) e[i] = 0.f;
+          for (int i = 0; i < 16; ++i) e[i] = 0.f;
         }
       } else {
         const int n_pts = 3 + 6 * prog.L_pts, n_dir = 3 + 6 * prog.L_dir;
         const int n = which == 0 ? n_pts : n_dir;
         const float* xp = args.x + (size_t)(valid ? p : 0) * args.x_ld + (which == 0 ? 0 : n_pts);
 #pragma unroll
-        for (int i = 0; i < 64; ++i) e[i] = (valid && i < n) ? xp[i] : 0.f;
+        for (int i = 0; i < 16; ++i) e[i] = (valid && 16 * g + i < n) ? xp[16 * g + i] : 0.f;
       }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) pk[i] = pack_bf16(e[2 * i], e[2 * i + 1]);
+    };
+    auto store_enc = [&](const uint32_t (&pk)[8]) {          // slab 4 <- this warpgroup's quarter; one arrival per warp
+      begin_produce(4);
+      store_quarter(slabs + 4 * kSlab, r, g, pk);
+      end_produce(4);
     };
 
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -496,13 +544,12 @@ __global__ void __launch_bounds__(kThreads, 1)
       auto gslot = [&](int slot) -> uint8_t* { return (kDirectStash && keep) ? gtile + (size_t)slot * kSlab : nullptr; };
       // ------------------------------------------------------------------ prologue
       if (!kBwd) {
-        if (g == 0) {
-          float e[64];
-          encoded_row(p, valid, 0, e);
-          begin_produce(4);
-          store_row64(slabs + 4 * kSlab, gslot(0), r, e);
-          end_produce(4);
+        if (!enc_done) {                // first tile of this CTA (later tiles: produced early, see the last step)
+          uint32_t epk[8];
+          encoded_quarter(p, valid, 0, epk);
+          store_enc(epk);
         }
+        enc_done = false;
       } else {
         // d raw row -> dZ of the first backward layer (through rgb_linear / output_linear) + d_raw slab
         float dr[5];
@@ -568,9 +615,23 @@ __global__ void __launch_bounds__(kThreads, 1)
         const size_t mask_idx = (((size_t)(st.mask_slot < 0 ? 0 : st.mask_slot) * n_tiles + tile) * 4 + g) * 128 + r;
         if (epi >= DLN_EPI_BWD_MASK && st.mask_slot >= 0) mw = reinterpret_cast<const uint2*>(args.masks)[mask_idx];
         const int trole = (et == 0) ? 1 : (et == 384 ? 2 : -1);
+        // Early prologue (forward): while this tile's LAST layer is still in the tensor pipe, warpgroup 0 encodes
+        // the next tile's positions into registers; slab 4 (encoded direction, read by this layer) is free as soon
+        // as acc_full fires, the row is stored and the next tile's layer 0 runs under this layer's epilogue.
+        uint32_t epk[8];
+        const long long next_tile = tile + gridDim.x;
+        const bool early = kEarlyPrologue && !kBwd && s == prog.n_steps - 1 && next_tile < n_tiles && prog.n_steps > 1;
+        if (early) {
+          const long long pn = next_tile * DLN_TILE_ROWS + r;
+          encoded_quarter(pn, pn < args.P, 0, epk);
+        }
         mbar_wait(&sm->acc_full[gstep & 1][0], (gstep >> 1) & 1);
         tc_fence_after();
         if (trole > 0) trace_ev(sm, args.trace, trole, gstep, 1);
+        if (early) {
+          store_enc(epk);
+          enc_done = true;
+        }
 
         const uint32_t t_acc = tmem_base + (gstep & 1) * 256 + lane_addr;
         const bool relu = (epi == DLN_EPI_RELU || epi == DLN_EPI_RELU_SIGMA || epi == DLN_EPI_RELU_RGB || epi == DLN_EPI_RELU_OUT);
@@ -634,14 +695,12 @@ __global__ void __launch_bounds__(kThreads, 1)
         pt.par ^= step_out_mask(st), pt.any |= step_out_mask(st);
 
         if (s == reload_step) {
-          // every MMA that reads the encoded position has completed (acc_full of this step): warpgroup 1
-          // overwrites slab 4 with the encoded view direction for the views layer
-          if (g == 1) {
-            float e[64];
-            encoded_row(p, valid, 1, e);
-            begin_produce(4);
-            store_row64(slabs + 4 * kSlab, gslot(1), r, e);
-            end_produce(4);
+          // every MMA that reads the encoded position has completed (acc_full of this step): slab 4 is
+          // overwritten with the encoded view direction for the views layer
+          {
+            uint32_t dpk[8];
+            encoded_quarter(p, valid, 1, dpk);
+            store_enc(dpk);
           }
           pt.par ^= 0x10u;
         }
