@@ -248,15 +248,7 @@ def run_ours(args):
     d_rays, d_tgt, d_dep = host_rays.to(dev), host_tgt.to(dev), host_dep.to(dev)
 
     def allreduce_grads():
-        if world == 1:
-            return
-        flat = torch.cat([p.grad.reshape(-1) for p in params])
-        dist.all_reduce(flat)
-        flat.div_(world)
-        o = 0
-        for p in params:
-            p.grad.copy_(flat[o:o + p.numel()].view_as(p))
-            o += p.numel()
+        dn.allreduce_gradients(params, world)
 
     def step(rays, t_rgb, t_dep):
         """Drop-in route: the reference's own call sequence (run_nerf.py:1416-1418, :1500-1536, :1759-1761, :1773)."""

@@ -28,7 +28,7 @@ def _batch(n_rgb=12, n_dep=8):
     return torch.randn(2, n_rgb + n_dep, 3, generator=g), torch.rand(n_rgb, 3, generator=g), torch.rand(n_dep, generator=g)
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, flat_views=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     rays, tgt, dep = _batch()
@@ -36,7 +36,19 @@ def _worker(rank, world, port, out):
     r, t, d, _, n_loc = dn.shard_ray_batch(rays, tgt, dep, n_rgb, rank, world)
     model = _model()
     _loss(model, r, t, d, n_loc).backward()
-    dn.allreduce_gradients(list(model.parameters()), world)
+    if flat_views:      # the layout the kernels produce: every .grad a view of one flat buffer (+ a scratch tail)
+        ps = list(model.parameters())
+        flat = torch.cat([p.grad.reshape(-1) for p in ps] + [torch.full((5,), float(rank))])
+        o = 0
+        for p in ps:
+            p.grad = flat[o:o + p.numel()].view_as(p)
+            o += p.numel()
+        extra = torch.nn.Parameter(torch.zeros(3))          # a foreign parameter with its own gradient tensor
+        extra.grad = torch.full((3,), float(rank + 1))
+        dn.allreduce_gradients(ps + [extra], world)
+        assert torch.allclose(extra.grad, torch.full((3,), 1.5)) and torch.allclose(flat[-5:], torch.full((5,), 0.5))
+    else:
+        dn.allreduce_gradients(list(model.parameters()), world)
     if rank == 0:
         torch.save([p.grad for p in model.parameters()], out)
     dist.destroy_process_group()
@@ -51,13 +63,14 @@ def test_shard_bounds_cover_everything():
             assert max(b - a for a, b in spans) - min(b - a for a, b in spans) <= 1
 
 
-def test_sharded_gradients_match_single_process(tmp_path):
+@pytest.mark.parametrize("flat_views", [False, True])
+def test_sharded_gradients_match_single_process(tmp_path, flat_views):
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
     out = str(tmp_path / "g.pt")
-    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, out, flat_views), nprocs=2, join=True)
     got = torch.load(out)
     rays, tgt, dep = _batch()
     model = _model()
