@@ -37,7 +37,7 @@ def _forward_with_stash(net, x_dev):
     return out, st, saved
 
 
-@pytest.mark.parametrize("D,P", [(8, 128), (8, 1000), (4, 300)])
+@pytest.mark.parametrize("D,P", [(8, 128), (8, 1000), (4, 300), (3, 200)])
 def test_forward_layers_against_emulated_reference(D, P):
     net, params, spec = make_net(D)
     x = _inputs(P, seed=D)
@@ -110,8 +110,10 @@ def _reference_grads(params, x, spec, cot, fwd=O.mlp_forward):
 
 
 # the last two cases put several 128-point tiles on every persistent CTA (> 148 tiles) and wrap the wgrad ring
+# netdepth 3 is what content_loss_local*.txt ship for the coarse net (no skip fires), 2 and 6 are other legal depths
 @pytest.mark.parametrize("D,P,vd", [(8, 128, True), (8, 900, True), (4, 515, True), (8, 300, False),
-                                    (8, 128 * 330 + 5, True), (4, 128 * 300, False)])
+                                    (8, 128 * 330 + 5, True), (4, 128 * 300, False), (3, 700, True), (2, 260, True),
+                                    (6, 400, True)])
 def test_backward_gradients(D, P, vd):
     net, params, spec = make_net(D, use_viewdirs=vd)
     x = _inputs(P, seed=10 + D)
