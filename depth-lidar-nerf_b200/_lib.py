@@ -76,6 +76,8 @@ SIGNATURES = {
     "dln_mlp_chain": [C.POINTER(ChainProgram), C.POINTER(ChainArgs), _I, _P],
     "dln_mlp_wgrad": [_P, _I, _I, _P, _I, _P, _I, _LL, _P, _P],
     "dln_mlp_pack_weights": [_P, _P, _I, _P, _P],
+    "dln_inv_depth_smooth_fwd": [_P, _P, _I, _I, _I, _P, _P],
+    "dln_inv_depth_smooth_bwd": [_P, _P, _I, _I, _I, _P, _P, _P, _P],
     "dln_mlp_fold": [_P, _LL, _I, _LL, _LL, _LL, _LL, _LL, _P],
     "dln_mlp_unfold_grads": [_P, _P, _LL, _I, _LL, _LL, _LL, _LL, _LL, _P],
     "dln_adam_step": [_P, _P, _P, _P, _LL, _D, _D, _D, _D, _I, _F, _P],

@@ -205,6 +205,15 @@ int dln_mlp_pack_weights(const float* params_flat, const DlnPackJob* jobs_dev, i
 /* Library / build information (arch string, e.g. "sm_100a"). */
 const char* dln_build_info(void);
 
+/* Image-aware inverse-depth smoothness on a rendered patch: InverseDepthSmoothnessLoss.forward, loss.py:87-133
+ * (called as depth_inv_loss(acc_depth, acc_rgb), run_nerf.py:1249, :1646).  idepth [N,1,H,W], image [N,3,H,W], fp32
+ * contiguous.  fwd ADDS sum|d_x idepth * w_x| to sums[0] and sum|d_y idepth * w_y| to sums[1] (the caller divides by
+ * N*H*(W-1) and N*(H-1)*W and adds: the loss is the sum of the two means); bwd writes d loss / d idepth and
+ * d loss / d image (either may be null), scaled by g_loss[0] (null = 1). */
+int dln_inv_depth_smooth_fwd(const float* idepth, const float* image, int N, int H, int W, float* sums, void* stream);
+int dln_inv_depth_smooth_bwd(const float* idepth, const float* image, int N, int H, int W, const float* g_loss,
+                             float* g_idepth, float* g_image, void* stream);
+
 /* feature_linear folded into views_linears (run_nerf_helpers.py:126-131: the feature layer has no activation, so
  * relu(W_v [W_f h + b_f ; dir] + b_v) = relu([W_v1 W_f] h + W_vd dir + [W_v1 b_f + b_v]); the chain then skips one
  * 256x256 layer in the forward pass, one dgrad step and one wgrad item).  All offsets are float offsets into the flat

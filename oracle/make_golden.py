@@ -304,6 +304,25 @@ def main():
                    g_fine_alpha=np_(net_f.alpha_linear.weight.grad))
     np.savez_compressed(os.path.join(out_dir, "render.npz"), **fix)
 
+    # ---- patch loss: InverseDepthSmoothnessLoss (loss.py:55-133) ----------------------------
+    print("inverse-depth smoothness loss")
+    import loss as ref_loss                      # /root/reference/loss.py (torch only)
+    g = torch.Generator().manual_seed(11)
+    idepth = (torch.rand(2, 1, 9, 14, generator=g) + 0.05).requires_grad_(True)
+    image = torch.rand(2, 3, 9, 14, generator=g)
+    image[0, :, 3, 4] = image[0, :, 3, 5]        # equal neighbours: |.|' = 0 there
+    image = image.requires_grad_(True)
+    l_ref = ref_loss.InverseDepthSmoothnessLoss()(idepth, image)
+    l_ref.backward()
+    i2, m2 = idepth.detach().clone().requires_grad_(True), image.detach().clone().requires_grad_(True)
+    l_m = O.inverse_depth_smoothness(i2, m2)
+    l_m.backward()
+    close(l_m, l_ref, 0.0, "inv-depth smoothness loss")
+    close(i2.grad, idepth.grad, 0.0, "d loss / d idepth")
+    close(m2.grad, image.grad, 0.0, "d loss / d image")
+    np.savez_compressed(os.path.join(out_dir, "inv_depth_smooth.npz"), idepth=np_(idepth), image=np_(image),
+                        loss=np_(l_ref), g_idepth=np_(idepth.grad), g_image=np_(image.grad))
+
     # ---- torchsearchsorted KAT grid (test/test_searchsorted.py:27-44) -----------------
     print("searchsorted grid")
     rs = np.random.RandomState(0)

@@ -337,6 +337,20 @@ def pack_rays(H: int, W: int, focal: float, rays_o: Tensor, rays_d: Tensor, ndc:
 
 
 # --------------------------------------------------------------------------- #
+# patch loss   loss.py:55-133
+# --------------------------------------------------------------------------- #
+def inverse_depth_smoothness(idepth: Tensor, image: Tensor) -> Tensor:
+    """InverseDepthSmoothnessLoss.forward (loss.py:87-133): forward differences a[.., j] - a[.., j+1] (:78-85),
+    image weights exp(-mean_c |d image|) (:121-124), loss = mean|d_x idepth * w_x| + mean|d_y idepth * w_y| (:127-129).
+    idepth (N,1,H,W), image (N,3,H,W)."""
+    gx = lambda t: t[:, :, :, :-1] - t[:, :, :, 1:]        # noqa: E731
+    gy = lambda t: t[:, :, :-1, :] - t[:, :, 1:, :]        # noqa: E731
+    wx = torch.exp(-torch.mean(torch.abs(gx(image)), dim=1, keepdim=True))
+    wy = torch.exp(-torch.mean(torch.abs(gy(image)), dim=1, keepdim=True))
+    return torch.mean(torch.abs(gx(idepth) * wx)) + torch.mean(torch.abs(gy(idepth) * wy))
+
+
+# --------------------------------------------------------------------------- #
 # R11 loss assembly                  run_nerf.py:1451-1466, :1500-1536, :1759-1761
 # --------------------------------------------------------------------------- #
 def train_loss(out: Dict[str, Tensor], n_rgb: int, target_rgb: Tensor, target_depth: Optional[Tensor],

@@ -263,3 +263,40 @@ def test_full_size_properties():
     assert (zs >= mids[:, :1] - 1e-6).all() and (zs <= mids[:, -1:] + 1e-6).all()
     # idempotence: merging is a permutation of the inputs
     assert torch.equal(torch.sort(torch.cat([z, zs], -1), -1)[0], zm)
+
+
+# ---------------------------------------------------------------------------------------- patch loss
+def test_inverse_depth_smoothness_loss_golden_and_patch(golden_dir):
+    """dn.InverseDepthSmoothnessLoss (dln_inv_depth_smooth_fwd/bwd) against the reference's loss.py:55-133: the
+    golden fixture generated by the unmodified reference, then a KITTI-360-sized patch pair [2, ., 94, 352] against
+    the pinned oracle in float64.  fp32 sums over 66 k terms: rtol 2e-6 on the value, 1e-6 x max|g| on gradients."""
+    d = dn()
+    crit = d.InverseDepthSmoothnessLoss()
+    g = np.load(os.path.join(golden_dir, "inv_depth_smooth.npz"))
+    idp = T(g["idepth"]).to(DEV).requires_grad_(True)
+    img = T(g["image"]).to(DEV).requires_grad_(True)
+    loss = crit(idp, img)
+    (3.0 * loss).backward()
+    report("loss (golden)", loss, g["loss"], rtol=2e-6)
+    report("d loss / d idepth (golden)", idp.grad, 3.0 * g["g_idepth"], atol=1e-6 * np.abs(g["g_idepth"]).max() * 3)
+    report("d loss / d image (golden)", img.grad, 3.0 * g["g_image"], atol=1e-6 * np.abs(g["g_image"]).max() * 3)
+    gen = torch.Generator().manual_seed(3)
+    idp = torch.rand(2, 1, 94, 352, generator=gen) + 0.01
+    img = torch.rand(2, 3, 94, 352, generator=gen)
+    i64, m64 = idp.double().requires_grad_(True), img.double().requires_grad_(True)
+    ref = O.inverse_depth_smoothness(i64, m64)
+    ref.backward()
+    a, b = idp.to(DEV).requires_grad_(True), img.to(DEV).requires_grad_(True)
+    out = crit(a, b)
+    out.backward()
+    report("loss (94x352 patch)", out, ref, rtol=2e-6)
+    report("d idepth (94x352 patch)", a.grad, i64.grad, atol=1e-6 * i64.grad.abs().max().item())
+    report("d image (94x352 patch)", b.grad, m64.grad, atol=1e-6 * m64.grad.abs().max().item())
+    # only one input needs a gradient (the no-grad part of a patch); shape / type errors as in the reference
+    a2 = idp.to(DEV).requires_grad_(True)
+    crit(a2, img.to(DEV)).backward()
+    report("d idepth, image without grad", a2.grad, i64.grad, atol=1e-6 * i64.grad.abs().max().item())
+    with pytest.raises(ValueError):
+        crit(idp.to(DEV)[0], img.to(DEV))
+    with pytest.raises(TypeError):
+        crit(idp.numpy(), img.to(DEV))

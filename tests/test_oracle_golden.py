@@ -126,3 +126,15 @@ def test_ndc_and_render_and_loss(golden_dir):
     np.testing.assert_allclose(pfg["rgb_linear.weight"].grad.numpy(), g["g_fine_rgb"], atol=1e-5)
     np.testing.assert_allclose(pfg["alpha_linear.weight"].grad.numpy(), g["g_fine_alpha"], atol=1e-5)
     np.testing.assert_allclose(pcg["pts_linears.0.weight"].grad.numpy(), g["g_coarse_l0"], atol=1e-5)
+
+
+def test_inverse_depth_smoothness_golden(golden_dir):
+    """oracle.inverse_depth_smoothness against InverseDepthSmoothnessLoss of the reference (loss.py:55-133): value
+    and both gradients, bit-exact (same torch ops in the same order)."""
+    g = np.load(os.path.join(golden_dir, "inv_depth_smooth.npz"))
+    d = torch.from_numpy(g["idepth"]).requires_grad_(True)
+    im = torch.from_numpy(g["image"]).requires_grad_(True)
+    loss = O.inverse_depth_smoothness(d, im)
+    loss.backward()
+    assert float(loss) == float(g["loss"])
+    assert np.array_equal(d.grad.numpy(), g["g_idepth"]) and np.array_equal(im.grad.numpy(), g["g_image"])
