@@ -34,7 +34,8 @@ constexpr int kNumSlabs = 5;       // 0..3 activations, 4 encoded position -> en
 constexpr bool kSplitN = false;    // issue 256-wide layers as two N=128 halves (measured slower: the MMA issue cost is per instruction)
 constexpr bool kEarlyPrologue = true;  // forward: encode the next tile's positions under the last layer's MMAs
 constexpr bool kDirectStash = false;  // epilogue threads write the stash images straight to global memory instead of
-                                      // staging them in smem for bulk copies: parity-green but 50% slower (scattered 16-byte stores)
+                                      // staging them in smem for bulk copies: parity-green; 50 % slower with 16-byte stores, still 13 % slower (fwd D=8
+                                      // 1.00 vs 0.88 ms) with one 256-bit store per 32-byte sector -- kept selectable
 constexpr int kMaxBiasFloats = 2432;   // 9 x 256 + 128: netdepth <= 8 with view directions, <= 9 without
 
 struct ChainSmall {
@@ -151,6 +152,26 @@ __device__ __forceinline__ void store_packed32(uint8_t* act, int r, int cb, cons
   for (int q = 0; q < 4; ++q)
     *reinterpret_cast<uint4*>(row + (((ch0 + q) ^ (r & 7)) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
 }
+// Global-memory variants for the direct stash: the two 16-byte swizzle chunks (2k, 2k+1) of a row are adjacent,
+// whatever the XOR with (r & 7) does to their order, so 16 columns are ONE aligned 32-byte sector = one 256-bit store.
+__device__ __forceinline__ void st_global_256(void* p, const uint32_t* lo4, const uint32_t* hi4) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(lo4[0]), "r"(lo4[1]),
+               "r"(lo4[2]), "r"(lo4[3]), "r"(hi4[0]), "r"(hi4[1]), "r"(hi4[2]), "r"(hi4[3])
+               : "memory");
+}
+// columns [cb, cb+16) of row r of a slab image in global memory (pk = 8 packed words)
+__device__ __forceinline__ void store_global16(uint8_t* gslab_base, int r, int cb, const uint32_t* pk) {
+  uint8_t* row = gslab_base + (cb >> 6) * kSlab + (r >> 3) * 1024 + (r & 7) * 128;
+  const int c_even = ((cb & 63) >> 3) ^ (r & 7);          // swizzled position of the first chunk
+  uint8_t* sector = row + ((c_even & ~1) << 4);
+  if (c_even & 1) st_global_256(sector, pk + 4, pk);      // odd position: the first chunk is the upper half
+  else st_global_256(sector, pk, pk + 4);
+}
+__device__ __forceinline__ void store_global32(uint8_t* gslab_base, int r, int cb, const uint32_t (&pk)[16]) {
+  store_global16(gslab_base, r, cb, pk);
+  store_global16(gslab_base, r, cb + 16, pk + 8);
+}
+
 template <bool kRelu>
 __device__ __forceinline__ void store_cols32(uint8_t* act, uint8_t*, int r, int cb, const float (&f)[32]) {
   uint32_t pk[16];
@@ -530,9 +551,10 @@ __global__ void __launch_bounds__(kThreads, 1)
 #pragma unroll
       for (int i = 0; i < 8; ++i) pk[i] = pack_bf16(e[2 * i], e[2 * i + 1]);
     };
-    auto store_enc = [&](const uint32_t (&pk)[8]) {          // slab 4 <- this warpgroup's quarter; one arrival per warp
+    auto store_enc = [&](const uint32_t (&pk)[8], uint8_t* gslab) {   // slab 4 <- this warpgroup's quarter (+ direct stash)
       begin_produce(4);
       store_quarter(slabs + 4 * kSlab, r, g, pk);
+      if (gslab != nullptr) store_global16(gslab, r, 16 * g, pk);
       end_produce(4);
     };
 
@@ -547,7 +569,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         if (!enc_done) {                // first tile of this CTA (later tiles: produced early, see the last step)
           uint32_t epk[8];
           encoded_quarter(p, valid, 0, epk);
-          store_enc(epk);
+          store_enc(epk, gslot(0));
         }
         enc_done = false;
       } else {
@@ -586,7 +608,10 @@ __global__ void __launch_bounds__(kThreads, 1)
               // dZ of the first backward layer -> tensor memory, in the buffer the previous step (last step of the
               // previous tile) accumulated in, over columns only this thread reads
               tmem_st16(tmem_base + ((gstep + 1) & 1) * 256 + lane_addr + cb, pk);
-              if (keep) store_packed32(kDirectStash ? gtile + (size_t)prog.pro_slot * kSlab : slabs, r, cb, pk);
+              if (keep) {
+                if (kDirectStash) store_global32(gtile + (size_t)prog.pro_slot * kSlab, r, cb, pk);
+                else store_packed32(slabs, r, cb, pk);
+              }
               end_produce(cb >> 6);
             }
           }
@@ -629,7 +654,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         tc_fence_after();
         if (trole > 0) trace_ev(sm, args.trace, trole, gstep, 1);
         if (early) {
-          store_enc(epk);
+          store_enc(epk, (kDirectStash && keep) ? reinterpret_cast<uint8_t*>(args.stash) + (size_t)next_tile * prog.stash_slots * kSlab : nullptr);
           enc_done = true;
         }
 
@@ -669,7 +694,7 @@ __global__ void __launch_bounds__(kThreads, 1)
             begin_produce(cb0 >> 6);
             if (trole > 0) trace_ev(sm, args.trace, trole, gstep, 5);
             if (!kDirectStash) store_packed32(slabs, r, cb0, pk);
-            else if (st.stash_slot >= 0) store_packed32(gtile + (size_t)st.stash_slot * kSlab, r, cb0, pk);
+            else if (st.stash_slot >= 0) store_global32(gtile + (size_t)st.stash_slot * kSlab, r, cb0, pk);
           }
           if (trole > 0) trace_ev(sm, args.trace, trole, gstep, 0);
           tmem_st16(t_acc + cb0, pk);
@@ -684,7 +709,7 @@ __global__ void __launch_bounds__(kThreads, 1)
             if (keep) {
               begin_produce(cb1 >> 6);
               if (!kDirectStash) store_packed32(slabs, r, cb1, pk);
-              else if (st.stash_slot >= 0) store_packed32(gtile + (size_t)st.stash_slot * kSlab, r, cb1, pk);
+              else if (st.stash_slot >= 0) store_global32(gtile + (size_t)st.stash_slot * kSlab, r, cb1, pk);
             }
             end_produce(cb1 >> 6);
             if (trole > 0) trace_ev(sm, args.trace, trole, gstep, 7);
@@ -700,7 +725,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           {
             uint32_t dpk[8];
             encoded_quarter(p, valid, 1, dpk);
-            store_enc(dpk);
+            store_enc(dpk, gslot(1));
           }
           pt.par ^= 0x10u;
         }
