@@ -41,6 +41,7 @@ constexpr int kMaxBiasFloats = 2432;   // 9 x 256 + 128: netdepth <= 8 with view
 struct ChainSmall {
   uint64_t w_full[kNumStages], w_empty[kNumStages];
   uint64_t a_ready[kNumSlabs], s_free[kNumSlabs];
+  uint64_t s_ready[4];             // smem staging image of activation slab i complete (epilogue -> stash lane)
   uint64_t acc_full[2][2];         // [accumulator buffer][128-column half]
   uint64_t grp_full[kNumStages];   // weights of a group of <=4 stages have landed (helper -> MMA thread); rotating,
                                    // so a parity wait can never alias: at most kNumStages groups are ever in flight
@@ -293,7 +294,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   if (threadIdx.x == 0) {
     for (int i = 0; i < kNumStages; ++i) mbar_init(&sm->w_full[i], 1), mbar_init(&sm->w_empty[i], 1);
     for (int i = 0; i < kNumSlabs; ++i) mbar_init(&sm->a_ready[i], i < 4 ? 8 : (kBwd ? 4 : 16)), mbar_init(&sm->s_free[i], 1);   // one arrival per producing warp
-    for (int i = 0; i < 4; ++i) mbar_init(&sm->acc_full[i >> 1][i & 1], 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&sm->acc_full[i >> 1][i & 1], 1), mbar_init(&sm->s_ready[i], 8);
     for (int i = 0; i < kNumStages; ++i) mbar_init(&sm->grp_full[i], 1);
     mbar_fence_init();
   }
@@ -452,7 +453,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         };
         auto handle = [&](int slab, int slot) {
           if (pending == slab) flush();
-          mbar_wait(&sm->a_ready[slab], (par >> slab) & 1u);
+          mbar_wait(slab < 4 ? &sm->s_ready[slab] : &sm->a_ready[slab], (par >> slab) & 1u);
           par ^= 1u << slab;
           if (slab < 4) trace_ev(sm, args.trace, 3, sgstep, slab);
           if (slot >= 0) {
@@ -513,12 +514,31 @@ __global__ void __launch_bounds__(kThreads, 1)
     auto begin_produce = [&](int slab) {
       if (!kDirectStash && keep && ((pt.any >> slab) & 1)) mbar_wait(&sm->s_free[slab], ((pt.par >> slab) & 1) ^ 1);
     };
-    auto end_produce = [&](int slab) {   // one arrival per warp
-      if (slab < 4) tmem_st_wait();
-      if (slab == 4 || (keep && !kDirectStash)) fence_async_smem();
+    auto end_produce = [&](int slab) {   // slab 4 (shared memory only): one arrival per warp
+      fence_async_smem();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm->a_ready[slab]);
+    };
+    // Activation slab: the MMA warp is released as soon as the tensor-memory write has landed; the shared-memory
+    // staging image for the stash copy (wait for the previous copy, 4 x st.shared, proxy fence) comes AFTER that
+    // arrival and signals the stash lane on its own barrier -- it is off the epilogue -> MMA critical path.
+    auto publish = [&](int slab, int cb, const uint32_t (&pk)[16], uint8_t* gdirect) {
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm->a_ready[slab]);
+      if (keep) {
+        if (kDirectStash) {
+          if (gdirect != nullptr) store_global32(gdirect, r, cb, pk);
+        } else {
+          begin_produce(slab);
+          store_packed32(slabs, r, cb, pk);
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sm->s_ready[slab]);
+        }
+      }
     };
     // columns [16g, 16g+16) of one encoded row (which = 0 position / 1 direction) of point p, packed to bf16 pairs;
     // fused (rays, z) or pre-encoded (x) input.  All four warpgroups take part: a quarter of the row each.
@@ -588,7 +608,6 @@ __global__ void __launch_bounds__(kThreads, 1)
             if (128 * h < width) {
               const int cb = 128 * h + 32 * g;
               const uint32_t mk = h ? mw.y : mw.x;
-              begin_produce(cb >> 6);
               float f[32];
 #pragma unroll
               for (int i = 0; i < 32; ++i) f[i] = 0.f;
@@ -608,11 +627,7 @@ __global__ void __launch_bounds__(kThreads, 1)
               // dZ of the first backward layer -> tensor memory, in the buffer the previous step (last step of the
               // previous tile) accumulated in, over columns only this thread reads
               tmem_st16(tmem_base + ((gstep + 1) & 1) * 256 + lane_addr + cb, pk);
-              if (keep) {
-                if (kDirectStash) store_global32(gtile + (size_t)prog.pro_slot * kSlab, r, cb, pk);
-                else store_packed32(slabs, r, cb, pk);
-              }
-              end_produce(cb >> 6);
+              publish(cb >> 6, cb, pk, keep ? gtile + (size_t)prog.pro_slot * kSlab : nullptr);
             }
           }
         }
@@ -690,15 +705,10 @@ __global__ void __launch_bounds__(kThreads, 1)
           if (trole > 0) trace_ev(sm, args.trace, trole, gstep, 2);
           dispatch(v, mw.x, mo0, cb0);
           if (trole > 0) trace_ev(sm, args.trace, trole, gstep, 3);
-          if (keep) {
-            begin_produce(cb0 >> 6);
-            if (trole > 0) trace_ev(sm, args.trace, trole, gstep, 5);
-            if (!kDirectStash) store_packed32(slabs, r, cb0, pk);
-            else if (st.stash_slot >= 0) store_global32(gtile + (size_t)st.stash_slot * kSlab, r, cb0, pk);
-          }
-          if (trole > 0) trace_ev(sm, args.trace, trole, gstep, 0);
+          uint8_t* const gdirect = (keep && st.stash_slot >= 0) ? gtile + (size_t)st.stash_slot * kSlab : nullptr;
           tmem_st16(t_acc + cb0, pk);
-          end_produce(cb0 >> 6);
+          if (trole > 0) trace_ev(sm, args.trace, trole, gstep, 0);
+          publish(cb0 >> 6, cb0, pk, gdirect);
           if (trole > 0) trace_ev(sm, args.trace, trole, gstep, 6);
           if (st.n_out == 256) {                     // chunk 1: features [128 + 32g, +32)
             const int cb1 = 128 + 32 * g;
@@ -706,12 +716,7 @@ __global__ void __launch_bounds__(kThreads, 1)
             tmem_ld_wait();
             dispatch(v, mw.y, mo1, cb1);
             tmem_st16(t_acc + cb1, pk);
-            if (keep) {
-              begin_produce(cb1 >> 6);
-              if (!kDirectStash) store_packed32(slabs, r, cb1, pk);
-              else if (st.stash_slot >= 0) store_global32(gtile + (size_t)st.stash_slot * kSlab, r, cb1, pk);
-            }
-            end_produce(cb1 >> 6);
+            publish(cb1 >> 6, cb1, pk, gdirect);
             if (trole > 0) trace_ev(sm, args.trace, trole, gstep, 7);
           }
           if (relu && st.mask_slot >= 0 && args.masks != nullptr)
