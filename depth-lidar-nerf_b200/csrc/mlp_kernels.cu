@@ -1,22 +1,24 @@
 // NeRF MLP (run_nerf_helpers.py:77-145) on the Blackwell tensor cores.
 //
-// Three kernels, all tcgen05 (UMMA, fp32 accumulators in TMEM) with bf16 operands staged in shared
-// memory in the SWIZZLE_128B canonical layout and moved by the bulk-copy (TMA) engine:
+// Three kernels, all tcgen05 (UMMA, fp32 accumulators in TMEM), bf16 operands, weights moved by the bulk-copy (TMA)
+// engine as SWIZZLE_128B canonical shared-memory images:
 //
-//  chain_kernel   the fused per-tile layer chain.  One persistent CTA per SM walks 128-point tiles; the
-//                 activations of the tile stay in shared memory from the first layer to the last, the
-//                 weights of every layer are streamed from L2 through a 3-stage ring of 32 KB stages,
-//                 and the epilogue of layer l (TMEM -> bias/ReLU -> bf16 -> smem) overlaps the MMAs of
-//                 layer l+1 slab by slab (two TMEM accumulators).  The same machine runs the forward
-//                 pass (prologue = stratified point + positional encoding computed in-kernel, heads =
-//                 alpha / rgb on CUDA cores in the epilogue) and the dgrad pass (prologue = d raw ->
-//                 d hidden through rgb_linear, epilogue = ReLU mask from 1-bit masks).
-//  wgrad_kernel   dW += dZ^T * X over all points, both operands read back from the slab stashes the
-//                 chain kernels wrote, as MN-major UMMA operands; split over the points across CTAs.
+//  chain_kernel   the fused per-tile layer chain.  One persistent CTA per SM walks 128-point tiles.  The weights
+//                 of every layer are streamed from L2 through a ring of four 32 KB stages (= one whole 256x256
+//                 layer, refilled while the epilogue runs).  The epilogue of layer l (TMEM -> bias / ReLU ->
+//                 bf16) writes the activations back IN PLACE into tensor memory, where the MMAs of layer l+1
+//                 read them as their A operand (TS form) while accumulating into the other of the two TMEM
+//                 buffers; shared-memory images of the activations exist only as staging for the stash copies
+//                 (training).  The same machine runs the forward pass (positions + positional encoding computed
+//                 in-kernel by all four epilogue warpgroups, heads = alpha / rgb on CUDA cores) and the dgrad pass
+//                 (prologue = d raw -> d hidden through rgb_linear, epilogue = 1-bit ReLU masks).
+//  wgrad_kernel   dW += dZ^T * X over all points, both operands read back from the slab stashes the chain
+//                 kernels wrote, as MN-major UMMA operands; split over the points across CTAs.
 //  pack_kernel    fp32 master weights -> bf16 swizzled weight stages.
 //
-// Warp roles in chain_kernel (384 threads): warp 0 weight producer, warp 1 MMA issuer (+TMEM owner),
-// warp 2 stash writer, warps 4..11 epilogue (two warpgroups, each owns half of the output columns).
+// Warp roles in chain_kernel (640 threads): warp 0 weight producer, warp 1 MMA issuer (+TMEM owner), warp 2 stash
+// lane, warp 3 weight-arrival helper, warps 4..19 epilogue (four warpgroups; warpgroup g owns the columns
+// [128 h + 32 g, +32), h = 0, 1, of every layer output).
 #include "common.cuh"
 #include "../../include/dlnerf_b200.h"
 #include <math.h>
@@ -31,7 +33,6 @@ constexpr int kNumStages = 4;      // the ring holds one whole 256x256 layer: it
 constexpr int kStageBytes = 32768;
 constexpr int kSlab = DLN_SLAB_BYTES;
 constexpr int kNumSlabs = 5;       // 0..3 activations, 4 encoded position -> encoded direction (fwd) / d_raw (bwd)
-constexpr bool kSplitN = false;    // issue 256-wide layers as two N=128 halves (measured slower: the MMA issue cost is per instruction)
 constexpr bool kEarlyPrologue = true;  // forward: encode the next tile's positions under the last layer's MMAs
 constexpr bool kDirectStash = false;  // epilogue threads write the stash images straight to global memory instead of
                                       // staging them in smem for bulk copies: parity-green; 50 % slower with 16-byte stores, still 13 % slower (fwd D=8
@@ -42,7 +43,7 @@ struct ChainSmall {
   uint64_t w_full[kNumStages], w_empty[kNumStages];
   uint64_t a_ready[kNumSlabs], s_free[kNumSlabs];
   uint64_t s_ready[4];             // smem staging image of activation slab i complete (epilogue -> stash lane)
-  uint64_t acc_full[2][2];         // [accumulator buffer][128-column half]
+  uint64_t acc_full[2];            // accumulator buffer complete (tcgen05.commit of the step's last MMA)
   uint64_t grp_full[kNumStages];   // weights of a group of <=4 stages have landed (helper -> MMA thread); rotating,
                                    // so a parity wait can never alias: at most kNumStages groups are ever in flight
   uint32_t tmem_base;
@@ -173,13 +174,6 @@ __device__ __forceinline__ void store_global32(uint8_t* gslab_base, int r, int c
   store_global16(gslab_base, r, cb + 16, pk + 8);
 }
 
-template <bool kRelu>
-__device__ __forceinline__ void store_cols32(uint8_t* act, uint8_t*, int r, int cb, const float (&f)[32]) {
-  uint32_t pk[16];
-  pack32<kRelu>(f, pk);
-  store_packed32(act, r, cb, pk);
-}
-
 // two fp32 adds in one instruction (FADD2)
 __device__ __forceinline__ void add2(float& a0, float& a1, float b0, float b1) {
   unsigned long long a, b;
@@ -294,7 +288,8 @@ __global__ void __launch_bounds__(kThreads, 1)
   if (threadIdx.x == 0) {
     for (int i = 0; i < kNumStages; ++i) mbar_init(&sm->w_full[i], 1), mbar_init(&sm->w_empty[i], 1);
     for (int i = 0; i < kNumSlabs; ++i) mbar_init(&sm->a_ready[i], i < 4 ? 8 : (kBwd ? 4 : 16)), mbar_init(&sm->s_free[i], 1);   // one arrival per producing warp
-    for (int i = 0; i < 4; ++i) mbar_init(&sm->acc_full[i >> 1][i & 1], 1), mbar_init(&sm->s_ready[i], 8);
+    for (int i = 0; i < 2; ++i) mbar_init(&sm->acc_full[i], 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&sm->s_ready[i], 8);
     for (int i = 0; i < kNumStages; ++i) mbar_init(&sm->grp_full[i], 1);
     mbar_fence_init();
   }
@@ -352,65 +347,50 @@ __global__ void __launch_bounds__(kThreads, 1)
               if ((catch_mask >> slab) & 1) mbar_wait(&sm->a_ready[slab], ((catch_par >> slab) & 1) ^ 1);
             catch_mask = 0;
           }
-          // A 256-wide layer is issued as two 128-column halves (M128 N128 K16) when its K slabs fit the ring:
-          // the first half's accumulator is committed early, so the epilogue of columns 0..127 overlaps the
-          // MMAs of columns 128..255.  (5-slab steps reuse a ring slot and are issued unsplit.)
-          const bool split = kSplitN && st.n_out == 256 && st.nk <= kNumStages;
-          const int nhalf = split ? 2 : 1;
-          const uint32_t idesc = umma_idesc_bf16(128, split ? 128 : st.n_out, 0, 0);
-          const uint32_t stage0 = stage;
+          const uint32_t idesc = umma_idesc_bf16(128, st.n_out, 0, 0);
+          const uint32_t d_tmem = tmem_base + (gstep & 1) * 256;
           trace_ev(sm, args.trace, 0, gstep, 0);
-          for (int half = 0; half < nhalf; ++half) {
-            const uint32_t d_tmem = tmem_base + (gstep & 1) * 256 + half * 128;
-            stage = stage0;
-            for (int j = 0; j < st.nk; ++j) {
-              const int slab = st.kslab[j];
-              if (half == 0) {
-                mbar_wait(&sm->a_ready[slab], ((par >> slab) & 1) ^ 1);   // last production completed
-                if (j < 5) trace_ev(sm, args.trace, 0, gstep, 1 + j);
-                if ((j & 3) == 0) {          // the helper thread has seen w_full of this group of <=4 stages
-                  mbar_wait(&sm->grp_full[grp & (kNumStages - 1)], (grp / kNumStages) & 1);
-                  ++grp;
-                }
-                tc_fence_after();
-              }
-              // descriptors differ only in the 14-bit start-address field: +2 (= 32 B) per K=16 step
-              const uint64_t bd = desc_k | (uint64_t)((ring_addr0 + stage * kStageBytes + half * (kStageBytes / 2)) >> 4);
-              const int kc = st.kcnt[j];
-              if (slab < 4) {
-                // activations of the previous step: bf16 pairs in tensor memory, written in place over the
-                // accumulator buffer the previous step used -- each 32-feature group [32q, +32) packed into the
-                // first 16 of its own 32 accumulator columns, so K step kk of slab j starts at column
-                // 64 j + 32 (kk >> 1) + 8 (kk & 1)
-                const uint32_t at = tmem_base + ((gstep + 1) & 1) * 256 + slab * 64;
-                if (elect_one()) {
-                  umma_bf16_ts(d_tmem, at, bd, idesc, j != 0);
-                  if (kc > 1) umma_bf16_ts(d_tmem, at + 8, bd + 2, idesc, 1);
-                  if (kc > 2) umma_bf16_ts(d_tmem, at + 32, bd + 4, idesc, 1);
-                  if (kc > 3) umma_bf16_ts(d_tmem, at + 40, bd + 6, idesc, 1);
-                  if (half == nhalf - 1) umma_commit(&sm->w_empty[stage]);
-                }
-              } else {
-                // encoded position / direction (fwd) or d_raw (bwd): a shared-memory slab
-                const uint64_t ad = desc_k | (uint64_t)((slab_addr0 + slab * kSlab) >> 4);
-                if (elect_one()) {
-                  umma_bf16(d_tmem, ad, bd, idesc, j != 0);
-                  if (kc > 1) umma_bf16(d_tmem, ad + 2, bd + 2, idesc, 1);
-                  if (kc > 2) umma_bf16(d_tmem, ad + 4, bd + 4, idesc, 1);
-                  if (kc > 3) umma_bf16(d_tmem, ad + 6, bd + 6, idesc, 1);
-                  if (half == nhalf - 1) umma_commit(&sm->w_empty[stage]);
-                }
-              }
-              __syncwarp();
-              if (++stage == kNumStages) stage = 0;
+          for (int j = 0; j < st.nk; ++j) {
+            const int slab = st.kslab[j];
+            mbar_wait(&sm->a_ready[slab], ((par >> slab) & 1) ^ 1);   // last production completed
+            if (j < 5) trace_ev(sm, args.trace, 0, gstep, 1 + j);
+            if ((j & 3) == 0) {          // the helper thread has seen w_full of this group of <=4 stages
+              mbar_wait(&sm->grp_full[grp & (kNumStages - 1)], (grp / kNumStages) & 1);
+              ++grp;
             }
-            if (elect_one()) {
-              umma_commit(&sm->acc_full[gstep & 1][half]);
-              if (!split) umma_commit(&sm->acc_full[gstep & 1][1]);
+            tc_fence_after();
+            // descriptors differ only in the 14-bit start-address field: +2 (= 32 B) per K=16 step
+            const uint64_t bd = desc_k | (uint64_t)((ring_addr0 + stage * kStageBytes) >> 4);
+            const int kc = st.kcnt[j];
+            if (slab < 4) {
+              // activations of the previous step: bf16 pairs in tensor memory, written in place over the
+              // accumulator buffer the previous step used -- each 32-feature group [32q, +32) packed into the
+              // first 16 of its own 32 accumulator columns, so K step kk of slab j starts at column
+              // 64 j + 32 (kk >> 1) + 8 (kk & 1)
+              const uint32_t at = tmem_base + ((gstep + 1) & 1) * 256 + slab * 64;
+              if (elect_one()) {
+                umma_bf16_ts(d_tmem, at, bd, idesc, j != 0);
+                if (kc > 1) umma_bf16_ts(d_tmem, at + 8, bd + 2, idesc, 1);
+                if (kc > 2) umma_bf16_ts(d_tmem, at + 32, bd + 4, idesc, 1);
+                if (kc > 3) umma_bf16_ts(d_tmem, at + 40, bd + 6, idesc, 1);
+                umma_commit(&sm->w_empty[stage]);
+              }
+            } else {
+              // encoded position / direction (fwd) or d_raw (bwd): a shared-memory slab
+              const uint64_t ad = desc_k | (uint64_t)((slab_addr0 + slab * kSlab) >> 4);
+              if (elect_one()) {
+                umma_bf16(d_tmem, ad, bd, idesc, j != 0);
+                if (kc > 1) umma_bf16(d_tmem, ad + 2, bd + 2, idesc, 1);
+                if (kc > 2) umma_bf16(d_tmem, ad + 4, bd + 4, idesc, 1);
+                if (kc > 3) umma_bf16(d_tmem, ad + 6, bd + 6, idesc, 1);
+                umma_commit(&sm->w_empty[stage]);
+              }
             }
             __syncwarp();
-            if (half == 0) trace_ev(sm, args.trace, 0, gstep, 6);
+            if (++stage == kNumStages) stage = 0;
           }
+          if (elect_one()) umma_commit(&sm->acc_full[gstep & 1]);
+          __syncwarp();
           trace_ev(sm, args.trace, 0, gstep, 7);
           par ^= step_out_mask(st);
           if (s == reload_step) par ^= 0x10u;
@@ -665,7 +645,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           const long long pn = next_tile * DLN_TILE_ROWS + r;
           encoded_quarter(pn, pn < args.P, 0, epk);
         }
-        mbar_wait(&sm->acc_full[gstep & 1][0], (gstep >> 1) & 1);
+        mbar_wait(&sm->acc_full[gstep & 1], (gstep >> 1) & 1);
         tc_fence_after();
         if (trole > 0) trace_ev(sm, args.trace, trole, gstep, 1);
         if (early) {
