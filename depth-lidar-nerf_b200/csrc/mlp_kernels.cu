@@ -782,6 +782,7 @@ __global__ void __launch_bounds__(kWgThreads, 1)
   WgradSmall* sm = reinterpret_cast<WgradSmall*>(smem + kWgStages * kWgStageBytes);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+  // item-major grid with EQUAL split counts: CTA k of every item covers the same tile range (see the host side)
   const DlnWgradItem it = items[blockIdx.x / splits];
   const int split = blockIdx.x % splits;
   const long long per = (n_tiles + splits - 1) / splits;

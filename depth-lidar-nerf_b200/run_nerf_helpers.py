@@ -230,7 +230,11 @@ class NeRF(nn.Module):
         elif pl.fold:
             gflat[pl.n_params:].zero_()        # dM / db' scratch of THIS call (the buffer accumulates across calls)
         n_items = len(pl.wgrad)
-        splits = int(max(1, min(n_tiles, (2 * st["sms"]) // n_items)))
+        # ONE wave (n_items * splits <= #SMs): every item's CTA k then walks the same tile range at about the same
+        # pace, so slabs two items share (dZ of the skip layer, the last hidden layer, dZ_views) are found in L2 by
+        # the second reader and neighbouring slots of a tile are read together; two waves or per-item split counts
+        # proportional to the bytes were both measured 10-50 % slower.
+        splits = int(max(1, min(n_tiles, st["sms"] // n_items)))
         L.call("dln_mlp_wgrad", st["items"].data_ptr(), n_items, splits, stash_f.data_ptr(), pl.fwd_slots,
                                   stash_b.data_ptr(), pl.bwd_slots, n_tiles, gflat.data_ptr(), s, tag="mlp_wgrad D=%d" % self.D)
         if pl.fold:
