@@ -76,47 +76,44 @@ def batchify_rays(rays_flat, chunk=1024 * 32, **kwargs):
     return {k: (v[0] if len(v) == 1 else torch.cat(v, 0)) for k, v in all_ret.items()}
 
 
+def _ray_batch(H, W, focal, rays, c2w, ndc, near, far, use_viewdirs, c2w_staticcam=None, depths=None):
+    """The flat [N, 8 | 9 | 11 | 12] batch render_rays consumes (run_nerf.py:138-183) and the leading shape of the
+    rays: [o, d, near, far, (depth), (unit view direction taken BEFORE the NDC warp)].  Device tensors with scalar
+    near / far -- the training loop -- are packed by one kernel (ops.pack_rays); everything else (static camera,
+    per-ray depths, tensor-valued bounds, CPU tensors) goes through the equivalent torch operations."""
+    origins, dirs = get_rays(H, W, focal, c2w) if c2w is not None else rays
+    lead = list(dirs.shape[:-1])
+    scalar_bounds = not torch.is_tensor(near) and not torch.is_tensor(far)
+    if c2w_staticcam is None and depths is None and scalar_bounds and torch.is_tensor(dirs) and dirs.is_cuda:
+        return ops.pack_rays(H, W, focal, origins, dirs, ndc, near, far, use_viewdirs), lead
+    unit = None
+    if use_viewdirs:
+        unit = (dirs / dirs.norm(dim=-1, keepdim=True)).reshape(-1, 3).float()
+        if c2w_staticcam is not None:          # view directions from c2w, geometry from the static camera (:150-152)
+            origins, dirs = get_rays(H, W, focal, c2w_staticcam)
+    if ndc:
+        origins, dirs = ndc_rays(H, W, focal, 1., origins, dirs)
+    origins, dirs = origins.reshape(-1, 3).float(), dirs.reshape(-1, 3).float()
+    ones = torch.ones_like(dirs[:, :1])
+    parts = [origins, dirs, near * ones, far * ones]
+    if depths is not None:
+        parts.append(depths.reshape(-1, 1))
+    if unit is not None:
+        parts.append(unit)
+    return torch.cat(parts, -1), lead
+
+
+def _unflatten(all_ret, lead):
+    return {k: v.reshape(lead + list(v.shape[1:])) for k, v in all_ret.items()}
+
+
 def render(H, W, focal, chunk=1024 * 32, rays=None, c2w=None, ndc=True, near=0., far=1., use_viewdirs=False,
            c2w_staticcam=None, depths=None, **kwargs):
     """run_nerf.py:112-194.  Returns [rgb_map, disp_map, acc_map, depth_map, extras]."""
-    if c2w is not None:
-        rays_o, rays_d = get_rays(H, W, focal, c2w)
-    else:
-        rays_o, rays_d = rays
-    if (c2w_staticcam is None and depths is None and torch.is_tensor(rays_d) and rays_d.is_cuda
-            and not isinstance(near, torch.Tensor) and not isinstance(far, torch.Tensor)):
-        # the training-loop case: one kernel instead of the ~15 element-wise launches below (same operation order)
-        sh = rays_d.shape
-        packed = ops.pack_rays(H, W, focal, rays_o, rays_d, ndc, near, far, use_viewdirs)
-        all_ret = batchify_rays(packed, chunk, **kwargs)
-        for k in all_ret:
-            all_ret[k] = torch.reshape(all_ret[k], list(sh[:-1]) + list(all_ret[k].shape[1:]))
-        k_extract = ['rgb_map', 'disp_map', 'acc_map', 'depth_map']
-        return [all_ret[k] for k in k_extract] + [{k: all_ret[k] for k in all_ret if k not in k_extract}]
-    viewdirs = None
-    if use_viewdirs:
-        viewdirs = rays_d
-        if c2w_staticcam is not None:
-            rays_o, rays_d = get_rays(H, W, focal, c2w_staticcam)
-        viewdirs = viewdirs / torch.norm(viewdirs, dim=-1, keepdim=True)
-        viewdirs = torch.reshape(viewdirs, [-1, 3]).float()
-    sh = rays_d.shape
-    if ndc:
-        rays_o, rays_d = ndc_rays(H, W, focal, 1., rays_o, rays_d)
-    rays_o = torch.reshape(rays_o, [-1, 3]).float()
-    rays_d = torch.reshape(rays_d, [-1, 3]).float()
-    near, far = near * torch.ones_like(rays_d[..., :1]), far * torch.ones_like(rays_d[..., :1])
-    cols = [rays_o, rays_d, near, far]
-    if depths is not None:
-        cols.append(depths.reshape(-1, 1))
-    if use_viewdirs:
-        cols.append(viewdirs)
-    packed = torch.cat(cols, -1)
-    all_ret = batchify_rays(packed, chunk, **kwargs)
-    for k in all_ret:
-        all_ret[k] = torch.reshape(all_ret[k], list(sh[:-1]) + list(all_ret[k].shape[1:]))
-    k_extract = ['rgb_map', 'disp_map', 'acc_map', 'depth_map']
-    return [all_ret[k] for k in k_extract] + [{k: all_ret[k] for k in all_ret if k not in k_extract}]
+    packed, lead = _ray_batch(H, W, focal, rays, c2w, ndc, near, far, use_viewdirs, c2w_staticcam, depths)
+    out = _unflatten(batchify_rays(packed, chunk, **kwargs), lead)
+    head = ('rgb_map', 'disp_map', 'acc_map', 'depth_map')
+    return [out[k] for k in head] + [{k: v for k, v in out.items() if k not in head}]
 
 
 def batchify_rays_feature_loss(rays_flat, chunk=1024 * 32, keep_keys=None, **kwargs):
@@ -137,34 +134,10 @@ def render_feature_loss(H, W, focal, chunk=1024 * 32, rays=None, c2w=None, ndc=T
     renders the few gradient-carrying rays of a patch normally and the rest under ``torch.no_grad()``; without an
     autograd graph the MLP kernels run in their forward-only form (no activation stash, no ReLU masks).  Returns
     ``[rgb_map, disp_map, acc_map (those kept)] + [dict of every kept entry]``."""
-    if c2w is not None:
-        rays_o, rays_d = get_rays(H, W, focal, c2w)
-    else:
-        rays_o, rays_d = rays
-    sh = rays_d.shape
-    if c2w_staticcam is None and torch.is_tensor(rays_d) and rays_d.is_cuda:
-        packed = ops.pack_rays(H, W, focal, rays_o, rays_d, ndc, near, far, use_viewdirs)
-    else:
-        viewdirs = None
-        if use_viewdirs:
-            viewdirs = rays_d
-            if c2w_staticcam is not None:
-                rays_o, rays_d = get_rays(H, W, focal, c2w_staticcam)
-            viewdirs = torch.reshape(viewdirs / torch.norm(viewdirs, dim=-1, keepdim=True), [-1, 3]).float()
-        if ndc:
-            rays_o, rays_d = ndc_rays(H, W, focal, 1., rays_o, rays_d)
-        rays_o, rays_d = torch.reshape(rays_o, [-1, 3]).float(), torch.reshape(rays_d, [-1, 3]).float()
-        cols = [rays_o, rays_d, near * torch.ones_like(rays_d[..., :1]), far * torch.ones_like(rays_d[..., :1])]
-        if use_viewdirs:
-            cols.append(viewdirs)
-        packed = torch.cat(cols, -1)
-    all_ret = batchify_rays_feature_loss(packed, chunk, keep_keys=keep_keys, **kwargs)
-    for k in all_ret:
-        all_ret[k] = torch.reshape(all_ret[k], list(sh[:-1]) + list(all_ret[k].shape[1:]))
-    k_extract = ['rgb_map', 'disp_map', 'acc_map']
-    if keep_keys:
-        k_extract = [k for k in k_extract if k in keep_keys]
-    return [all_ret[k] for k in k_extract] + [{k: all_ret[k] for k in all_ret}]
+    packed, lead = _ray_batch(H, W, focal, rays, c2w, ndc, near, far, use_viewdirs, c2w_staticcam)
+    out = _unflatten(batchify_rays_feature_loss(packed, chunk, keep_keys=keep_keys, **kwargs), lead)
+    head = [k for k in ('rgb_map', 'disp_map', 'acc_map') if not keep_keys or k in keep_keys]
+    return [out[k] for k in head] + [dict(out)]
 
 
 def render_path(render_poses, hwf, chunk, render_kwargs, gt_imgs=None, savedir=None, render_factor=0, iteration=0,
