@@ -136,5 +136,5 @@ def test_inverse_depth_smoothness_golden(golden_dir):
     im = torch.from_numpy(g["image"]).requires_grad_(True)
     loss = O.inverse_depth_smoothness(d, im)
     loss.backward()
-    assert float(loss) == float(g["loss"])
+    assert float(loss.detach()) == float(g["loss"])
     assert np.array_equal(d.grad.numpy(), g["g_idepth"]) and np.array_equal(im.grad.numpy(), g["g_image"])
