@@ -1,0 +1,102 @@
+"""Minimal training loop in the shape of the reference's train() (run_nerf.py:1328-1420, :1500-1536, :1759-1774,
+:1843-1847) on the B200 path, with a synthetic scene instead of a dataset (none ships with the reference):
+
+    colour target  = 0.5 + 0.5 * unit view direction      (a view-dependent "sky")
+    depth  target  = 0.7 in NDC for the depth rays         (a fronto-parallel wall)
+
+It uses the optional swaps of INTEGRATION.md: DeviceRayLoader for RayDataset + DataLoader, FlatAdam for
+torch.optim.Adam, GraphedTrainStep for render + loss + backward.  Prints loss / PSNR every 50 iterations.
+
+    python examples/train_synthetic.py [--iters 300] [--n-rand 1024] [--drop-in]
+"""
+import argparse
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import dlnerf_b200 as dn  # noqa: E402
+
+H, W, FOCAL = 94, 352, 138.14          # KITTI-360 at factor 4 (configs/fern_dsnerf.txt:22, :50-51)
+
+
+def synthetic_rays(n_views=8, seed=0):
+    """[N, ro+rd+rgb, 3] like the reference's rays_rgb array (run_nerf.py:1126-1140), from jittered forward poses."""
+    rs = np.random.RandomState(seed)
+    i, j = np.meshgrid(np.arange(W, dtype=np.float32), np.arange(H, dtype=np.float32), indexing='xy')
+    dirs = np.stack([(i - W * .5) / FOCAL, -(j - H * .5) / FOCAL, -np.ones_like(i)], -1)
+    out = []
+    for _ in range(n_views):
+        t = np.array([rs.uniform(-.3, .3), rs.uniform(-.05, .05), rs.uniform(-.3, .3)], np.float32)
+        rd = dirs.reshape(-1, 3)
+        ro = np.broadcast_to(t, rd.shape)
+        unit = rd / np.linalg.norm(rd, axis=-1, keepdims=True)
+        out.append(np.stack([ro, rd, 0.5 + 0.5 * unit], 1))
+    return np.concatenate(out, 0).astype(np.float32)
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--iters", type=int, default=300)
+    ap.add_argument("--n-rand", type=int, default=1024)
+    ap.add_argument("--lrate", type=float, default=5e-4)
+    ap.add_argument("--drop-in", action="store_true", help="render() + img2mse + loss.backward() instead of the graphed step")
+    args = ap.parse_args(argv)
+    dev = torch.device("cuda")
+    torch.manual_seed(3407)
+    model = dn.NeRF(D=4, W=256, input_ch=63, input_ch_views=27, use_viewdirs=True).to(dev)
+    model_fine = dn.NeRF(D=8, W=256, input_ch=63, input_ch_views=27, use_viewdirs=True).to(dev)
+    optimizer = dn.FlatAdam([model, model_fine], lr=args.lrate, betas=(0.9, 0.999))
+    n_rgb = args.n_rand // 2
+    n_dep = args.n_rand - n_rgb
+    rays = synthetic_rays()
+    rgb_loader = dn.DeviceRayLoader(rays, batch_size=n_rgb, device=dev)
+    dep_loader = dn.DeviceRayLoader(rays, batch_size=n_dep, device=dev)
+    rgb_it, dep_it = iter(rgb_loader), iter(dep_loader)
+    target_depth = torch.full((n_dep,), 0.7, device=dev)
+    kw = dict(N_samples=64, N_importance=64, perturb=1., raw_noise_std=1., depth_lambda=0.1, depth_importance=1.)
+    step = None if args.drop_in else dn.GraphedTrainStep(H, W, FOCAL, args.n_rand, n_rgb, model, model_fine, **kw)
+    q = dn.FusedQuery(dn.get_embedder(10, 0)[0], dn.get_embedder(4, 0)[0], 65536, 10, 4, 0)
+    losses = []
+    for i in range(args.iters):
+        def nxt(it, loader):
+            try:
+                b = next(it)
+                if b.shape[0] == loader.batch_size:
+                    return b, it
+            except StopIteration:
+                pass
+            it = iter(loader)               # the reference's restart idiom (run_nerf.py:1335-1340)
+            return next(it), it
+        b_rgb, rgb_it = nxt(rgb_it, rgb_loader)
+        b_dep, dep_it = nxt(dep_it, dep_loader)
+        batch = torch.cat([b_rgb, b_dep], 0).transpose(0, 1)         # [3, N_rand, 3]
+        batch_rays, target_s = batch[:2].contiguous(), batch[2, :n_rgb].contiguous()
+        if step is not None:
+            out = step(batch_rays, target_s, target_depth)
+            loss, psnr = out["loss"], out["psnr"]
+        else:
+            rgb, disp, acc, depth, extras = dn.render(H, W, FOCAL, chunk=1 << 20, rays=batch_rays, retraw=True,
+                                                      network_query_fn=q, perturb=1., N_importance=64,
+                                                      network_fine=model_fine, N_samples=64, network_fn=model,
+                                                      use_viewdirs=True, white_bkgd=False, raw_noise_std=1., ndc=True,
+                                                      near=0., far=1.)
+            optimizer.zero_grad()
+            img_loss = dn.img2mse(rgb[:n_rgb], target_s)
+            loss = img_loss + 0.1 * dn.img2mse(depth[n_rgb:], target_depth) + dn.img2mse(extras['rgb0'][:n_rgb], target_s)
+            loss.backward()
+            psnr = dn.mse2psnr(img_loss)
+        optimizer.step()
+        new_lrate = args.lrate * (0.1 ** (i / 250000.))                 # run_nerf.py:1843-1847
+        for g in optimizer.param_groups:
+            g['lr'] = new_lrate
+        if i % 50 == 0 or i == args.iters - 1:
+            losses.append((float(loss.detach()), float(psnr.detach())))
+            print("iter %4d  loss %.5f  psnr %.2f" % (i, losses[-1][0], losses[-1][1]), flush=True)
+    return losses
+
+
+if __name__ == "__main__":
+    main()
