@@ -1,0 +1,49 @@
+"""bench.py prints exactly ONE JSON line on stdout with the keys the driver reads.  The reference arm runs on the
+CPU (here); the B200 arm is checked on the GPU box."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+             "vs_baseline", "dtype", "data", "config", "e2e", "cpu_baseline"}
+
+
+def _run(args, timeout):
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py")] + args, capture_output=True, text=True,
+                         timeout=timeout, cwd=ROOT)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [l for l in res.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, "stdout must carry exactly one line, got %d" % len(lines)
+    return json.loads(lines[0])
+
+
+def test_reference_arm_prints_one_contract_line():
+    d = _run(["--impl", "reference", "--steps", "1", "--warmup", "0"], timeout=600)
+    assert BASE_KEYS <= set(d) and d["impl"] == "reference"
+    assert d["metric"] == "training rays/sec (fwd+bwd)" and d["unit"] == "rays/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["vs_baseline"] is None and "workload" in d["config"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+@pytest.mark.gpu
+def test_b200_arm_prints_one_contract_line():
+    d = _run(["--steps", "3", "--warmup", "3", "--no-cpu-baseline"], timeout=900)
+    assert (BASE_KEYS | {"clocks", "gpu_launches", "roofline", "kernels"}) <= set(d)
+    assert d["metric"] == "training rays/sec (fwd+bwd)" and d["unit"] == "rays/s" and d["n_gpus"] == 1
+    assert d["steps"] == 3 and d["warmup"] >= 3 and d["dtype"] == "bf16" and d["data"] == "synthetic"
+    assert d["value"] > 1e5 and abs(d["value"] - 4096 / (d["ms_per_step"] * 1e-3)) <= 1e-6 * d["value"]
+    assert d["gpu_launches"] > 0 and "workload" in d["config"]
+    e = d["e2e"]
+    assert e["value"] > 0 and e["unit"] == "rays/s" and e["h2d_bytes_per_step"] == (2 * 4096 * 3 + 2048 * 3 + 2048) * 4
+    assert e["d2h_bytes_per_step"] == 4 and e["value"] <= 1.05 * d["value"]
+    r = d["roofline"]
+    assert r["bound"] in ("tensor", "hbm") and r["unit"] in ("TFLOP/s", "GB/s")
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and 0.05 < r["frac"] < 1.0 and "traffic" in r
+    c = d["clocks"]
+    assert c["sm_mhz"] > 0 and c["sm_max_mhz"] >= c["sm_mhz"] and isinstance(c["reasons"], list)
