@@ -182,7 +182,7 @@ def workload_config(args, world):
             "netwidth": 256, "use_viewdirs": True, "perturb": 1.0, "raw_noise_std": 1.0, "ndc": True,
             "depth_lambda": DEPTH_LAMBDA, "optimizer_step": "excluded (BASELINE.md §3)",
             "parallelism": "ray-sharded dp%d, NCCL all-reduce of MLP grads" % world,
-            "l2": "per-step working set (activation stashes, ~1.3 MB/ray) is far larger than the 126 MB L2; no flush"}
+            "l2": "per-step working set (activation stashes, ~1.5 MB/ray = 6 GB per 4096-ray step) is far larger than the 126 MB L2; no flush"}
 
 
 def cpu_baseline(seconds_budget=25.0):
