@@ -389,3 +389,82 @@ def test_patch_render_grad_and_no_grad_split():
     worst = max(rel_l2(a, p.grad) for a, p in zip(got, nets))
     print("  patch gradients vs render() on the gradient rays: worst per-tensor rel-L2 %.3e" % worst)
     assert worst <= 2e-3
+
+
+def test_kitti360_patch_iteration_against_oracle():
+    """BASELINE config 3 in miniature (run_nerf.py:1552-1647): a patch of a KITTI-360-shaped view (fractional pixel
+    rays, no NDC, near/far in metres) is rendered with a block of gradient-carrying rays (render_feature_loss) and
+    the rest under no_grad, assembled into [2,3,h,w] colour / [2,1,h,w] depth images (fine + coarse), and the
+    inverse-depth smoothness loss (loss.py:55-133) is back-propagated into both networks.  Oracle: the same
+    computation with oracle.render_rays / oracle.inverse_depth_smoothness and the bf16-emulating MLP twin."""
+    d = dn()
+    hh, ww, gh, gw = 12, 20, 6, 8                       # patch and its gradient block (94x352 / 32x64 in the config)
+    Hk, Wk, fk = 94, 352, 138.14
+    net_c, pc, spec_c = make_net(4, seed=81, sigma_bias=1.0)
+    net_f, pf, spec_f = make_net(8, seed=82, sigma_bias=1.0)
+    gen = torch.Generator().manual_seed(9)
+    # rays through a fractional pixel grid of the patch (load_llff.py:486 style coordinates / factor)
+    ii, jj = torch.meshgrid(torch.arange(hh, dtype=torch.float32), torch.arange(ww, dtype=torch.float32), indexing="ij")
+    px, py = 100.25 + jj * 1.5, 30.5 + ii * 1.5
+    dirs = torch.stack([(px - Wk * .5) / fk, -(py - Hk * .5) / fk, -torch.ones_like(px)], -1).reshape(-1, 3)
+    ro = torch.tensor([0.1, -0.05, 0.2]).expand_as(dirs).contiguous()
+    mask = torch.zeros(hh, ww, dtype=torch.bool)
+    mask[3:3 + gh, 5:5 + gw] = True
+    gidx, nidx = mask.reshape(-1).nonzero()[:, 0], (~mask).reshape(-1).nonzero()[:, 0]
+    near, far = 0.5, 6.0
+    q = d.FusedQuery(d.get_embedder(10, 0)[0], d.get_embedder(4, 0)[0], 1 << 16, 10, 4, 0)
+    kw = dict(network_query_fn=q, perturb=0., N_importance=64, network_fine=net_f, N_samples=64, network_fn=net_c,
+              use_viewdirs=True, white_bkgd=False, raw_noise_std=0., ndc=False, near=near, far=far)
+    keep = ['rgb_map', 'rgb0', 'depth_map', 'depth_map0']
+    rod, dd = ro.to(DEV), dirs.to(DEV)
+    g_out = d.render_feature_loss(Hk, Wk, fk, chunk=1 << 20, rays=(rod[gidx], dd[gidx]), keep_keys=keep, **kw)[-1]
+    with torch.no_grad():
+        n_out = d.render_feature_loss(Hk, Wk, fk, chunk=64, rays=(rod[nidx], dd[nidx]), keep_keys=keep, **kw)[-1]
+
+    def assemble(go, no, dev):
+        rgb = torch.empty(2, hh * ww, 3, device=dev, dtype=go['rgb_map'].dtype)
+        dep = torch.empty(2, hh * ww, device=dev, dtype=go['rgb_map'].dtype)
+        gi, ni = gidx.to(dev), nidx.to(dev)
+        for lvl, (kc, kd) in enumerate((('rgb_map', 'depth_map'), ('rgb0', 'depth_map0'))):
+            rgb[lvl, ni], dep[lvl, ni] = no[kc], no[kd]
+            rgb[lvl, gi], dep[lvl, gi] = go[kc], go[kd]
+        acc_rgb = rgb.reshape(2, hh, ww, 3).permute(0, 3, 1, 2).clamp(0, 1).contiguous()
+        acc_depth = dep.reshape(2, 1, hh, ww).contiguous()
+        return acc_depth, acc_rgb
+
+    acc_depth, acc_rgb = assemble(g_out, n_out, DEV)
+    loss = d.InverseDepthSmoothnessLoss()(acc_depth, acc_rgb)
+    nets = list(net_c.named_parameters()) + list(net_f.named_parameters())
+    for _, p in nets:
+        p.grad = None
+    loss.backward()
+
+    # oracle: same patch, same split, bf16-emulating MLP (the function the kernels evaluate)
+    pcg = {k: v.clone().requires_grad_(True) for k, v in pc.items()}
+    pfg = {k: v.clone().requires_grad_(True) for k, v in pf.items()}
+    rb = O.pack_rays(Hk, Wk, fk, ro, dirs, ndc=False, near=near, far=far)
+    ro_g = O.render_rays(rb[gidx], pcg, spec_c, pfg, spec_f, 64, 64, O.RenderRNG(), raw_noise_std=0.0,
+                         mlp_fn=mlp_forward_emulated)
+    with torch.no_grad():
+        ro_n = O.render_rays(rb[nidx], pcg, spec_c, pfg, spec_f, 64, 64, O.RenderRNG(), raw_noise_std=0.0,
+                             mlp_fn=mlp_forward_emulated)
+    name = dict(rgb_map='rgb_map', rgb0='rgb0', depth_map='depth_map', depth_map0='depth_map0')
+    od, orgb = assemble({k: ro_g[v] for k, v in name.items()}, {k: ro_n[v] for k, v in name.items()}, "cpu")
+    ref = O.inverse_depth_smoothness(od, orgb)
+    ref.backward()
+    report("patch depth (fine, coarse)", acc_depth, od, atol=2e-2)
+    report("patch colour", acc_rgb, orgb, atol=2e-2)
+    report("inverse-depth smoothness loss", loss, ref, rtol=2e-2)
+    got = [(("c." if i < len(list(net_c.parameters())) else "f.") + n, p.grad) for i, (n, p) in enumerate(nets)]
+    refg = {("c." + k): v.grad for k, v in pcg.items()}
+    refg.update({("f." + k): v.grad for k, v in pfg.items()})
+    num = den = 0.0
+    for n, g in got:
+        r = refg[n]
+        if r is None:
+            continue
+        num += float((g.detach().double().cpu() - r.double()).pow(2).sum())
+        den += float(r.double().pow(2).sum())
+    agg = (num / den) ** 0.5
+    print("  aggregate rel-L2 of the parameter gradients vs the bf16-emulating oracle: %.3e" % agg)
+    assert agg <= 5e-2
