@@ -13,12 +13,13 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
 CSRC = os.path.join(_HERE, "csrc")
 SO_PATH = os.path.join(_HERE, "libdlnerf_b200.so")
-SOURCES = ["render_kernels.cu", "mlp_kernels.cu", "optim_kernels.cu"]
+SOURCES = ["render_kernels.cu", "mlp_kernels.cu", "optim_kernels.cu", "semantic_kernels.cu"]
 
 MAX_STEPS = 12
 MAX_KSLABS = 6
 SLAB_BYTES = 16384
 TILE_ROWS = 128
+SEM_MAX_CLASSES = 32
 
 EPI_RELU, EPI_RELU_SIGMA, EPI_LINEAR, EPI_RELU_RGB, EPI_RELU_OUT = 0, 1, 2, 3, 4
 EPI_BWD_COPY, EPI_BWD_MASK, EPI_BWD_MASK_SIGMA = 8, 9, 10
@@ -43,7 +44,8 @@ class ChainArgs(C.Structure):
     _fields_ = [("P", C.c_longlong), ("rays", C.c_void_p), ("ray_stride", C.c_int32), ("vd_col", C.c_int32),
                 ("z", C.c_void_p), ("S", C.c_int32), ("x", C.c_void_p), ("x_ld", C.c_int32),
                 ("wblob", C.c_void_p), ("fblob", C.c_void_p), ("out", C.c_void_p), ("d_out", C.c_void_p),
-                ("stash", C.c_void_p), ("masks", C.c_void_p), ("trace", C.c_void_p)]
+                ("stash", C.c_void_p), ("masks", C.c_void_p), ("trace", C.c_void_p),
+                ("sem_g", C.c_void_p), ("sem_g_div", C.c_int32), ("pad_", C.c_int32)]
 
 
 class WgradItem(C.Structure):
@@ -58,6 +60,12 @@ class PackJob(C.Structure):
     _fields_ = [("src_off", C.c_int64), ("ld", C.c_int32), ("row0", C.c_int32), ("col0", C.c_int32),
                 ("n_valid", C.c_int32), ("k_valid", C.c_int32), ("transposed", C.c_int32),
                 ("n_rows", C.c_int32), ("dst_off", C.c_uint32)]
+
+
+class SemOffsets(C.Structure):
+    _fields_ = [("w_f", C.c_int64), ("b_f", C.c_int64), ("w_s1", C.c_int64), ("b_s1", C.c_int64),
+                ("w_s2", C.c_int64), ("b_s2", C.c_int64), ("A", C.c_int64), ("a", C.c_int64),
+                ("Sw", C.c_int64), ("sc", C.c_int64), ("K", C.c_int32), ("pad_", C.c_int32)]
 
 
 _P, _I, _F, _LL, _D = C.c_void_p, C.c_int, C.c_float, C.c_longlong, C.c_double
@@ -80,6 +88,13 @@ SIGNATURES = {
     "dln_inv_depth_smooth_bwd": [_P, _P, _I, _I, _I, _P, _P, _P, _P],
     "dln_mlp_fold": [_P, _LL, _I, _LL, _LL, _LL, _LL, _LL, _P],
     "dln_mlp_unfold_grads": [_P, _P, _LL, _I, _LL, _LL, _LL, _LL, _LL, _P],
+    "dln_sem_fold": [_P, C.POINTER(SemOffsets), _P],
+    "dln_sem_unfold_grads": [_P, _P, C.POINTER(SemOffsets), _P],
+    "dln_sem_head_fwd": [_P, _I, _I, _LL, _I, _P, C.POINTER(SemOffsets), _P, _P, _I, _P],
+    "dln_sem_head_bwd": [_P, _I, _P, _LL, _I, _P, _P, C.POINTER(SemOffsets), _P, _P],
+    "dln_sample_sum": [_P, _I, _I, _I, _I, _P, _P],
+    "dln_sample_sum_bwd": [_P, _I, _I, _I, _I, _P, _P],
+    "dln_sem_ce_loss": [_P, _I, _P, _I, _I, _I, _F, _P, _P, _P],
     "dln_adam_step": [_P, _P, _P, _P, _LL, _D, _D, _D, _D, _I, _F, _P],
     "dln_abi_sizes": [C.POINTER(C.c_int)],
 }

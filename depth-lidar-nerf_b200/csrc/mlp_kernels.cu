@@ -193,7 +193,7 @@ template <int EPI>
 __device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], const float* __restrict__ bias,
                                           const float* __restrict__ hw, int n_out, int nheads, float dsig,
                                           uint32_t mw_in, uint32_t& mw_out, float (&hacc)[5], uint32_t (&pk)[16],
-                                          int cb) {
+                                          int cb, const float* __restrict__ semrow) {
   constexpr bool kFwd = EPI <= DLN_EPI_RELU_OUT;
   constexpr bool kRelu = EPI == DLN_EPI_RELU || EPI == DLN_EPI_RELU_SIGMA || EPI == DLN_EPI_RELU_RGB || EPI == DLN_EPI_RELU_OUT;
   float f[32];
@@ -212,6 +212,14 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], const float* 
     for (int q = 0; q < 8; ++q) {
       const float4 h = __ldg(reinterpret_cast<const float4*>(hw + cb + 4 * q));
       f[4 * q] += dsig * h.x, f[4 * q + 1] += dsig * h.y, f[4 * q + 2] += dsig * h.z, f[4 * q + 3] += dsig * h.w;
+    }
+    if (semrow != nullptr) {      // semantic head: dH += dsem Sw, one fp32 row per ray (dln_sem_head_bwd)
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 h = __ldg(reinterpret_cast<const float4*>(semrow + cb + 4 * q));
+        add2(f[4 * q], f[4 * q + 1], h.x, h.y);
+        add2(f[4 * q + 2], f[4 * q + 3], h.z, h.w);
+      }
     }
   }
   if (kRelu) {
@@ -270,7 +278,7 @@ struct ProdTrack {
 // ---------------------------------------------------------------------------------------------
 // the chain kernel
 // ---------------------------------------------------------------------------------------------
-template <bool kBwd>
+template <bool kBwd, bool kSem = false>      // kSem: dgrad with the semantic head's per-ray term (args.sem_g)
 __global__ void __launch_bounds__(kThreads, 1)
     chain_kernel(const __grid_constant__ DlnChainProgram prog, const __grid_constant__ DlnChainArgs args,
                  const long long n_tiles) {
@@ -562,6 +570,8 @@ __global__ void __launch_bounds__(kThreads, 1)
       const long long p = tile * DLN_TILE_ROWS + r;
       const bool valid = p < args.P;
       float dsig = 0.f;
+      const float* const semrow =
+          (kBwd && kSem) ? args.sem_g + (size_t)((valid ? p : args.P - 1) / args.sem_g_div) * 256 : nullptr;
       uint8_t* const gtile = keep ? reinterpret_cast<uint8_t*>(args.stash) + (size_t)tile * prog.stash_slots * kSlab : nullptr;
       auto gslot = [&](int slot) -> uint8_t* { return (kDirectStash && keep) ? gtile + (size_t)slot * kSlab : nullptr; };
       // ------------------------------------------------------------------ prologue
@@ -663,7 +673,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           uint32_t pk[16];
           auto run = [&](auto tag, const uint32_t(&v)[32], uint32_t mi, uint32_t& mo, int cb) {
             constexpr int E = decltype(tag)::value;
-            epi_chunk<E>(v, bias, hw, st.n_out, nheads, dsig, mi, mo, hacc, pk, cb);
+            epi_chunk<E>(v, bias, hw, st.n_out, nheads, dsig, mi, mo, hacc, pk, cb, semrow);
           };
           auto dispatch = [&](const uint32_t(&v)[32], uint32_t mi, uint32_t& mo, int cb) {
             if (!kBwd) {
@@ -957,6 +967,7 @@ int dln_mlp_chain(const DlnChainProgram* prog, const DlnChainArgs* args, int num
   DLN_CHECK_ARG(prog->reload_step < prog->n_steps);
   if (prog->backward) {
     DLN_CHECK_ARG(args->d_out && args->masks);
+    DLN_CHECK_ARG(!args->sem_g || (args->sem_g_div >= 1 && (reinterpret_cast<uintptr_t>(args->sem_g) & 15) == 0));
   } else {
     DLN_CHECK_ARG(args->out);
     DLN_CHECK_ARG(args->x || (args->rays && args->z && args->S >= 1 && args->ray_stride >= 6));
@@ -970,10 +981,14 @@ int dln_mlp_chain(const DlnChainProgram* prog, const DlnChainArgs* args, int num
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemBytes);
     if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(chain_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemBytes);
+    if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
   const unsigned grid = (unsigned)(n_tiles < num_sms ? n_tiles : num_sms);
-  if (prog->backward)
+  if (prog->backward && args->sem_g)
+    chain_kernel<true, true><<<grid, kThreads, kChainSmemBytes, (cudaStream_t)stream>>>(*prog, *args, n_tiles);
+  else if (prog->backward)
     chain_kernel<true><<<grid, kThreads, kChainSmemBytes, (cudaStream_t)stream>>>(*prog, *args, n_tiles);
   else
     chain_kernel<false><<<grid, kThreads, kChainSmemBytes, (cudaStream_t)stream>>>(*prog, *args, n_tiles);
@@ -1005,7 +1020,7 @@ int dln_mlp_pack_weights(const float* params_flat, const DlnPackJob* jobs_dev, i
 int dln_abi_sizes(int* out) {
   DLN_CHECK_ARG(out);
   out[0] = (int)sizeof(DlnChainStep), out[1] = (int)sizeof(DlnChainProgram), out[2] = (int)sizeof(DlnChainArgs);
-  out[3] = (int)sizeof(DlnWgradItem), out[4] = (int)sizeof(DlnPackJob);
+  out[3] = (int)sizeof(DlnWgradItem), out[4] = (int)sizeof(DlnPackJob), out[5] = (int)sizeof(DlnSemOffsets);
   return DLN_OK;
 }
 

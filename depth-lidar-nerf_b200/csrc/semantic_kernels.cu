@@ -1,0 +1,402 @@
+// Semantic head of the NeRF module (run_nerf_helpers.py:107-111, :126-127) and the per-ray semantic logits of
+// raw2outputs (:586-589), plus the cross-entropy of the training loop (run_nerf.py:1541-1548).
+//
+// The head is two Linear layers WITHOUT an activation behind feature_linear, which has none either, so per point
+//     semantic = W_s2 (W_s1 (W_f h + b_f) + b_s1) + b_s2 = Sw h + sc,   Sw = W_s2 W_s1 W_f  [K x 256],
+// with h the last hidden activation of the trunk -- the very slabs the MLP chain already keeps for wgrad.  And the
+// reference sums the logits UNWEIGHTED over the samples of a ray (:589), so per ray
+//     sem_preds = Sw (sum_s h_s) + S sc.
+// The head therefore never enters the tensor-core chain: one HBM-bound pass over the kept activations (512 B per
+// point) forms Hsum = sum_s h_s per ray, and everything else is [rays x 256] x [256 x K] work:
+//     forward   sem_head_fwd : Hsum, sem_preds                       (S = 1 gives per-point logits for `raw`)
+//     backward  sem_head_bwd : G = dsem Sw (added to dH of the last trunk layer by the dgrad chain's epilogue),
+//                              dSw += dsem^T Hsum, dsc += S sum dsem
+//     fold / unfold          : Sw, sc from the six parameter tensors after a weight update; dSw, dsc back into
+//                              their gradients (and into feature_linear's) after a backward pass.
+// K <= 32 classes (KITTI-360: 19).
+#include "common.cuh"
+#include "../../include/dlnerf_b200.h"
+#include <math.h>
+
+namespace {
+
+constexpr int kW = 256;       // trunk width
+constexpr int kHid = 128;     // hidden width of the semantic head (W/2)
+constexpr int kMaxK = DLN_SEM_MAX_CLASSES;
+
+// ------------------------------------------------------------------------------------------------
+// fold: A = W_s1 W_f [128 x 256], a = W_s1 b_f + b_s1 [128];  Sw = W_s2 A [K x 256], sc = W_s2 a + b_s2 [K]
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sem_fold_a_kernel(float* __restrict__ flat, DlnSemOffsets o) {
+  __shared__ float wrow[kW];
+  __shared__ float red[8];
+  const int i = blockIdx.x, j = threadIdx.x;
+  wrow[j] = flat[o.w_s1 + (long long)i * kW + j];
+  __syncthreads();
+  const float* wf = flat + o.w_f;
+  float acc = 0.f;
+#pragma unroll 8
+  for (int k = 0; k < kW; ++k) acc = fmaf(wrow[k], wf[k * kW + j], acc);
+  flat[o.A + (long long)i * kW + j] = acc;
+  const float b = dln::warp_sum(wrow[j] * flat[o.b_f + j]);
+  if ((j & 31) == 0) red[j >> 5] = b;
+  __syncthreads();
+  if (j == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    flat[o.a + i] = t + flat[o.b_s1 + i];
+  }
+}
+
+__global__ void __launch_bounds__(256) sem_fold_s_kernel(float* __restrict__ flat, DlnSemOffsets o) {
+  __shared__ float wrow[kHid];
+  __shared__ float red[8];
+  const int k = blockIdx.x, j = threadIdx.x;
+  if (j < kHid) wrow[j] = flat[o.w_s2 + (long long)k * kHid + j];
+  __syncthreads();
+  const float* A = flat + o.A;
+  float acc = 0.f;
+#pragma unroll 8
+  for (int i = 0; i < kHid; ++i) acc = fmaf(wrow[i], A[i * kW + j], acc);
+  flat[o.Sw + (long long)k * kW + j] = acc;
+  const float b = dln::warp_sum(j < kHid ? wrow[j] * flat[o.a + j] : 0.f);
+  if ((j & 31) == 0) red[j >> 5] = b;
+  __syncthreads();
+  if (j == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    flat[o.sc + k] = t + flat[o.b_s2 + k];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// unfold (after one backward call; g[o.Sw], g[o.sc] hold dSw, dsc of that call):
+//   launch 1: dW_s2[k][i] += sum_j dSw[k][j] A[i][j] + dsc[k] a[i];  db_s2 += dsc
+//             dA[i][j] = sum_k W_s2[k][i] dSw[k][j]  -> g[o.A];      da[i] = sum_k W_s2[k][i] dsc[k] -> g[o.a]
+//   launch 2: dW_s1[i][m] += sum_j dA[i][j] W_f[m][j] + da[i] b_f[m];  db_s1 += da
+//             dW_f[m][j] += sum_i W_s1[i][m] dA[i][j];                db_f[m] += sum_i W_s1[i][m] da[i]
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sem_unfold1_kernel(const float* __restrict__ flat, float* __restrict__ g,
+                                                          DlnSemOffsets o) {
+  __shared__ float sh[kW];
+  const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int K = o.K;
+  if (b < K) {                    // row k of dW_s2: a warp per i, lanes over j
+    const int k = b;
+    sh[t] = g[o.Sw + (long long)k * kW + t];
+    __syncthreads();
+    const float dk = g[o.sc + k];
+    for (int i = warp; i < kHid; i += 8) {
+      const float* Ai = flat + o.A + (long long)i * kW;
+      float acc = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc = fmaf(sh[q * 32 + lane], __ldg(Ai + q * 32 + lane), acc);
+      acc = dln::warp_sum(acc);
+      if (lane == 0) g[o.w_s2 + (long long)k * kHid + i] += acc + dk * flat[o.a + i];
+    }
+    if (t == 0) g[o.b_s2 + k] += dk;
+  } else if (b < K + kHid) {      // row i of dA
+    const int i = b - K;
+    if (t < K) sh[t] = flat[o.w_s2 + (long long)t * kHid + i];
+    __syncthreads();
+    float acc = 0.f, da = 0.f;
+    for (int k = 0; k < K; ++k) {
+      acc = fmaf(sh[k], g[o.Sw + (long long)k * kW + t], acc);
+      da = fmaf(sh[k], g[o.sc + k], da);
+    }
+    g[o.A + (long long)i * kW + t] = acc;
+    if (t == 0) g[o.a + i] = da;
+  }
+}
+
+__global__ void __launch_bounds__(256) sem_unfold2_kernel(const float* __restrict__ flat, float* __restrict__ g,
+                                                          DlnSemOffsets o) {
+  __shared__ float sh[kW];
+  __shared__ float out[kW];
+  const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  if (b < kHid) {                 // row i of dW_s1: (W_f dA_i)[m] + da_i b_f[m]; a warp per m, lanes over j
+    const int i = b;
+    sh[t] = g[o.A + (long long)i * kW + t];
+    __syncthreads();
+    const float dai = g[o.a + i];
+#pragma unroll 4
+    for (int m = warp; m < kW; m += 8) {
+      const float* wf = flat + o.w_f + (long long)m * kW;
+      float acc = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc = fmaf(sh[q * 32 + lane], __ldg(wf + q * 32 + lane), acc);
+      acc = dln::warp_sum(acc);
+      if (lane == 0) out[m] = acc;
+    }
+    __syncthreads();
+    g[o.w_s1 + (long long)i * kW + t] += out[t] + dai * __ldg(flat + o.b_f + t);
+    if (t == 0) g[o.b_s1 + i] += dai;
+  } else if (b < kHid + kW) {     // row m of dW_f: sum_i W_s1[i][m] dA[i][:]
+    const int m = b - kHid;
+    if (t < kHid) sh[t] = flat[o.w_s1 + (long long)t * kW + m];
+    __syncthreads();
+    float acc = 0.f;
+#pragma unroll 16
+    for (int i = 0; i < kHid; ++i) acc = fmaf(sh[i], g[o.A + (long long)i * kW + t], acc);
+    g[o.w_f + (long long)m * kW + t] += acc;
+  } else {                        // db_f
+    if (t < kHid) sh[t] = g[o.a + t];
+    __syncthreads();
+    float acc = 0.f;
+#pragma unroll 16
+    for (int i = 0; i < kHid; ++i) acc = fmaf(__ldg(flat + o.w_s1 + (long long)i * kW + t), sh[i], acc);
+    g[o.b_f + t] += acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward: a warp per group of S consecutive points (a ray; S = 1: a point).  Lane l owns features [8l, 8l+8):
+// one 16-byte chunk of the point's 128-byte row in slab l/8 of the kept activation (SWIZZLE_128B image, see
+// DESIGN.md section 2), i.e. a warp reads the four rows of a point as 4 x 128 contiguous bytes.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void acc_bf16x8(float (&h)[8], const uint4 v) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    h[2 * i] += __uint_as_float(w[i] << 16);
+    h[2 * i + 1] += __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    sem_head_fwd_kernel(const uint8_t* __restrict__ stash, int fwd_slots, int h_slot, long long P, int S,
+                        const float* __restrict__ Sw, const float* __restrict__ sc, int K,
+                        float* __restrict__ hsum, float* __restrict__ out, int out_ld, long long n_groups) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long n_warps = (long long)gridDim.x * (blockDim.x >> 5);
+  const size_t tile_bytes = (size_t)fwd_slots * DLN_SLAB_BYTES;
+  const uint8_t* base = stash + (size_t)(h_slot + (lane >> 3)) * DLN_SLAB_BYTES;
+  const uint32_t chunk = lane & 7;
+  for (long long g = warp0; g < n_groups; g += n_warps) {
+    float h[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const long long p0 = g * S;
+    long long p1 = p0 + S;
+    if (p1 > P) p1 = P;
+    auto addr = [&](long long p) {
+      const uint32_t r = (uint32_t)(p & (DLN_TILE_ROWS - 1));
+      return reinterpret_cast<const uint4*>(base + (size_t)(p >> 7) * tile_bytes + (r >> 3) * 1024u + (r & 7u) * 128u +
+                                            (((chunk ^ r) & 7u) << 4));
+    };
+    long long p = p0;
+    for (; p + 4 <= p1; p += 4) {           // four independent 16-byte loads in flight per lane
+      const uint4 v0 = __ldg(addr(p)), v1 = __ldg(addr(p + 1)), v2 = __ldg(addr(p + 2)), v3 = __ldg(addr(p + 3));
+      acc_bf16x8(h, v0), acc_bf16x8(h, v1), acc_bf16x8(h, v2), acc_bf16x8(h, v3);
+    }
+    for (; p < p1; ++p) acc_bf16x8(h, __ldg(addr(p)));
+    if (hsum != nullptr) {
+      float4* hs = reinterpret_cast<float4*>(hsum + (size_t)g * kW + 8 * lane);
+      hs[0] = make_float4(h[0], h[1], h[2], h[3]);
+      hs[1] = make_float4(h[4], h[5], h[6], h[7]);
+    }
+    if (out != nullptr) {
+      const float cnt = (float)(p1 - p0);
+      float mine = 0.f;                      // lane k keeps logit k
+      for (int k = 0; k < K; ++k) {
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(Sw + (size_t)k * kW + 8 * lane));
+        const float4 w1 = __ldg(reinterpret_cast<const float4*>(Sw + (size_t)k * kW + 8 * lane + 4));
+        float a = h[0] * w0.x;
+        a = fmaf(h[1], w0.y, a), a = fmaf(h[2], w0.z, a), a = fmaf(h[3], w0.w, a);
+        a = fmaf(h[4], w1.x, a), a = fmaf(h[5], w1.y, a), a = fmaf(h[6], w1.z, a), a = fmaf(h[7], w1.w, a);
+        a = dln::warp_sum(a);
+        if (lane == k) mine = a + cnt * __ldg(sc + k);
+      }
+      if (lane < K) out[(size_t)g * out_ld + lane] = mine;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward: thread f of a block owns feature f; the block walks a contiguous range of groups.
+//   G[g][f]  = sum_k dsem[g][k] Sw[k][f]          (what the dgrad chain adds to dH of the last trunk layer)
+//   dSw[k][f] += sum_g dsem[g][k] Hsum[g][f],   dsc[k] += sum_g cnt_g dsem[g][k]
+// ------------------------------------------------------------------------------------------------
+constexpr int kBwdGroupsPerStage = 32;
+
+__global__ void __launch_bounds__(256)
+    sem_head_bwd_kernel(const float* __restrict__ dsem, int dsem_ld, const float* __restrict__ hsum,
+                        const float* __restrict__ Sw, int K, long long n_groups, long long P, int S,
+                        float* __restrict__ G, float* __restrict__ dSw, float* __restrict__ dsc) {
+  __shared__ float ds[kBwdGroupsPerStage][kMaxK];
+  const int f = threadIdx.x;
+  float sw[kMaxK], acc[kMaxK];
+#pragma unroll
+  for (int k = 0; k < kMaxK; ++k) {
+    sw[k] = k < K ? __ldg(Sw + (size_t)k * kW + f) : 0.f;
+    acc[k] = 0.f;
+  }
+  float bsum = 0.f;                     // thread k < K: sum_g cnt_g dsem[g][k]
+  const long long per = (n_groups + gridDim.x - 1) / gridDim.x;
+  const long long g0 = (long long)blockIdx.x * per;
+  const long long g1 = g0 + per < n_groups ? g0 + per : n_groups;
+  for (long long gb = g0; gb < g1; gb += kBwdGroupsPerStage) {
+    const int n = (int)(g1 - gb < kBwdGroupsPerStage ? g1 - gb : kBwdGroupsPerStage);
+    __syncthreads();
+    for (int idx = f; idx < n * kMaxK; idx += 256) {
+      const int gi = idx / kMaxK, k = idx % kMaxK;
+      ds[gi][k] = k < K ? __ldg(dsem + (size_t)(gb + gi) * dsem_ld + k) : 0.f;
+    }
+    __syncthreads();
+    for (int gi = 0; gi < n; ++gi) {
+      const long long g = gb + gi;
+      const float h = __ldg(hsum + (size_t)g * kW + f);
+      float gv = 0.f;
+#pragma unroll
+      for (int k = 0; k < kMaxK; ++k) {
+        const float d = ds[gi][k];
+        gv = fmaf(d, sw[k], gv);
+        acc[k] = fmaf(d, h, acc[k]);
+      }
+      G[(size_t)g * kW + f] = gv;
+      if (f < K) {
+        long long cnt = P - g * S;
+        cnt = cnt < S ? cnt : S;
+        bsum = fmaf((float)cnt, ds[gi][f], bsum);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < kMaxK; ++k)
+    if (k < K && acc[k] != 0.f) atomicAdd(dSw + (size_t)k * kW + f, acc[k]);
+  if (f < K && bsum != 0.f) atomicAdd(dsc + f, bsum);
+}
+
+// ------------------------------------------------------------------------------------------------
+// cross-entropy of the per-ray logits against class indices (F.cross_entropy, mean reduction, run_nerf.py:1542):
+// loss_sum += sum_{n < n_rgb} (logsumexp(x_n) - x_n[t_n]);  dsem[n] = coef (softmax(x_n) - onehot(t_n)), 0 for the
+// rays behind n_rgb (the depth rays carry no semantic target, :1458-1460).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    sem_ce_kernel(const float* __restrict__ logits, int ld, const long long* __restrict__ target, int n_rgb, int N,
+                  int K, float coef, float* __restrict__ dsem, float* __restrict__ loss_sum) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  float loss = 0.f;
+  if (n < N) {
+    float* d = dsem + (size_t)n * K;
+    if (n < n_rgb) {
+      const float* x = logits + (size_t)n * ld;
+      const int t = (int)target[n];
+      float m = -INFINITY;
+      for (int k = 0; k < K; ++k) m = fmaxf(m, x[k]);
+      float s = 0.f;
+      for (int k = 0; k < K; ++k) s += expf(x[k] - m);
+      const float lse = m + logf(s);
+      const bool ok = t >= 0 && t < K;       // anything else contributes nothing (cross_entropy would have raised)
+      loss = ok ? lse - x[t] : 0.f;
+      const float inv = 1.f / s;
+      for (int k = 0; k < K; ++k) d[k] = ok ? coef * (expf(x[k] - m) * inv - (k == t ? 1.f : 0.f)) : 0.f;
+    } else {
+      for (int k = 0; k < K; ++k) d[k] = 0.f;
+    }
+  }
+  loss = dln::warp_sum(loss);
+  if ((threadIdx.x & 31) == 0 && loss != 0.f) atomicAdd(loss_sum, loss);
+}
+
+// ------------------------------------------------------------------------------------------------
+// generic route: torch.sum(raw[..., c0:], -2) of raw2outputs (:589) and its broadcast backward
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    sample_sum_kernel(const float* __restrict__ raw, int C, int c0, int N, int S, float* __restrict__ out) {
+  const int Kc = C - c0;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)N * Kc) return;
+  const int n = (int)(idx / Kc), k = (int)(idx % Kc);
+  const float* p = raw + (size_t)n * S * C + c0 + k;
+  float a = 0.f;
+  for (int s = 0; s < S; ++s) a += p[(size_t)s * C];
+  out[idx] = a;
+}
+
+__global__ void __launch_bounds__(256)
+    sample_sum_bwd_kernel(const float* __restrict__ g, int C, int c0, int N, int S, float* __restrict__ d_raw) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)N * S * C) return;
+  const int c = (int)(idx % C);
+  const long long n = idx / ((long long)S * C);
+  d_raw[idx] = c >= c0 ? g[n * (C - c0) + c - c0] : 0.f;
+}
+
+bool offsets_ok(const DlnSemOffsets* o) {
+  return o && o->K >= 1 && o->K <= kMaxK && o->w_f >= 0 && o->b_f >= 0 && o->w_s1 >= 0 && o->b_s1 >= 0 &&
+         o->w_s2 >= 0 && o->b_s2 >= 0 && o->A >= 0 && o->a >= 0 && o->Sw >= 0 && o->sc >= 0 && (o->Sw & 3) == 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dln_sem_fold(float* params_flat, const DlnSemOffsets* off, void* stream) {
+  DLN_CHECK_ARG(params_flat && offsets_ok(off));
+  sem_fold_a_kernel<<<kHid, 256, 0, (cudaStream_t)stream>>>(params_flat, *off);
+  sem_fold_s_kernel<<<off->K, 256, 0, (cudaStream_t)stream>>>(params_flat, *off);
+  return dln_launch_status();
+}
+
+int dln_sem_unfold_grads(const float* params_flat, float* grads_flat, const DlnSemOffsets* off, void* stream) {
+  DLN_CHECK_ARG(params_flat && grads_flat && offsets_ok(off));
+  sem_unfold1_kernel<<<off->K + kHid, 256, 0, (cudaStream_t)stream>>>(params_flat, grads_flat, *off);
+  sem_unfold2_kernel<<<kHid + kW + 1, 256, 0, (cudaStream_t)stream>>>(params_flat, grads_flat, *off);
+  return dln_launch_status();
+}
+
+int dln_sem_head_fwd(const void* stash_fwd, int fwd_slots, int h_slot, long long P, int S, const float* params_flat,
+                     const DlnSemOffsets* off, float* hsum, float* out, int out_ld, void* stream) {
+  DLN_CHECK_ARG(stash_fwd && params_flat && offsets_ok(off) && P >= 0 && S >= 1 && fwd_slots >= 4 && h_slot >= 0 &&
+                h_slot + 4 <= fwd_slots);
+  DLN_CHECK_ARG((hsum || out) && (!out || out_ld >= off->K));
+  DLN_CHECK_ARG((reinterpret_cast<uintptr_t>(stash_fwd) & 15) == 0 && (reinterpret_cast<uintptr_t>(hsum) & 15) == 0);
+  if (P == 0) return DLN_OK;
+  const long long n_groups = (P + S - 1) / S;
+  long long blocks = (n_groups + 7) / 8;
+  blocks = blocks > 148 * 8 ? 148 * 8 : blocks;
+  sem_head_fwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const uint8_t*>(stash_fwd), fwd_slots, h_slot, P, S, params_flat + off->Sw, params_flat + off->sc,
+      off->K, hsum, out, out_ld, n_groups);
+  return dln_launch_status();
+}
+
+int dln_sem_head_bwd(const float* dsem, int dsem_ld, const float* hsum, long long P, int S, const float* params_flat,
+                     float* grads_flat, const DlnSemOffsets* off, float* G, void* stream) {
+  DLN_CHECK_ARG(dsem && hsum && params_flat && grads_flat && G && offsets_ok(off) && P >= 0 && S >= 1 &&
+                dsem_ld >= off->K);
+  if (P == 0) return DLN_OK;
+  const long long n_groups = (P + S - 1) / S;
+  long long blocks = (n_groups + kBwdGroupsPerStage - 1) / kBwdGroupsPerStage;
+  blocks = blocks > 148 * 2 ? 148 * 2 : blocks;
+  sem_head_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      dsem, dsem_ld, hsum, params_flat + off->Sw, off->K, n_groups, P, S, G, grads_flat + off->Sw, grads_flat + off->sc);
+  return dln_launch_status();
+}
+
+int dln_sample_sum(const float* raw, int C, int c0, int N, int S, float* out, void* stream) {
+  DLN_CHECK_ARG(raw && out && C > c0 && c0 >= 0 && N >= 0 && S >= 1);
+  if (N == 0) return DLN_OK;
+  const long long n = (long long)N * (C - c0);
+  sample_sum_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(raw, C, c0, N, S, out);
+  return dln_launch_status();
+}
+
+int dln_sample_sum_bwd(const float* g, int C, int c0, int N, int S, float* d_raw, void* stream) {
+  DLN_CHECK_ARG(g && d_raw && C > c0 && c0 >= 0 && N >= 0 && S >= 1);
+  if (N == 0) return DLN_OK;
+  const long long n = (long long)N * S * C;
+  sample_sum_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(g, C, c0, N, S, d_raw);
+  return dln_launch_status();
+}
+
+int dln_sem_ce_loss(const float* logits, int ld, const long long* target, int n_rgb, int N, int K, float coef,
+                    float* dsem, float* loss_sum, void* stream) {
+  DLN_CHECK_ARG(logits && dsem && loss_sum && N >= 0 && n_rgb >= 0 && n_rgb <= N && K >= 1 && K <= kMaxK && ld >= K);
+  DLN_CHECK_ARG(n_rgb == 0 || target);
+  if (N == 0) return DLN_OK;
+  sem_ce_kernel<<<(N + 255) / 256, 256, 0, (cudaStream_t)stream>>>(logits, ld, target, n_rgb, N, K, coef, dsem, loss_sum);
+  return dln_launch_status();
+}
+
+}  // extern "C"

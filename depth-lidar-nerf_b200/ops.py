@@ -117,6 +117,49 @@ def composite(raw: Tensor, z_vals: Tensor, rays_d: Tensor, noise: Optional[Tenso
     return _Composite.apply(raw, z_vals, rays_d, noise, noise_std, white_bkgd)
 
 
+class _SampleSum(torch.autograd.Function):
+    """torch.sum(raw[..., c0:], -2) (run_nerf_helpers.py:589) for a caller-supplied raw tensor."""
+
+    @staticmethod
+    def forward(ctx, raw, c0):
+        raw_c = _f32(raw, "sample_sum")
+        N, S, Cc = raw_c.shape
+        out = torch.empty(N, Cc - c0, device=raw_c.device)
+        L.call("dln_sample_sum", raw_c.data_ptr(), Cc, c0, N, S, out.data_ptr(), _stream(), tag="sample_sum")
+        ctx.cfg = (N, S, Cc, c0)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        N, S, Cc, c0 = ctx.cfg
+        gc = _f32(g, "sample_sum.backward")
+        d_raw = torch.empty(N, S, Cc, device=gc.device)
+        L.call("dln_sample_sum_bwd", gc.data_ptr(), Cc, c0, N, S, d_raw.data_ptr(), _stream(), tag="sample_sum_bwd")
+        return d_raw, None
+
+
+def sample_sum(raw: Tensor, c0: int = 4) -> Tensor:
+    """Per-ray semantic logits of raw2outputs: the unweighted sum of raw[..., c0:] over the samples."""
+    if raw.dim() != 3 or raw.shape[-1] <= c0:
+        raise ValueError("raw must be [N, S, >%d] to carry semantic logits" % c0)
+    return _SampleSum.apply(raw, c0)
+
+
+def semantic_ce(sem: Tensor, target: Tensor, n_rgb: int, coef: float, loss_sum: Tensor) -> Tensor:
+    """F.cross_entropy(sem[:n_rgb], target) (run_nerf.py:1542, :1546), fused forward + gradient: ADDS the summed
+    loss of the first n_rgb rays to loss_sum[0] and returns dsem = coef * (softmax - onehot) (zero rows behind
+    n_rgb)."""
+    s = _f32(sem, "semantic_ce")
+    N, K = s.shape
+    t = target.to(device=s.device, dtype=torch.int64).contiguous() if n_rgb > 0 else None
+    if t is not None and t.numel() < n_rgb:
+        raise ValueError("target_semantic needs one class index per RGB ray")
+    dsem = torch.empty_like(s)
+    L.call("dln_sem_ce_loss", s.data_ptr(), K, _ptr(t), int(n_rgb), N, K, float(coef), dsem.data_ptr(),
+           loss_sum.data_ptr(), _stream(), tag="semantic_ce")
+    return dsem
+
+
 def composite_bwd_fused_loss(raw: Tensor, z_vals: Tensor, rays_d: Tensor, noise: Optional[Tensor], noise_std: float,
                              white_bkgd: bool, target_rgb: Optional[Tensor], target_depth: Optional[Tensor],
                              ray_weights: Optional[Tensor], n_rgb: int, coef_rgb: float, coef_depth: float,

@@ -29,6 +29,7 @@ class NetShape:
     output_ch: int = 5
     skips: Sequence[int] = (4,)
     use_viewdirs: bool = True
+    semantic_num_classes: int = 0      # K > 0: semantic_linear = Linear(W, W/2) -> Linear(W/2, K) (helpers:107-111)
 
     def validate(self) -> None:
         if self.W != 256:
@@ -46,6 +47,14 @@ class NetShape:
                                  "module cannot be built that way either (run_nerf_helpers.py:91,:119)")
         if not self.use_viewdirs and not (1 <= self.output_ch <= 5):
             raise NotImplementedError("output_ch must be in [1,5]")
+        if not 0 <= self.semantic_num_classes <= L.SEM_MAX_CLASSES:
+            raise NotImplementedError("the semantic head kernels handle up to %d classes" % L.SEM_MAX_CLASSES)
+
+    @property
+    def sem_K(self) -> int:
+        """Semantic logits per output row: the reference only evaluates the head with view directions
+        (run_nerf_helpers.py:122-140); without them the layers exist but are never used."""
+        return self.semantic_num_classes if self.use_viewdirs else 0
 
     @property
     def L_pts(self) -> int:
@@ -79,6 +88,10 @@ class NetShape:
                     ("rgb_linear.weight", (3, self.W // 2)), ("rgb_linear.bias", (3,))]
         else:
             out += [("output_linear.weight", (self.output_ch, self.W)), ("output_linear.bias", (self.output_ch,))]
+        if self.semantic_num_classes:
+            out += [("semantic_linear.0.weight", (self.W // 2, self.W)), ("semantic_linear.0.bias", (self.W // 2,)),
+                    ("semantic_linear.1.weight", (self.semantic_num_classes, self.W // 2)),
+                    ("semantic_linear.1.bias", (self.semantic_num_classes,))]
         return out
 
 
@@ -104,6 +117,10 @@ class Plan:
     n_flat: int = 0
     off_M: int = -1
     off_bM: int = -1
+    # semantic head (csrc/semantic_kernels.cu): derived operands A, a, Sw, sc behind M / b' in the flat buffer; the
+    # gradient buffer's copies are per-call scratch (dA, da, dSw, dsc) that dln_sem_unfold_grads consumes
+    sem: L.SemOffsets = None
+    h_last_slot: int = -1
 
 
 def _set_k(step: L.ChainStep, slabs: List[int], cnts: List[int]) -> None:
@@ -139,6 +156,19 @@ def build_plan(shape: NetShape, fold_feature: bool = True) -> Plan:
         pl.off_M, pl.off_bM = off, off + (W // 2) * W
         pl.n_flat = pl.off_bM + W // 2
     O = pl.offsets
+    if shape.sem_K:
+        K = shape.sem_K
+        so = L.SemOffsets()
+        so.w_f, so.b_f = O["feature_linear.weight"], O["feature_linear.bias"]
+        so.w_s1, so.b_s1 = O["semantic_linear.0.weight"], O["semantic_linear.0.bias"]
+        so.w_s2, so.b_s2 = O["semantic_linear.1.weight"], O["semantic_linear.1.bias"]
+        so.A = pl.n_flat
+        so.a = so.A + (W // 2) * W
+        so.Sw = so.a + W // 2
+        so.sc = so.Sw + K * W
+        so.K = K
+        pl.n_flat = so.sc + (K + 3) // 4 * 4
+        pl.sem = so
     kc_pts = _ceil_div(shape.input_ch, 16)
     kc_dir = _ceil_div(shape.input_ch_views, 16)
 
@@ -182,6 +212,7 @@ def build_plan(shape: NetShape, fold_feature: bool = True) -> Plan:
                 st.head_off, st.head_bias_off = O["output_linear.weight"], O["output_linear.bias"]
         steps += 1
     feat_slot = H_slot(D)
+    pl.h_last_slot = H_slot(D - 1)
     hv_slot = feat_slot + (0 if pl.fold else 4)
     if shape.use_viewdirs:
         if not pl.fold:

@@ -145,19 +145,23 @@ def render_path(render_poses, hwf, chunk, render_kwargs, gt_imgs=None, savedir=N
     """run_nerf.py:268-359: full-image renders for a list of poses (evaluation / video), no autograd graph and
     therefore no activation stash.  Returns (rgbs[P,H,W,3], disps[P,H,W]) as numpy like the reference; with
     ``savedir`` each view's maps go to ``{i:03d}.npz`` (+ an 8-bit PNG when cv2 is importable -- imageio, the
-    reference's writer, is not a dependency here).  Tensorboard ``writer`` images and the semantic-map video are
-    the caller's visualisation code and are not reproduced."""
+    reference's writer, is not a dependency here).  With ``semantic_loss`` in ``render_kwargs`` a third array is
+    returned like the reference does (:355-357) -- here the per-pixel class indices argmax(sem_preds) [P,H,W]; the
+    colour palette (SemanticSegmentorHelper) and the Tensorboard ``writer`` images are the caller's visualisation
+    code and are not reproduced."""
     H, W, focal = hwf
     if render_factor != 0:
         H, W, focal = H // render_factor, W // render_factor, focal / render_factor
     H, W = int(H), int(W)
-    rgbs, disps = [], []
+    rgbs, disps, sems = [], [], []
     for i, c2w in enumerate(render_poses):
         with torch.no_grad():
             rgb, disp, acc, depth, extras = render(H, W, focal, chunk=chunk, c2w=c2w[:3, :4], retraw=True,
                                                    **render_kwargs)
         rgbs.append(rgb.cpu().numpy())
         disps.append(disp.cpu().numpy())
+        if 'sem_preds' in extras:
+            sems.append(torch.argmax(extras['sem_preds'], dim=-1).cpu().numpy())
         if savedir is not None:
             rgb8 = to8b(np.nan_to_num(rgbs[-1]))
             np.savez(os.path.join(savedir, '{:03d}.npz'.format(i)), rgb=rgbs[-1], disp=disps[-1],
@@ -167,6 +171,8 @@ def render_path(render_poses, hwf, chunk, render_kwargs, gt_imgs=None, savedir=N
                 cv2.imwrite(os.path.join(savedir, '{:03d}.png'.format(i)), rgb8[..., ::-1])
             except ImportError:
                 pass
+    if sems:
+        return np.stack(rgbs, 0), np.stack(disps, 0), np.stack(sems, 0)
     return np.stack(rgbs, 0), np.stack(disps, 0)
 
 
@@ -191,8 +197,6 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
     if sigma_loss is not None:
         raise NotImplementedError("sigma_loss reads an undefined variable in the reference train loop "
                                   "(run_nerf.py:1527) and is not part of the hot path")
-    if semantic_loss:
-        raise NotImplementedError("semantic head is outside this round's scope")
     if network_fn is None:
         raise NotImplementedError("the alpha_model branch (run_nerf.py:606-622) is dead code in the reference")
     rb = ops._f32(ray_batch, "render_rays")
@@ -208,10 +212,19 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
         return (torch.rand if kind == "u" else torch.randn)(shape, device=dev)
 
     def query(net, z):
+        """(raw, per-ray semantic logits | None).  Fused route: the logits come from the kept activations of the
+        last trunk layer (one sum per ray, csrc/semantic_kernels.cu) and raw carries its semantic columns only when
+        the caller asked for raw; generic route: raw[N, S, 4+K] from the query function, summed over the samples."""
         if isinstance(network_query_fn, FusedQuery) and network_query_fn.fused_ok(net, rb):
-            return net.forward_rays(rb, z)
+            K = net.sem_K
+            if semantic_loss and not K:
+                raise RuntimeError("semantic_loss=True needs networks built with semantic_num_classes")
+            if semantic_loss:
+                return net.forward_rays(rb, z, semantic=True, point_logits=bool(retraw))
+            return net.forward_rays(rb, z, point_logits=bool(retraw and K)), None
         pts = rays_o[..., None, :] + rays_d[..., None, :] * z[..., :, None]
-        return network_query_fn(pts, viewdirs, net)
+        raw = network_query_fn(pts, viewdirs, net)
+        return raw, (ops.sample_sum(raw, 4) if semantic_loss else None)          # helpers:589
 
     def composite(raw, z, noise_name):
         noise = draw(noise_name, "n", (N, z.shape[1])) if raw_noise_std > 0. else None
@@ -219,23 +232,27 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
 
     t_rand = draw("t_rand", "u", (N, N_samples)) if perturb > 0. else None
     z_vals = ops.stratified_z(rb, N_samples, t_rand, lindisp)
-    raw = query(network_fn, z_vals)
+    raw, sem = query(network_fn, z_vals)
     rgb_map, disp_map, acc_map, weights, depth_map = composite(raw, z_vals, "noise0")
 
     ret = {}
     if N_importance > 0:
-        rgb_map_0, disp_map_0, acc_map_0, depth_map0 = rgb_map, disp_map, acc_map, depth_map
+        rgb_map_0, disp_map_0, acc_map_0, depth_map0, sem0 = rgb_map, disp_map, acc_map, depth_map, sem
         u = draw("u", "u", (N, N_importance)) if perturb != 0. else None        # det = (perturb == 0)
         z_samples, z_vals = ops.importance_resample(z_vals, weights.detach(), N_importance, u)
         run_fn = network_fn if network_fine is None else network_fine
-        raw = query(run_fn, z_vals)
+        raw, sem = query(run_fn, z_vals)
         rgb_map, disp_map, acc_map, weights, depth_map = composite(raw, z_vals, "noise1")
     ret.update(rgb_map=rgb_map, disp_map=disp_map, acc_map=acc_map, depth_map=depth_map)
     if retraw:
         ret['raw'] = raw
+    if semantic_loss:
+        ret['sem_preds'] = sem                                                     # :652-653
     if N_importance > 0:
         ret['rgb0'], ret['disp0'], ret['acc0'], ret['depth_map0'] = rgb_map_0, disp_map_0, acc_map_0, depth_map0
         ret['z_std'] = torch.std(z_samples, dim=-1, unbiased=False)
+        if semantic_loss:
+            ret['sem_preds0'] = sem0                                               # :662-663
     return ret
 
 

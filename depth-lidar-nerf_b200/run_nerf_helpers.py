@@ -16,6 +16,7 @@ import torch.nn as nn
 
 from . import _lib as L
 from . import ops
+from .ops import _ptr
 from .plan import NetShape, Plan, build_plan
 
 Tensor = torch.Tensor
@@ -89,18 +90,40 @@ class _MLP(torch.autograd.Function):
         return (None, None, None, None, None) + tuple(grads)
 
 
+class _MLPSem(torch.autograd.Function):
+    """``_MLP`` for a network with the semantic head: returns (raw4 [P,4], sem [G,K], point_logits [P,K] | empty).
+    ``sem`` are the logits summed over groups of ``S`` consecutive points (run_nerf_helpers.py:589; S = 1: per
+    point); ``point_logits`` only fills the semantic columns of a returned ``raw`` and carries no gradient."""
+
+    @staticmethod
+    def forward(ctx, net: "NeRF", mode, a, b, P, S, want_points, *params):
+        train = any(ctx.needs_input_grad[7:])
+        out, saved, sem, pts = net._run_forward(mode, a, b, P, keep=train, sem_group=S, sem_points=want_points)
+        ctx.net, ctx.saved, ctx.P = net, saved, P
+        if pts is None:
+            pts = out.new_empty(0)
+        ctx.mark_non_differentiable(pts)
+        if sem is None:
+            sem = out.new_empty(0)
+            ctx.mark_non_differentiable(sem)
+        return out, sem, pts
+
+    @staticmethod
+    def backward(ctx, d_out, d_sem, _d_pts):
+        net: "NeRF" = ctx.net
+        grads = net._run_backward(d_out, ctx.saved, ctx.P, d_sem=d_sem)
+        ctx.saved = None
+        return (None,) * 7 + tuple(grads)
+
+
 class NeRF(nn.Module):
     def __init__(self, D=8, W=256, input_ch=3, input_ch_views=3, output_ch=5, skips=[4], use_viewdirs=False,
                  semantic_num_classes=None):
         super().__init__()
-        if semantic_num_classes:
-            raise NotImplementedError("the semantic head (run_nerf_helpers.py:107-111) is outside the B200 "
-                                      "hot-path scope of this round")
         self.D, self.W = D, W
         self.input_ch, self.input_ch_views = input_ch, input_ch_views
         self.skips, self.use_viewdirs = skips, use_viewdirs
         self.semantic_num_classes = semantic_num_classes
-        self.semantic_linear = False
         # identical registration order / names / shapes / init to the reference (:90-105)
         self.pts_linears = nn.ModuleList(
             [nn.Linear(input_ch, W)] + [nn.Linear(W, W) if i not in self.skips else nn.Linear(W + input_ch, W)
@@ -112,9 +135,14 @@ class NeRF(nn.Module):
             self.rgb_linear = nn.Linear(W // 2, 3)
         else:
             self.output_linear = nn.Linear(W, output_ch)
+        if semantic_num_classes:        # (:107-111) two Linear layers, no activation; registered last
+            self.semantic_linear = nn.Sequential(nn.Linear(W, W // 2), nn.Linear(W // 2, semantic_num_classes))
+        else:
+            self.semantic_linear = False
         self.output_ch = output_ch
         self._shape = NetShape(D=D, W=W, input_ch=input_ch, input_ch_views=input_ch_views, output_ch=output_ch,
-                               skips=tuple(skips), use_viewdirs=use_viewdirs)
+                               skips=tuple(skips), use_viewdirs=use_viewdirs,
+                               semantic_num_classes=int(semantic_num_classes or 0))
         self._plan: Optional[Plan] = None
         self._dev_state = None
 
@@ -170,6 +198,8 @@ class NeRF(nn.Module):
         lib, s = L.lib(), ops._stream()
         if pl.fold:
             L.call("dln_mlp_fold", st["flat"].data_ptr(), *self._fold_args(), s, tag="fold_feature")
+        if pl.sem is not None:
+            L.call("dln_sem_fold", st["flat"].data_ptr(), C.byref(pl.sem), s, tag="fold_semantic")
         L.call("dln_mlp_pack_weights", st["flat"].data_ptr(), st["fwd_jobs"].data_ptr(), len(pl.fwd_jobs),
                                          st["wf"].data_ptr(), s, tag="pack_weights(fwd)")
         L.call("dln_mlp_pack_weights", st["flat"].data_ptr(), st["bwd_jobs"].data_ptr(), len(pl.bwd_jobs),
@@ -182,7 +212,16 @@ class NeRF(nn.Module):
                 O["feature_linear.bias"], O["views_linears.0.bias"], pl.off_M, pl.off_bM)
 
     # ------------------------------------------------------------------ kernels
-    def _run_forward(self, mode, a, b, P, keep, force_pack=False):
+    @property
+    def sem_K(self) -> int:
+        """Semantic logits appended to every output row (0: no head, or a head the reference never evaluates)."""
+        return self._shape.sem_K
+
+    def _run_forward(self, mode, a, b, P, keep, force_pack=False, sem_group=0, sem_points=False):
+        """One forward chain launch.  Returns (out, saved) -- and, when the semantic head is asked for through
+        ``sem_group`` (points per summed group, run_nerf_helpers.py:589) / ``sem_points`` (per-point logits for
+        ``raw``), (out, saved, sem [G,K] | None, point_logits [P,K] | None).  The head reads the kept activations,
+        so an inference pass with semantics also writes the stash."""
         st = self._state()
         self._pack(st, force_pack)
         pl = self._plan
@@ -198,21 +237,57 @@ class NeRF(nn.Module):
             args.x, args.x_ld = a.data_ptr(), a.stride(0)
         args.wblob, args.fblob, args.out = st["wf"].data_ptr(), st["flat"].data_ptr(), out.data_ptr()
         saved = None
-        if keep:
+        want_sem = pl.sem is not None and (sem_group > 0 or sem_points)
+        if (sem_group > 0 or sem_points) and pl.sem is None:
+            raise RuntimeError("semantic logits requested from a NeRF built without semantic_num_classes / view directions")
+        stash = None
+        if keep or want_sem:
             stash = torch.empty(n_tiles * pl.fwd_slots * L.SLAB_BYTES, device=dev, dtype=torch.uint8)
+            args.stash = stash.data_ptr()
+        if keep:
             masks = torch.empty(pl.mask_slots * n_tiles * 2 * 128 * 4, device=dev, dtype=torch.int32)
-            args.stash, args.masks = stash.data_ptr(), masks.data_ptr()
+            args.masks = masks.data_ptr()
             saved = (stash, masks)
         L.call("dln_mlp_chain", C.byref(pl.fwd), C.byref(args), st["sms"], ops._stream(), tag="mlp_fwd D=%d" % self.D)
-        return out, saved
+        if not want_sem:
+            return out, saved
+        K = pl.sem.K
+        sem = pts = hsum = None
+        if sem_group > 0:
+            G = (P + sem_group - 1) // sem_group
+            sem = torch.empty(G, K, device=dev, dtype=torch.float32)
+            hsum = torch.empty(G, self.W, device=dev, dtype=torch.float32) if keep else None
+            L.call("dln_sem_head_fwd", stash.data_ptr(), pl.fwd_slots, pl.h_last_slot, P, int(sem_group),
+                   st["flat"].data_ptr(), C.byref(pl.sem), _ptr(hsum), sem.data_ptr(), K, ops._stream(),
+                   tag="sem_head_fwd")
+        if sem_points:
+            pts = torch.empty(P, K, device=dev, dtype=torch.float32)
+            L.call("dln_sem_head_fwd", stash.data_ptr(), pl.fwd_slots, pl.h_last_slot, P, 1, st["flat"].data_ptr(),
+                   C.byref(pl.sem), None, pts.data_ptr(), K, ops._stream(), tag="sem_point_logits")
+        if keep:
+            saved = (stash, masks, hsum, int(sem_group))
+        return out, saved, sem, pts
 
-    def _run_backward(self, d_out, saved, P, gflat=None, sms=None):
-        """dgrad chain + wgrad.  ``gflat`` (flat fp32 [n_params]) accumulates across calls when given (ray-chunked
-        steps); otherwise a zeroed buffer is allocated."""
+    def _run_backward(self, d_out, saved, P, gflat=None, sms=None, d_sem=None):
+        """dgrad chain + wgrad.  ``gflat`` (flat fp32 [n_flat]) accumulates across calls when given (ray-chunked
+        steps); otherwise a zeroed buffer is allocated.  ``d_sem`` [G, K]: gradient of the summed semantic logits
+        (``sem`` of ``_run_forward``); its input gradient enters the dgrad chain as one fp32 row per group."""
         st = self._state()
         pl = self._plan
         dev = st["device"]
-        stash_f, masks = saved
+        stash_f, masks = saved[0], saved[1]
+        if gflat is None:
+            gflat = torch.zeros(pl.n_flat, device=dev, dtype=torch.float32)
+        elif pl.n_flat > pl.n_params:
+            gflat[pl.n_params:].zero_()        # dM / db' / dSw / dsc scratch of THIS call (the buffer accumulates across calls)
+        sem_G = None
+        if d_sem is not None and pl.sem is not None and len(saved) > 2 and saved[2] is not None:
+            hsum, S = saved[2], saved[3]
+            ds = d_sem.reshape(hsum.shape[0], pl.sem.K)
+            ds = ds.contiguous() if ds.dtype == torch.float32 else ds.float().contiguous()
+            sem_G = torch.empty_like(hsum)
+            L.call("dln_sem_head_bwd", ds.data_ptr(), pl.sem.K, hsum.data_ptr(), P, S, st["flat"].data_ptr(),
+                   gflat.data_ptr(), C.byref(pl.sem), sem_G.data_ptr(), ops._stream(), tag="sem_head_bwd")
         n_tiles = (P + L.TILE_ROWS - 1) // L.TILE_ROWS
         d = d_out.reshape(P, self._shape.out_ch)
         d = d.contiguous() if d.dtype == torch.float32 else d.float().contiguous()
@@ -221,14 +296,12 @@ class NeRF(nn.Module):
         args.P = P
         args.wblob, args.fblob = st["wb"].data_ptr(), st["flat"].data_ptr()
         args.d_out, args.stash, args.masks = d.data_ptr(), stash_b.data_ptr(), masks.data_ptr()
+        if sem_G is not None:
+            args.sem_g, args.sem_g_div = sem_G.data_ptr(), S
         lib, s = L.lib(), ops._stream()
         # `sms` caps the persistent dgrad grid so that a concurrent kernel on another stream keeps some SMs
         L.call("dln_mlp_chain", C.byref(pl.bwd), C.byref(args), min(st["sms"], sms) if sms else st["sms"], s,
                tag="mlp_dgrad D=%d" % self.D)
-        if gflat is None:
-            gflat = torch.zeros(pl.n_flat, device=dev, dtype=torch.float32)
-        elif pl.fold:
-            gflat[pl.n_params:].zero_()        # dM / db' scratch of THIS call (the buffer accumulates across calls)
         n_items = len(pl.wgrad)
         # ONE wave (n_items * splits <= #SMs): every item's CTA k then walks the same tile range at about the same
         # pace, so slabs two items share (dZ of the skip layer, the last hidden layer, dZ_views) are found in L2 by
@@ -240,6 +313,9 @@ class NeRF(nn.Module):
         if pl.fold:
             L.call("dln_mlp_unfold_grads", st["flat"].data_ptr(), gflat.data_ptr(), *self._fold_args(), s,
                    tag="unfold_grads")
+        if sem_G is not None:
+            L.call("dln_sem_unfold_grads", st["flat"].data_ptr(), gflat.data_ptr(), C.byref(pl.sem), s,
+                   tag="unfold_semantic")
         grads = []
         for (name, shp), p in zip(self._shape.param_shapes(), self._ordered_params()):
             o = pl.offsets[name]
@@ -254,17 +330,34 @@ class NeRF(nn.Module):
             raise RuntimeError("expected at least %d input channels, got %d" % (n_in, x.shape[-1]))
         xs = ops._f32(x, "NeRF.forward").reshape(-1, x.shape[-1])
         P = xs.shape[0]
-        out = _MLP.apply(self, "x", xs, None, P, *self._ordered_params())
+        if self.sem_K:                  # [rgb, alpha, semantic logits] (:139-140); S = 1: per-point logits
+            out, sem, _ = _MLPSem.apply(self, "x", xs, None, P, 1, False, *self._ordered_params())
+            out = torch.cat([out, sem], -1)
+        else:
+            out = _MLP.apply(self, "x", xs, None, P, *self._ordered_params())
         return out.reshape(*x.shape[:-1], out.shape[-1])
 
-    def forward_rays(self, ray_batch: Tensor, z_vals: Tensor) -> Tensor:
+    def forward_rays(self, ray_batch: Tensor, z_vals: Tensor, semantic: bool = False, point_logits: bool = False):
         """Fused path of run_nerf.py:595 + run_network (:60-74) + forward: points o + d*z are formed,
         encoded (positions per sample, the unit view direction once per ray) and pushed through the MLP
-        inside one kernel.  ray_batch is the packed [N, 8|11] batch of render(); returns raw[N, S, C]."""
+        inside one kernel.  ray_batch is the packed [N, 8|11] batch of render(); returns raw[N, S, 4].
+
+        With the semantic head: ``semantic=True`` returns (raw, sem_preds[N, K]) -- the per-ray logits of
+        raw2outputs (helpers:589: the UNWEIGHTED sum of the per-sample logits), differentiable; ``point_logits``
+        appends the per-sample logits to raw ([N, S, 4+K] like the reference's), as values only."""
         rb, z = ops._f32(ray_batch, "forward_rays"), ops._f32(z_vals, "forward_rays")
         if self.use_viewdirs and rb.shape[1] < 11:
             raise RuntimeError("use_viewdirs=True needs the unit view direction in the last 3 ray columns")
         N, S = z.shape
+        if (semantic or point_logits) and not self.sem_K:
+            raise RuntimeError("this NeRF has no semantic head (semantic_num_classes / use_viewdirs)")
+        if semantic or point_logits:
+            out, sem, pts = _MLPSem.apply(self, "rays", rb, z, N * S, S if semantic else 0, bool(point_logits),
+                                          *self._ordered_params())
+            raw = out.reshape(N, S, 4)
+            if point_logits:
+                raw = torch.cat([raw, pts.reshape(N, S, -1)], -1)
+            return (raw, sem) if semantic else raw
         out = _MLP.apply(self, "rays", rb, z, N * S, *self._ordered_params())
         return out.reshape(N, S, out.shape[-1])
 
@@ -326,13 +419,15 @@ def sample_pdf(bins, weights, N_samples, det=False, pytest=False):
 # Compositing (run_nerf_helpers.py:542-595)
 # --------------------------------------------------------------------------------------------------
 def raw2outputs(raw, z_vals, rays_d, raw_noise_std=0, white_bkgd=False, pytest=False, semantic_loss=False):
-    """Returns (rgb_map, disp_map, acc_map, weights, depth_map), differentiable w.r.t. raw."""
-    if semantic_loss:
-        raise NotImplementedError("semantic logits (run_nerf_helpers.py:586-593) are outside this round's scope")
+    """Returns (rgb_map, disp_map, acc_map, weights, depth_map[, semantic_class_preds]), differentiable w.r.t.
+    raw.  semantic_loss: the per-ray logits are the UNWEIGHTED sum of raw[..., 4:] over the samples (:586-593)."""
     noise = None
     if raw_noise_std > 0.:
         noise = torch.randn(raw[..., 3].shape, device=raw.device)
         if pytest:       # the reference's hook draws UNIFORM numbers here (:567-571)
             np.random.seed(0)
             noise = torch.tensor(np.random.rand(*list(raw[..., 3].shape)), dtype=torch.float32, device=raw.device)
-    return ops.composite(raw, z_vals, rays_d, noise, float(raw_noise_std), bool(white_bkgd))
+    maps = ops.composite(raw, z_vals, rays_d, noise, float(raw_noise_std), bool(white_bkgd))
+    if semantic_loss:
+        return tuple(maps) + (ops.sample_sum(raw, 4),)
+    return maps

@@ -136,6 +136,7 @@ def train_step(H, W, focal, batch_rays: Tensor, target_s: Tensor, target_depth: 
                depth_importance: float = 1., ray_weights: Optional[Tensor] = None, depth_mode: str = "mse",
                coarse_loss: bool = True, world_size: int = 1, group=None, ray_chunk: Optional[int] = None,
                overlap_coarse_backward: bool = True, coarse_sms: Optional[int] = None,
+               target_semantic: Optional[Tensor] = None, semantic_lambda: float = 0.,
                _rng: Optional[Dict[str, Tensor]] = None, _force_pack: bool = False) -> Dict[str, Tensor]:
     """render + loss + backward for one ray batch; fills ``.grad`` of both networks (averaged over
     ``world_size`` ranks when > 1) and returns the loss terms as 0-d tensors (no host sync).
@@ -144,6 +145,11 @@ def train_step(H, W, focal, batch_rays: Tensor, target_s: Tensor, target_depth: 
     D=4/D=8 pair) are processed chunk by chunk -- each chunk a slice of the RGB rays plus the matching slice of
     the depth rays, full forward + backward, gradients accumulated in the same flat fp32 buffers -- which is
     the same sum as the unchunked step (config E: N_rand 16 k ... 256 k).
+
+    ``target_semantic`` (class index per RGB ray) with networks that carry the semantic head adds
+    ``semantic_lambda * (CE(sem_preds[:n_rgb]) + CE(sem_preds0[:n_rgb]))`` (run_nerf.py:1541-1548): the per-ray logits
+    come from one pass over the kept last-trunk-layer activations, the cross-entropy gradient is formed in one small
+    kernel and enters the dgrad chain as one fp32 row per ray.
 
     Random draws follow the reference's order (rand jitter, randn coarse noise, rand u, randn fine noise);
     ``_rng`` (tests) injects them."""
@@ -158,7 +164,12 @@ def train_step(H, W, focal, batch_rays: Tensor, target_s: Tensor, target_depth: 
     depth_norm = float(target_depth.max()) if (use_depth and mode == 2) else 1.0
     coef_rgb = 2.0 / (3.0 * max(n_rgb, 1))
     coef_dep = 2.0 * depth_lambda * depth_importance / max(n_dep, 1) if use_depth else 0.0
-    sums = torch.zeros(4, device=dev)
+    use_sem = target_semantic is not None and semantic_lambda != 0. and n_rgb > 0
+    if use_sem and not (network_fn.sem_K and network_fine.sem_K):
+        raise RuntimeError("target_semantic needs networks built with semantic_num_classes")
+    coef_sem = semantic_lambda / max(n_rgb, 1)
+    tsem = target_semantic.to(device=dev, dtype=torch.int64) if use_sem else None
+    sums = torch.zeros(8, device=dev)
     tgt = ops._f32(target_s, "train_step")
     tdep = ops._f32(target_depth, "train_step") if use_depth else None
     rw = ops._f32(ray_weights, "train_step") if (use_depth and ray_weights is not None) else None
@@ -171,6 +182,7 @@ def train_step(H, W, focal, batch_rays: Tensor, target_s: Tensor, target_depth: 
     for c in range(n_chunks):
         if n_chunks == 1:
             rb_c, tgt_c, tdep_c, rw_c, nr_c, rng = rb, tgt, tdep, rw, n_rgb, (_rng or {})
+            tsem_c = tsem
         else:
             r0, r1 = shard_bounds(n_rgb, c, n_chunks)
             d0, d1 = shard_bounds(n_dep, c, n_chunks)
@@ -178,6 +190,7 @@ def train_step(H, W, focal, batch_rays: Tensor, target_s: Tensor, target_depth: 
             rb_c, tgt_c, nr_c = pick(rb), tgt[r0:r1], r1 - r0
             tdep_c = tdep[d0:d1] if tdep is not None else None
             rw_c = rw[d0:d1] if rw is not None else None
+            tsem_c = tsem[r0:r1] if tsem is not None else None
             rng = {k: pick(v) for k, v in (_rng or {}).items()}
             if rb_c.shape[0] == 0:
                 continue
@@ -191,23 +204,25 @@ def train_step(H, W, focal, batch_rays: Tensor, target_s: Tensor, target_depth: 
 
         t_rand = draw("t_rand", "u", (Nc, N_samples)) if perturb > 0. else None
         z0 = ops.stratified_z(rb_c, N_samples, t_rand, lindisp)
-        raw0, saved0 = network_fn._run_forward("rays", rb_c, z0, Nc * N_samples, keep=True,
-                                               force_pack=_force_pack and c == 0)
+        sem_kw = lambda S: dict(sem_group=S) if use_sem else {}          # noqa: E731
+        raw0, saved0, *sem0 = network_fn._run_forward("rays", rb_c, z0, Nc * N_samples, keep=True,
+                                                      force_pack=_force_pack and c == 0, **sem_kw(N_samples))
         raw0 = raw0.view(Nc, N_samples, -1)
         noise0 = draw("noise0", "n", (Nc, N_samples)) if raw_noise_std > 0. else None
         rgb0, disp0, acc0, w0, depth0 = ops.composite(raw0, z0, rays_d, noise0, float(raw_noise_std),
                                                       bool(white_bkgd))
         u = draw("u", "u", (Nc, N_importance)) if perturb != 0. else None
         z_samples, z1 = ops.importance_resample(z0, w0, N_importance, u)
-        raw1, saved1 = network_fine._run_forward("rays", rb_c, z1, Nc * S1, keep=True,
-                                                 force_pack=_force_pack and c == 0)
+        raw1, saved1, *sem1 = network_fine._run_forward("rays", rb_c, z1, Nc * S1, keep=True,
+                                                        force_pack=_force_pack and c == 0, **sem_kw(S1))
         raw1 = raw1.view(Nc, S1, -1)
         noise1 = draw("noise1", "n", (Nc, S1)) if raw_noise_std > 0. else None
         # fine pass: colour loss on the RGB rays, depth loss on the depth rays (run_nerf.py:1461, :1500-1524)
         d_raw1 = ops.composite_bwd_fused_loss(raw1, z1, rays_d, noise1, raw_noise_std, white_bkgd, tgt_c, tdep_c,
                                               rw_c, nr_c, coef_rgb, coef_dep, mode, depth_norm, sums[0:2])
+        d_sem1 = ops.semantic_ce(sem1[0], tsem_c, nr_c, coef_sem, sums[4:5]) if use_sem else None
         side = None
-        if coarse_loss:
+        if coarse_loss or use_sem:
             # coarse pass: colour loss only (run_nerf.py:1759-1761); depth_map0 is unsupervised.  It depends on the
             # coarse forward alone, so it runs on a second stream next to the fine backward: its CTAs fill the SMs
             # the persistent fine-net kernels leave idle at their tails and under the HBM-bound wgrad.
@@ -217,15 +232,18 @@ def train_step(H, W, focal, batch_rays: Tensor, target_s: Tensor, target_depth: 
                 side.wait_stream(main)
             with torch.cuda.stream(side):
                 d_raw0 = ops.composite_bwd_fused_loss(raw0, z0, rays_d, noise0, raw_noise_std, white_bkgd, tgt_c,
-                                                      None, None, nr_c, coef_rgb, 0.0, 0, 1.0, sums[2:4])
+                                                      None, None, nr_c, coef_rgb if coarse_loss else 0.0, 0.0, 0, 1.0,
+                                                      sums[2:4])
+                # the coarse logits are supervised too (run_nerf.py:1545-1546), whatever no_coarse says
+                d_sem0 = ops.semantic_ce(sem0[0], tsem_c, nr_c, coef_sem, sums[5:6]) if use_sem else None
                 grads_c = network_fn._run_backward(d_raw0, saved0, Nc * N_samples, gflat=gacc[0],
-                                                   sms=coarse_sms if side is not main else None)
-        grads_f = network_fine._run_backward(d_raw1, saved1, Nc * S1, gflat=gacc[1])
+                                                   sms=coarse_sms if side is not main else None, d_sem=d_sem0)
+        grads_f = network_fine._run_backward(d_raw1, saved1, Nc * S1, gflat=gacc[1], d_sem=d_sem1)
         if side is not None and side is not torch.cuda.current_stream(dev):
             torch.cuda.current_stream(dev).wait_stream(side)
         del saved1, d_raw1, raw1, saved0
     _assign_grads(network_fine, grads_f)
-    if coarse_loss:
+    if coarse_loss or use_sem:
         _assign_grads(network_fn, grads_c)
     if world_size > 1:
         allreduce_gradients(list(network_fn.parameters()) + list(network_fine.parameters()), world_size, group)
@@ -233,8 +251,12 @@ def train_step(H, W, focal, batch_rays: Tensor, target_s: Tensor, target_depth: 
     img_loss0 = sums[2] / (3.0 * max(n_rgb, 1))
     depth_loss = sums[1] / max(n_dep, 1)
     loss = img_loss + depth_lambda * depth_importance * depth_loss + (img_loss0 if coarse_loss else 0.)
-    return {"loss": loss, "img_loss": img_loss, "img_loss0": img_loss0, "depth_loss": depth_loss,
-            "psnr": -10. * torch.log10(img_loss)}
+    out = {"img_loss": img_loss, "img_loss0": img_loss0, "depth_loss": depth_loss, "psnr": -10. * torch.log10(img_loss)}
+    if use_sem:
+        out["semantic_loss"], out["semantic_loss0"] = sums[4] / n_rgb, sums[5] / n_rgb
+        loss = loss + semantic_lambda * (out["semantic_loss"] + out["semantic_loss0"])
+    out["loss"] = loss
+    return out
 
 
 def _assign_grads(net: NeRF, grads) -> None:
@@ -266,8 +288,10 @@ class GraphedTrainStep:
         self.target_s = torch.zeros(n_rgb, 3, device=dev)
         self.target_depth = torch.zeros(n_rays - n_rgb, device=dev)
         self.ray_weights = torch.ones(n_rays - n_rgb, device=dev) if kw.pop("use_ray_weights", False) else None
+        self.target_semantic = (torch.zeros(n_rgb, device=dev, dtype=torch.int64)
+                                if kw.get("semantic_lambda", 0.) != 0. else None)
         args = (H, W, focal, self.rays, self.target_s, self.target_depth, n_rgb, network_fn, network_fine)
-        kw = dict(kw, ray_weights=self.ray_weights, world_size=1, _force_pack=True)
+        kw = dict(kw, ray_weights=self.ray_weights, target_semantic=self.target_semantic, world_size=1, _force_pack=True)
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
@@ -280,13 +304,15 @@ class GraphedTrainStep:
         self._grads = [(p, p.grad) for net in self.nets for p in net.parameters()]
 
     def __call__(self, batch_rays: Tensor, target_s: Tensor, target_depth: Optional[Tensor] = None,
-                 ray_weights: Optional[Tensor] = None) -> Dict[str, Tensor]:
+                 ray_weights: Optional[Tensor] = None, target_semantic: Optional[Tensor] = None) -> Dict[str, Tensor]:
         self.rays.copy_(batch_rays, non_blocking=True)
         self.target_s.copy_(target_s, non_blocking=True)
         if target_depth is not None:
             self.target_depth.copy_(target_depth, non_blocking=True)
         if ray_weights is not None and self.ray_weights is not None:
             self.ray_weights.copy_(ray_weights, non_blocking=True)
+        if target_semantic is not None and self.target_semantic is not None:
+            self.target_semantic.copy_(target_semantic, non_blocking=True)
         self.graph.replay()
         for p, g in self._grads:          # survive optimizer.zero_grad(set_to_none=True)
             p.grad = g

@@ -158,6 +158,10 @@ typedef struct {
   void* stash;             /* [tiles][stash_slots][DLN_SLAB_BYTES] or null                             */
   uint32_t* masks;         /* [mask_slots][tiles][4][128][2] relu bit masks                            */
   long long* trace;        /* optional debug timeline: 64 entries [4 roles][2 steps][8 events] of %clock, CTA 0 only */
+  const float* sem_g;      /* bwd, optional: G[ceil(P / sem_g_div), 256] added to dH of the last trunk layer
+                              (DLN_EPI_BWD_MASK_SIGMA step) -- the semantic head's input gradient, dln_sem_head_bwd */
+  int32_t sem_g_div;       /* points per row of sem_g (samples per ray; 1 = one row per point)                  */
+  int32_t pad_;
 } DlnChainArgs;
 
 /* Fused MLP chain (forward or dgrad).  prog_host / args_host are HOST structs passed by value to the
@@ -228,6 +232,50 @@ int dln_mlp_unfold_grads(const float* params_flat, float* grads_flat, long long 
                          long long off_bM, void* stream);
 
 /* ----------------------------------------------------------------------------------------------
+ * Semantic head: semantic_linear = Linear(256,128) -> Linear(128,K) on `feature`
+ * (run_nerf_helpers.py:107-111, :126-127), per-ray logits = UNWEIGHTED sum over the samples (:586-589), and the
+ * cross-entropy of run_nerf.py:1541-1548.  No activation sits between the last trunk layer h and the logits, so
+ * semantic(point) = Sw h + sc with Sw = W_s2 W_s1 W_f [K x 256] and sem_preds(ray) = Sw (sum_s h_s) + S sc: the head
+ * runs on the activation slabs the forward chain keeps, never on a per-point 256 -> 256 -> 128 -> K stack.
+ * -------------------------------------------------------------------------------------------- */
+#define DLN_SEM_MAX_CLASSES 32
+
+/* Float offsets into the flat parameter buffer (and, identically, the flat gradient buffer): the six parameter
+ * tensors the head touches and its derived operands behind the parameters. */
+typedef struct {
+  int64_t w_f, b_f;    /* feature_linear.weight [256 x 256], .bias [256]                                  */
+  int64_t w_s1, b_s1;  /* semantic_linear.0.weight [128 x 256], .bias [128]                               */
+  int64_t w_s2, b_s2;  /* semantic_linear.1.weight [K x 128], .bias [K]                                   */
+  int64_t A, a;        /* derived: A = W_s1 W_f [128 x 256], a = W_s1 b_f + b_s1 [128]  (gradient buffer: dA, da scratch) */
+  int64_t Sw, sc;      /* derived: Sw = W_s2 A [K x 256], sc = W_s2 a + b_s2 [K]        (gradient buffer: dSw, dsc of one call) */
+  int32_t K;           /* classes, 1..DLN_SEM_MAX_CLASSES                                                  */
+  int32_t pad_;
+} DlnSemOffsets;
+
+/* A, a, Sw, sc from the parameters (after every weight update). */
+int dln_sem_fold(float* params_flat, const DlnSemOffsets* off_host, void* stream);
+/* grads_flat[Sw / sc] hold dSw / dsc of ONE backward call: adds the gradients of semantic_linear.{0,1}.{weight,bias}
+ * and the head's share of feature_linear.{weight,bias} to their regions of grads_flat. */
+int dln_sem_unfold_grads(const float* params_flat, float* grads_flat, const DlnSemOffsets* off_host, void* stream);
+/* Groups of S consecutive points (a ray; S = 1: a point): hsum[g, 256] = sum of the kept last-trunk-layer activations
+ * (slabs h_slot..h_slot+3 of every tile of the forward stash; may be null) and out[g*out_ld + k] = Sw hsum + n_g sc
+ * (may be null).  Replaces semantic_linear's forward and `torch.sum(raw[..., 4:], -2)` (run_nerf_helpers.py:589). */
+int dln_sem_head_fwd(const void* stash_fwd, int fwd_slots, int h_slot, long long P, int S, const float* params_flat,
+                     const DlnSemOffsets* off_host, float* hsum, float* out, int out_ld, void* stream);
+/* dsem[g*dsem_ld + k] = d loss / d out of dln_sem_head_fwd.  Writes G[g, 256] = dsem Sw (hand it to the dgrad chain as
+ * DlnChainArgs.sem_g with sem_g_div = S) and ADDS dSw / dsc into grads_flat[Sw / sc] (zero them before the call). */
+int dln_sem_head_bwd(const float* dsem, int dsem_ld, const float* hsum, long long P, int S, const float* params_flat,
+                     float* grads_flat, const DlnSemOffsets* off_host, float* G, void* stream);
+/* Generic route (raw2outputs on a caller-supplied raw[N,S,C]): out[N, C-c0] = sum over the samples of raw[..., c0:]
+ * (run_nerf_helpers.py:589, c0 = 4), and its backward d_raw[n,s,c] = g[n, c-c0] for c >= c0, 0 below. */
+int dln_sample_sum(const float* raw, int C, int c0, int N, int S, float* out, void* stream);
+int dln_sample_sum_bwd(const float* g, int C, int c0, int N, int S, float* d_raw, void* stream);
+/* F.cross_entropy(logits[:n_rgb], target) with mean reduction (run_nerf.py:1542, :1546): ADDS the summed loss to
+ * loss_sum[0] and writes dsem[N, K] = coef * (softmax - onehot) for the first n_rgb rays, 0 for the others. */
+int dln_sem_ce_loss(const float* logits, int ld, const long long* target, int n_rgb, int N, int K, float coef,
+                    float* dsem, float* loss_sum, void* stream);
+
+/* ----------------------------------------------------------------------------------------------
  * Optimiser
  * -------------------------------------------------------------------------------------------- */
 
@@ -238,9 +286,9 @@ int dln_mlp_unfold_grads(const float* params_flat, float* grads_flat, long long 
 int dln_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, double lr,
                   double beta1, double beta2, double eps, int step, float grad_scale, void* stream);
 
-/* Host-only: sizeof of the five ABI structs, in the order ChainStep, ChainProgram, ChainArgs, WgradItem,
- * PackJob, so a binding can verify its mirror of this header without touching a GPU. */
-int dln_abi_sizes(int* out5_host);
+/* Host-only: sizeof of the six ABI structs, in the order ChainStep, ChainProgram, ChainArgs, WgradItem,
+ * PackJob, SemOffsets, so a binding can verify its mirror of this header without touching a GPU. */
+int dln_abi_sizes(int* out6_host);
 
 #ifdef __cplusplus
 }

@@ -11,7 +11,8 @@ torch.rand / torch.randn for the duration of each reference call, and
   2. writes small input/output fixtures to tests/golden/*.npz so the check can
      be repeated where /root/reference does not exist.
 
-Usage:  python oracle/make_golden.py            (re-writes tests/golden/)
+Usage:  python oracle/make_golden.py                    (re-writes tests/golden/)
+        python oracle/make_golden.py --only-semantic    (re-writes tests/golden/semantic.npz only)
 """
 from __future__ import annotations
 
@@ -125,10 +126,117 @@ def np_(t):
 
 
 # --------------------------------------------------------------------------- #
+def semantic_section(H, R, out_dir):
+    """Semantic head (run_nerf_helpers.py:107-111, :126-127, :586-593; run_nerf.py:1541-1548): module forward +
+    gradients, raw2outputs(semantic_loss=True), and a full render + RGB / depth / cross-entropy loss + backward."""
+    print("semantic head")
+    g = torch.Generator().manual_seed(77)
+    K, Wn = 19, 64
+    fix = {}
+    spec = O.MLPSpec(D=8, W=Wn, semantic_num_classes=K)
+    params = O.init_params(spec, seed=31)
+    net = H.NeRF(D=8, W=Wn, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True,
+                 semantic_num_classes=K)
+    sd = net.state_dict()
+    assert list(sd.keys()) == list(params.keys()), (list(sd.keys()), list(params.keys()))     # registration ORDER too
+    net.load_state_dict(params)
+    xin = torch.randn(96, 90, generator=g)
+    y_ref = net(xin)
+    assert y_ref.shape[-1] == 4 + K
+    close(O.mlp_forward(params, xin, spec), y_ref, 2e-6, "semantic mlp fwd")
+    cot = torch.randn(y_ref.shape, generator=g)
+    net.zero_grad()
+    (y_ref * cot).sum().backward()
+    pl = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    (O.mlp_forward(pl, xin, spec) * cot).sum().backward()
+    for k, v in net.named_parameters():
+        close(pl[k].grad, v.grad, 2e-5, "  grad " + k)
+        fix["mlp_g_" + k] = np_(v.grad)
+    fix.update(mlp_x=np_(xin), mlp_y=np_(y_ref), mlp_cot=np_(cot))
+    for k, v in params.items():
+        fix["mlp_p_" + k] = np_(v)
+
+    N, S = 24, 64
+    raw = torch.randn(N, S, 4 + K, generator=g)
+    z = torch.sort(torch.rand(N, S, generator=g), dim=-1)[0]
+    rd = torch.randn(N, 3, generator=g)
+    ref = H.raw2outputs(raw, z, rd, raw_noise_std=0.0, semantic_loss=True)
+    mine = O.raw2outputs(raw, z, rd, None, False, semantic_loss=True)
+    assert len(ref) == 6 and len(mine) == 6
+    close(mine[5], ref[5], 1e-5, "raw2outputs semantic_class_preds")
+    close(mine[0], ref[0], 1e-6, "raw2outputs rgb (4+K channels)")
+    fix.update(r2o_raw=np_(raw), r2o_z=np_(z), r2o_rays_d=np_(rd), r2o_sem=np_(ref[5]), r2o_rgb=np_(ref[0]),
+               r2o_depth=np_(ref[4]))
+
+    if R is not None:
+        Hh, Ww, focal = 94, 352, 138.14
+        n_rgb, n_dep = 12, 8
+        ro, rdw = O.synth_rays(n_rgb + n_dep, seed=6, H=Hh, W=Ww, focal=focal)
+        spec_c = O.MLPSpec(D=4, W=Wn, semantic_num_classes=K)
+        spec_f = O.MLPSpec(D=8, W=Wn, semantic_num_classes=K)
+        pc, pf = O.trained_like(O.init_params(spec_c, 201), 1.0), O.trained_like(O.init_params(spec_f, 202))
+        mk = lambda D: H.NeRF(D=D, W=Wn, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True,
+                              semantic_num_classes=K)
+        net_c, net_f = mk(4), mk(8)
+        net_c.load_state_dict(pc)
+        net_f.load_state_dict(pf)
+        e_p, _ = H.get_embedder(10, 0)
+        e_d, _ = H.get_embedder(4, 0)
+        R.device = torch.device("cpu")
+        qfn = lambda inputs, viewdirs, network_fn: R.run_network(inputs, viewdirs, network_fn, embed_fn=e_p,
+                                                                embeddirs_fn=e_d, netchunk=4096)
+        rng = O.synth_rng(n_rgb + n_dep, 64, 64, seed=19)
+        tgt, dep = O.synth_targets(n_rgb, n_dep, seed=19)
+        tsem = torch.randint(0, K, (n_rgb,), generator=g)
+        with rng_fifo([("rand", rng.t_rand), ("randn", rng.noise0), ("rand", rng.u), ("randn", rng.noise1)]):
+            rgb, disp, acc, depth, extras = R.render(
+                Hh, Ww, focal, chunk=4096, rays=torch.stack([ro, rdw], 0), retraw=True, near=0.0, far=1.0,
+                network_query_fn=qfn, perturb=1.0, N_importance=64, network_fine=net_f, N_samples=64,
+                network_fn=net_c, use_viewdirs=True, white_bkgd=False, raw_noise_std=1.0, ndc=True, semantic_loss=True)
+        F = torch.nn.functional
+        lam = 0.01
+        loss_ref = H.img2mse(rgb[:n_rgb], tgt) + 0.01 * 0.5 * H.img2mse(depth[n_rgb:], dep) \
+            + lam * (F.cross_entropy(extras["sem_preds"][:n_rgb], tsem) + F.cross_entropy(extras["sem_preds0"][:n_rgb], tsem)) \
+            + H.img2mse(extras["rgb0"][:n_rgb], tgt)                 # run_nerf.py:1536, :1541-1548, :1759-1761
+        net_c.zero_grad(); net_f.zero_grad()
+        loss_ref.backward()
+
+        rb = O.pack_rays(Hh, Ww, focal, ro, rdw, ndc=True, near=0.0, far=1.0, use_viewdirs=True)
+        pcg = {k: v.clone().requires_grad_(True) for k, v in pc.items()}
+        pfg = {k: v.clone().requires_grad_(True) for k, v in pf.items()}
+        om = O.render_rays(rb, pcg, spec_c, pfg, spec_f, 64, 64, rng, raw_noise_std=1.0, semantic_loss=True)
+        lm = O.train_loss(om, n_rgb, tgt, dep, depth_lambda=0.01, depth_importance=0.5, target_semantic=tsem,
+                          semantic_lambda=lam)
+        lm["loss"].backward()
+        close(om["rgb_map"], rgb, 2e-6, "semantic render rgb_map")
+        close(om["sem_preds"], extras["sem_preds"], 2e-5, "semantic render sem_preds")
+        close(om["sem_preds0"], extras["sem_preds0"], 2e-5, "semantic render sem_preds0")
+        close(om["raw"], extras["raw"], 1e-5, "semantic render raw")
+        close(lm["loss"], loss_ref, 1e-6, "semantic loss")
+        for k, v in net_f.named_parameters():
+            close(pfg[k].grad, v.grad, 1e-5, "  fine grad " + k)
+        for k, v in net_c.named_parameters():
+            close(pcg[k].grad, v.grad, 1e-5, "  coarse grad " + k)
+        fix.update(rays_o=np_(ro), rays_d=np_(rdw), tgt=np_(tgt), dep=np_(dep), tsem=np_(tsem), t_rand=np_(rng.t_rand),
+                   noise0=np_(rng.noise0), u=np_(rng.u), noise1=np_(rng.noise1), rgb=np_(rgb), depth=np_(depth),
+                   sem_preds=np_(extras["sem_preds"]), sem_preds0=np_(extras["sem_preds0"]),
+                   rgb0=np_(extras["rgb0"]), loss=np_(loss_ref.detach()),
+                   g_fine_sem1=np_(net_f.semantic_linear[1].weight.grad),
+                   g_fine_sem0=np_(net_f.semantic_linear[0].weight.grad),
+                   g_fine_feature_b=np_(net_f.feature_linear.bias.grad),
+                   g_fine_l7=np_(net_f.pts_linears[7].weight.grad),
+                   g_coarse_sem1_b=np_(net_c.semantic_linear[1].bias.grad),
+                   g_coarse_l0=np_(net_c.pts_linears[0].weight.grad))
+    np.savez_compressed(os.path.join(out_dir, "semantic.npz"), **fix)
+
+
 def main():
     H, R = import_reference()
     out_dir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
+    if "--only-semantic" in sys.argv:
+        semantic_section(H, R, out_dir)
+        return
     torch.manual_seed(3407)
     g = torch.Generator().manual_seed(3407)
 
@@ -342,6 +450,7 @@ def main():
                     i += 1
     cases["n"] = np.array([i])
     np.savez_compressed(os.path.join(out_dir, "searchsorted.npz"), **cases)
+    semantic_section(H, R, out_dir)
     print("golden vectors written to", out_dir)
 
 

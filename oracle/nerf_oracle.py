@@ -61,6 +61,7 @@ class MLPSpec:
     output_ch: int = 5
     skips: Sequence[int] = (4,)
     use_viewdirs: bool = True
+    semantic_num_classes: int = 0      # K > 0: semantic_linear = Linear(W, W/2) -> Linear(W/2, K)  (:107-111)
 
     def param_shapes(self) -> Dict[str, tuple]:
         """Parameter names/shapes exactly as the reference's state_dict
@@ -87,6 +88,11 @@ class MLPSpec:
         else:
             shp["output_linear.weight"] = (self.output_ch, self.W)
             shp["output_linear.bias"] = (self.output_ch,)
+        if self.semantic_num_classes:
+            shp["semantic_linear.0.weight"] = (self.W // 2, self.W)
+            shp["semantic_linear.0.bias"] = (self.W // 2,)
+            shp["semantic_linear.1.weight"] = (self.semantic_num_classes, self.W // 2)
+            shp["semantic_linear.1.bias"] = (self.semantic_num_classes,)
         return shp
 
 
@@ -126,7 +132,12 @@ def mlp_forward(p: Dict[str, Tensor], x: Tensor, spec: MLPSpec) -> Tensor:
     hv = torch.cat([feat, x_dir], dim=-1)
     hv = torch.relu(hv @ p["views_linears.0.weight"].T + p["views_linears.0.bias"])
     rgb = hv @ p["rgb_linear.weight"].T + p["rgb_linear.bias"]
-    return torch.cat([rgb, sigma], dim=-1)
+    out = torch.cat([rgb, sigma], dim=-1)
+    if spec.semantic_num_classes:
+        sem = feat @ p["semantic_linear.0.weight"].T + p["semantic_linear.0.bias"]
+        sem = sem @ p["semantic_linear.1.weight"].T + p["semantic_linear.1.bias"]
+        out = torch.cat([out, sem], dim=-1)
+    return out
 
 
 def run_network(pts: Tensor, viewdirs: Optional[Tensor], p: Dict[str, Tensor], spec: MLPSpec,
@@ -147,8 +158,8 @@ def run_network(pts: Tensor, viewdirs: Optional[Tensor], p: Dict[str, Tensor], s
 # R8  alpha compositing              run_nerf_helpers.py:542-595
 # --------------------------------------------------------------------------- #
 def raw2outputs(raw: Tensor, z_vals: Tensor, rays_d: Tensor, noise: Optional[Tensor] = None,
-                white_bkgd: bool = False):
-    """Returns (rgb_map, disp_map, acc_map, weights, depth_map).
+                white_bkgd: bool = False, semantic_loss: bool = False):
+    """Returns (rgb_map, disp_map, acc_map, weights, depth_map[, semantic_class_preds]).
 
     ``noise`` is the ALREADY SCALED density noise (randn * raw_noise_std,
     run_nerf_helpers.py:563-565) or None.
@@ -157,7 +168,8 @@ def raw2outputs(raw: Tensor, z_vals: Tensor, rays_d: Tensor, noise: Optional[Ten
     * alpha = 1 - exp(-relu(raw[..., 3] + noise) * dist)          (:555, :573)
     * weights = alpha * exclusive_cumprod(1 - alpha + 1e-10)      (:575)
     * rgb/depth/acc sums, disp = 1 / max(1e-10, depth / acc)      (:576-580)
-    * optional white background                                   (:582-583)"""
+    * optional white background                                   (:582-583)
+    * semantic_loss: per-ray logits = UNWEIGHTED sum of raw[..., 4:] over the samples (:586-593)"""
     dt = raw.dtype
     delta = z_vals[..., 1:] - z_vals[..., :-1]
     delta = torch.cat([delta, torch.full_like(delta[..., :1], 1e10)], dim=-1)
@@ -174,6 +186,8 @@ def raw2outputs(raw: Tensor, z_vals: Tensor, rays_d: Tensor, noise: Optional[Ten
     disp_map = 1.0 / torch.maximum(torch.full_like(depth_map, 1e-10), depth_map / acc_map)
     if white_bkgd:
         rgb_map = rgb_map + (1.0 - acc_map[..., None])
+    if semantic_loss:
+        return rgb_map.to(dt), disp_map, acc_map, weights, depth_map, torch.sum(raw[..., 4:], dim=-2)
     return rgb_map.to(dt), disp_map, acc_map, weights, depth_map
 
 
@@ -284,9 +298,10 @@ def stratified_z(near: Tensor, far: Tensor, n_samples: int, t_rand: Optional[Ten
 def render_rays(ray_batch: Tensor, p_coarse, spec_coarse: MLPSpec, p_fine, spec_fine: MLPSpec,
                 N_samples: int, N_importance: int, rng: RenderRNG, raw_noise_std: float = 0.0,
                 white_bkgd: bool = False, lindisp: bool = False, L_pts: int = 10, L_dir: int = 4,
-                retraw: bool = True, mlp_fn=None) -> Dict[str, Tensor]:
+                retraw: bool = True, mlp_fn=None, semantic_loss: bool = False) -> Dict[str, Tensor]:
     """run_nerf.py:520-675 (the network_fn-is-not-None / no alpha_model /
-    no sigma_loss / no semantic branch, i.e. what every shipped config runs)."""
+    no sigma_loss branch, i.e. what every shipped config runs).  semantic_loss adds
+    sem_preds / sem_preds0 (:601-603, :629-630, :643-644, :652-653, :662-663)."""
     o, d = ray_batch[:, 0:3], ray_batch[:, 3:6]
     vdir = ray_batch[:, -3:] if ray_batch.shape[-1] > 9 else None          # :567
     near, far = ray_batch[:, 6:7], ray_batch[:, 7:8]
@@ -294,10 +309,10 @@ def render_rays(ray_batch: Tensor, p_coarse, spec_coarse: MLPSpec, p_fine, spec_
     pts = o[:, None, :] + d[:, None, :] * z[:, :, None]                    # :595
     raw = run_network(pts, vdir, p_coarse, spec_coarse, L_pts, L_dir, mlp_fn)
     n0 = None if rng.noise0 is None else rng.noise0 * raw_noise_std
-    rgb, disp, acc, w, depth = raw2outputs(raw, z, d, n0, white_bkgd)
+    rgb, disp, acc, w, depth, *sem = raw2outputs(raw, z, d, n0, white_bkgd, semantic_loss)
     out: Dict[str, Tensor] = {}
     if N_importance > 0:
-        rgb0, disp0, acc0, depth0 = rgb, disp, acc, depth
+        rgb0, disp0, acc0, depth0, sem0 = rgb, disp, acc, depth, sem
         z_mid = 0.5 * (z[..., 1:] + z[..., :-1])                           # :632
         z_new = sample_pdf(z_mid, w[..., 1:-1], N_importance, det=(rng.u is None), u=rng.u)
         z_new = z_new.detach()                                             # :634
@@ -306,10 +321,14 @@ def render_rays(ray_batch: Tensor, p_coarse, spec_coarse: MLPSpec, p_fine, spec_
         raw = run_network(pts, vdir, p_fine if p_fine is not None else p_coarse,
                           spec_fine if p_fine is not None else spec_coarse, L_pts, L_dir, mlp_fn)
         n1 = None if rng.noise1 is None else rng.noise1 * raw_noise_std
-        rgb, disp, acc, w, depth = raw2outputs(raw, z, d, n1, white_bkgd)
+        rgb, disp, acc, w, depth, *sem = raw2outputs(raw, z, d, n1, white_bkgd, semantic_loss)
+        if semantic_loss:
+            out["sem_preds0"] = sem0[0]
         out.update(rgb0=rgb0, disp0=disp0, acc0=acc0, depth_map0=depth0,
                    z_std=torch.std(z_new, dim=-1, unbiased=False))         # :659
     out.update(rgb_map=rgb, disp_map=disp, acc_map=acc, depth_map=depth)
+    if semantic_loss:
+        out["sem_preds"] = sem[0]
     out["weights"] = w          # not returned by the reference; kept for kernel checks
     out["z_vals"] = z
     if retraw:
@@ -355,13 +374,15 @@ def inverse_depth_smoothness(idepth: Tensor, image: Tensor) -> Tensor:
 # --------------------------------------------------------------------------- #
 def train_loss(out: Dict[str, Tensor], n_rgb: int, target_rgb: Tensor, target_depth: Optional[Tensor],
                depth_lambda: float = 0.0, depth_importance: float = 1.0,
-               ray_weights: Optional[Tensor] = None, mode: str = "mse") -> Dict[str, Tensor]:
+               ray_weights: Optional[Tensor] = None, mode: str = "mse",
+               target_semantic: Optional[Tensor] = None, semantic_lambda: float = 0.0) -> Dict[str, Tensor]:
     """RGB rays come first, depth rays after them (:1409-1411).  Colour losses use
     the RGB rays only (:1455-1462, :1500, :1759-1761); the depth loss supervises
     the FINE depth of the depth rays only (:1461, :1503-1524).
 
     mode: "mse" (:1524), "weighted" (:1517), "weighted_norm" (:1520),
-    "relative" (:1522)."""
+    "relative" (:1522).  target_semantic (class index per RGB ray): cross-entropy of
+    the fine and coarse per-ray logits of the RGB rays, times semantic_lambda (:1458-1460, :1541-1548)."""
     rgb = out["rgb_map"][:n_rgb]
     img = torch.mean((rgb - target_rgb) ** 2)
     res = {"img_loss": img}
@@ -378,6 +399,11 @@ def train_loss(out: Dict[str, Tensor], n_rgb: int, target_rgb: Tensor, target_de
             dl = torch.mean((dcol - target_depth) ** 2)
         res["depth_loss"] = dl
         loss = loss + depth_lambda * depth_importance * dl
+    if target_semantic is not None:
+        sl = torch.nn.functional.cross_entropy(out["sem_preds"][:n_rgb], target_semantic)
+        sl0 = torch.nn.functional.cross_entropy(out["sem_preds0"][:n_rgb], target_semantic) if "sem_preds0" in out else 0.0
+        res["semantic_loss"], res["semantic_loss0"] = sl, sl0
+        loss = loss + semantic_lambda * (sl + sl0)
     if "rgb0" in out:
         img0 = torch.mean((out["rgb0"][:n_rgb] - target_rgb) ** 2)
         res["img_loss0"] = img0

@@ -36,11 +36,11 @@ def test_header_symbols_are_exported_and_bound(lib):
 
 
 def test_struct_mirrors_match_the_c_structs(lib):
-    out = (C.c_int * 5)()
+    out = (C.c_int * 6)()
     assert lib.dln_abi_sizes(out) == 0
     L = dn._lib
     assert list(out) == [C.sizeof(L.ChainStep), C.sizeof(L.ChainProgram), C.sizeof(L.ChainArgs),
-                         C.sizeof(L.WgradItem), C.sizeof(L.PackJob)]
+                         C.sizeof(L.WgradItem), C.sizeof(L.PackJob), C.sizeof(L.SemOffsets)]
 
 
 def test_invalid_arguments_return_minus_one_without_touching_the_gpu(lib):
@@ -135,5 +135,5 @@ def test_plan_rejects_what_the_kernels_cannot_do():
         plan_mod.build_plan(plan_mod.NetShape(D=8, W=128, input_ch=63, input_ch_views=27))
     with pytest.raises(ValueError):
         plan_mod.build_plan(plan_mod.NetShape(D=5, input_ch=63, input_ch_views=27))   # skip after last layer
-    with pytest.raises(NotImplementedError):
-        dn.NeRF(D=8, W=256, input_ch=63, input_ch_views=27, use_viewdirs=True, semantic_num_classes=19)
+    with pytest.raises(NotImplementedError):     # the semantic kernels hold one class per register / lane: K <= 32
+        dn.NeRF(D=8, W=256, input_ch=63, input_ch_views=27, use_viewdirs=True, semantic_num_classes=33)._state()
