@@ -32,6 +32,7 @@ if ROOT not in sys.path:
 H, W, FOCAL = 378, 504, 407.6
 N_SAMPLES, N_IMPORTANCE = 64, 64
 COARSE_D, FINE_D = 4, 8
+SEMANTIC_LAMBDA = 0.01      # configs/fern_dsnerf.txt:56
 DEPTH_LAMBDA = 0.01
 
 # algorithmic (unpadded) MACs per point, SURVEY.md §8(d)
@@ -234,18 +235,26 @@ def run_ours(args):
     torch.manual_seed(3407 + rank)
 
     torch.manual_seed(3407)              # identical random-init weights (nn.Linear default) on every rank
-    net_c = dn.NeRF(D=COARSE_D, W=256, input_ch=63, input_ch_views=27, use_viewdirs=True).to(dev)
-    net_f = dn.NeRF(D=FINE_D, W=256, input_ch=63, input_ch_views=27, use_viewdirs=True).to(dev)
+    semK = int(args.semantic)           # > 0: fern_dsnerf.txt:55-56 (semantic_loss = True, semantic_lambda = 0.01)
+    net_c = dn.NeRF(D=COARSE_D, W=256, input_ch=63, input_ch_views=27, use_viewdirs=True,
+                    semantic_num_classes=semK or None).to(dev)
+    net_f = dn.NeRF(D=FINE_D, W=256, input_ch=63, input_ch_views=27, use_viewdirs=True,
+                    semantic_num_classes=semK or None).to(dev)
     torch.manual_seed(3407 + rank)
     params = list(net_c.parameters()) + list(net_f.parameters())
     q = dn.FusedQuery(dn.get_embedder(10, 0)[0], dn.get_embedder(4, 0)[0], 65536, 10, 4, 0)
     kw = dict(network_query_fn=q, perturb=1.0, N_importance=N_IMPORTANCE, network_fine=net_f, N_samples=N_SAMPLES,
-              network_fn=net_c, use_viewdirs=True, white_bkgd=False, raw_noise_std=1.0, ndc=True, near=0., far=1.)
+              network_fn=net_c, use_viewdirs=True, white_bkgd=False, raw_noise_std=1.0, ndc=True, near=0., far=1.,
+              semantic_loss=bool(semK))
 
     ro, rd, tgt, dep, n_rgb, n_dep = make_batch(args.n_rand, 3407 + rank)
     host_rays = torch.stack([ro, rd], 0).pin_memory()
     host_tgt, host_dep = tgt.pin_memory(), dep.pin_memory()
     d_rays, d_tgt, d_dep = host_rays.to(dev), host_tgt.to(dev), host_dep.to(dev)
+    # class index per RGB ray (run_nerf.py:1331-1332); device-resident in every route, 8 B/ray next to the 36 B/ray of rays
+    d_sem = (torch.randint(0, semK, (n_rgb,), generator=torch.Generator().manual_seed(3407 + rank)).to(dev)
+             if semK else None)
+    sem_kw = dict(target_semantic=d_sem, semantic_lambda=SEMANTIC_LAMBDA) if semK else {}
 
     def allreduce_grads():
         dn.allreduce_gradients(params, world)
@@ -257,6 +266,9 @@ def run_ours(args):
             p.grad = None
         loss = dn.img2mse(rgb[:n_rgb], t_rgb) + DEPTH_LAMBDA * dn.img2mse(depth[n_rgb:], t_dep) \
             + dn.img2mse(extras["rgb0"][:n_rgb], t_rgb)
+        if semK:                                                  # run_nerf.py:1541-1548
+            ce = torch.nn.functional.cross_entropy
+            loss = loss + SEMANTIC_LAMBDA * (ce(extras["sem_preds"][:n_rgb], d_sem) + ce(extras["sem_preds0"][:n_rgb], d_sem))
         loss.backward()
         allreduce_grads()
         return loss
@@ -265,18 +277,19 @@ def run_ours(args):
         """Same step through dlnerf_b200.train_step: loss gradient fused into the compositing backward kernel."""
         out = dn.train_step(H, W, FOCAL, rays, t_rgb, t_dep, n_rgb, net_c, net_f, N_samples=N_SAMPLES,
                             N_importance=N_IMPORTANCE, perturb=1., raw_noise_std=1., depth_lambda=DEPTH_LAMBDA,
-                            depth_importance=1., world_size=world, overlap_coarse_backward=overlap)
+                            depth_importance=1., world_size=world, overlap_coarse_backward=overlap, **sem_kw)
         return out["loss"]
 
     graphed = None
     if args.path == "graph":
         graphed = dn.GraphedTrainStep(H, W, FOCAL, args.n_rand, n_rgb, net_c, net_f, world_size=world,
                                       N_samples=N_SAMPLES, N_importance=N_IMPORTANCE, perturb=1., raw_noise_std=1.,
-                                      depth_lambda=DEPTH_LAMBDA, depth_importance=1.)
+                                      depth_lambda=DEPTH_LAMBDA, depth_importance=1.,
+                                      **({"semantic_lambda": SEMANTIC_LAMBDA} if semK else {}))
 
     def graph_step(rays, t_rgb, t_dep):
         """train_step replayed from a CUDA graph (one launch per step; weight re-pack included in the graph)."""
-        return graphed(rays, t_rgb, t_dep)["loss"]
+        return graphed(rays, t_rgb, t_dep, target_semantic=d_sem)["loss"]
 
     dev_step = {"dropin": step, "fused": fused_step, "graph": graph_step}[args.path]
 
@@ -394,7 +407,7 @@ def run_ours(args):
         # same host-buffer protocol through the CUDA-graph step (pinned host tensors are copied straight into the
         # graph's static inputs, loss read back with .item())
         def e2e_graph_step():
-            return float(graphed(host_rays, host_tgt, host_dep)["loss"].item())
+            return float(graphed(host_rays, host_tgt, host_dep, target_semantic=d_sem)["loss"].item())
         for _ in range(3):
             e2e_graph_step()
         ms_g = timed(e2e_graph_step, args.steps)
@@ -409,7 +422,10 @@ def run_ours(args):
             "metric": "training rays/sec (fwd+bwd)", "value": value, "unit": "rays/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": dict(workload_config(args, world), value_route={"graph": "dlnerf_b200.GraphedTrainStep (CUDA graph of train_step)", "fused": "dlnerf_b200.train_step", "dropin": "render()+loss.backward()"}[args.path]), "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches,
+            "config": dict(workload_config(args, world), semantic_head=(
+                "off (headline workload: RGB + LiDAR-depth loss)" if not semK else
+                "on: %d classes, cross-entropy of fine + coarse per-ray logits, lambda %g (fern_dsnerf.txt:55-56)" % (semK, SEMANTIC_LAMBDA)),
+                value_route={"graph": "dlnerf_b200.GraphedTrainStep (CUDA graph of train_step)", "fused": "dlnerf_b200.train_step", "dropin": "render()+loss.backward()"}[args.path]), "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches,
             "roofline": roofline, "cpu_baseline": cb, "kernels": kern, "kernel_times_from": kernel_times_from}))
     if world > 1:
         dist.destroy_process_group()
@@ -423,6 +439,9 @@ def main():
     ap.add_argument("--n-rand", type=int, default=4096, help="rays per step per GPU (config B: 4096)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--semantic", type=int, default=0,
+                    help="classes of the semantic head (fern_dsnerf.txt:55 turns it on with the KITTI-360 label set, 19); "
+                         "0 = the headline workload (RGB + depth loss)")
     ap.add_argument("--path", default="graph", choices=["graph", "fused", "dropin"],
                     help="route of the device-resident `value`: CUDA-graph replay of train_step, train_step (fused "
                          "loss), or render()+loss.backward(); `e2e` always uses the drop-in route")

@@ -571,7 +571,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       const bool valid = p < args.P;
       float dsig = 0.f;
       const float* const semrow =
-          (kBwd && kSem) ? args.sem_g + (size_t)((valid ? p : args.P - 1) / args.sem_g_div) * 256 : nullptr;
+          (kBwd && kSem && valid) ? args.sem_g + (size_t)(p / args.sem_g_div) * 256 : nullptr;   // padded rows: dZ = 0
       uint8_t* const gtile = keep ? reinterpret_cast<uint8_t*>(args.stash) + (size_t)tile * prog.stash_slots * kSlab : nullptr;
       auto gslot = [&](int slot) -> uint8_t* { return (kDirectStash && keep) ? gtile + (size_t)slot * kSlab : nullptr; };
       // ------------------------------------------------------------------ prologue

@@ -212,19 +212,22 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
         return (torch.rand if kind == "u" else torch.randn)(shape, device=dev)
 
     def query(net, z):
-        """(raw, per-ray semantic logits | None).  Fused route: the logits come from the kept activations of the
-        last trunk layer (one sum per ray, csrc/semantic_kernels.cu) and raw carries its semantic columns only when
-        the caller asked for raw; generic route: raw[N, S, 4+K] from the query function, summed over the samples."""
+        """(raw for compositing, per-ray semantic logits | None, raw as the reference returns it).  Fused route: the
+        logits come from the kept activations of the last trunk layer (one sum per ray, csrc/semantic_kernels.cu);
+        compositing runs on the 4-channel raw and the per-sample logits are appended only to the returned copy.
+        Generic route: raw[N, S, 4+K] from the query function, summed over the samples (helpers:589)."""
         if isinstance(network_query_fn, FusedQuery) and network_query_fn.fused_ok(net, rb):
             K = net.sem_K
             if semantic_loss and not K:
                 raise RuntimeError("semantic_loss=True needs networks built with semantic_num_classes")
-            if semantic_loss:
-                return net.forward_rays(rb, z, semantic=True, point_logits=bool(retraw))
-            return net.forward_rays(rb, z, point_logits=bool(retraw and K)), None
+            if not (semantic_loss or (retraw and K)):
+                raw = net.forward_rays(rb, z)
+                return raw, None, raw
+            raw, sem, pts = net.forward_rays(rb, z, semantic=bool(semantic_loss), point_logits=bool(retraw))
+            return raw, sem, (torch.cat([raw, pts], -1) if retraw else raw)
         pts = rays_o[..., None, :] + rays_d[..., None, :] * z[..., :, None]
         raw = network_query_fn(pts, viewdirs, net)
-        return raw, (ops.sample_sum(raw, 4) if semantic_loss else None)          # helpers:589
+        return raw, (ops.sample_sum(raw, 4) if semantic_loss else None), raw
 
     def composite(raw, z, noise_name):
         noise = draw(noise_name, "n", (N, z.shape[1])) if raw_noise_std > 0. else None
@@ -232,7 +235,7 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
 
     t_rand = draw("t_rand", "u", (N, N_samples)) if perturb > 0. else None
     z_vals = ops.stratified_z(rb, N_samples, t_rand, lindisp)
-    raw, sem = query(network_fn, z_vals)
+    raw, sem, raw_ret = query(network_fn, z_vals)
     rgb_map, disp_map, acc_map, weights, depth_map = composite(raw, z_vals, "noise0")
 
     ret = {}
@@ -241,11 +244,11 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
         u = draw("u", "u", (N, N_importance)) if perturb != 0. else None        # det = (perturb == 0)
         z_samples, z_vals = ops.importance_resample(z_vals, weights.detach(), N_importance, u)
         run_fn = network_fn if network_fine is None else network_fine
-        raw, sem = query(run_fn, z_vals)
+        raw, sem, raw_ret = query(run_fn, z_vals)
         rgb_map, disp_map, acc_map, weights, depth_map = composite(raw, z_vals, "noise1")
     ret.update(rgb_map=rgb_map, disp_map=disp_map, acc_map=acc_map, depth_map=depth_map)
     if retraw:
-        ret['raw'] = raw
+        ret['raw'] = raw_ret
     if semantic_loss:
         ret['sem_preds'] = sem                                                     # :652-653
     if N_importance > 0:

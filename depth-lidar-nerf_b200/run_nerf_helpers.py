@@ -342,9 +342,9 @@ class NeRF(nn.Module):
         encoded (positions per sample, the unit view direction once per ray) and pushed through the MLP
         inside one kernel.  ray_batch is the packed [N, 8|11] batch of render(); returns raw[N, S, 4].
 
-        With the semantic head: ``semantic=True`` returns (raw, sem_preds[N, K]) -- the per-ray logits of
-        raw2outputs (helpers:589: the UNWEIGHTED sum of the per-sample logits), differentiable; ``point_logits``
-        appends the per-sample logits to raw ([N, S, 4+K] like the reference's), as values only."""
+        With the semantic head, ``semantic`` / ``point_logits`` make it return (raw[N, S, 4], sem_preds[N, K] | None,
+        logits[N, S, K] | None): the per-ray logits of raw2outputs (helpers:589: the UNWEIGHTED sum of the per-sample
+        logits; differentiable) and the per-sample logits that fill raw[..., 4:] in the reference (values only)."""
         rb, z = ops._f32(ray_batch, "forward_rays"), ops._f32(z_vals, "forward_rays")
         if self.use_viewdirs and rb.shape[1] < 11:
             raise RuntimeError("use_viewdirs=True needs the unit view direction in the last 3 ray columns")
@@ -354,10 +354,8 @@ class NeRF(nn.Module):
         if semantic or point_logits:
             out, sem, pts = _MLPSem.apply(self, "rays", rb, z, N * S, S if semantic else 0, bool(point_logits),
                                           *self._ordered_params())
-            raw = out.reshape(N, S, 4)
-            if point_logits:
-                raw = torch.cat([raw, pts.reshape(N, S, -1)], -1)
-            return (raw, sem) if semantic else raw
+            return (out.reshape(N, S, 4), sem if semantic else None,
+                    pts.reshape(N, S, -1) if point_logits else None)
         out = _MLP.apply(self, "rays", rb, z, N * S, *self._ordered_params())
         return out.reshape(N, S, out.shape[-1])
 

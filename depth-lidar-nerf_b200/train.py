@@ -39,15 +39,18 @@ def shard_bounds(n: int, rank: int, world: int):
 
 
 def shard_ray_batch(batch_rays: Tensor, target_s: Tensor, target_depth: Optional[Tensor], n_rgb: int, rank: int,
-                    world: int, ray_weights: Optional[Tensor] = None):
+                    world: int, ray_weights: Optional[Tensor] = None, target_semantic: Optional[Tensor] = None):
     """Slice the step's batch [2, n_rgb + n_depth, 3] (RGB rays first, run_nerf.py:1409-1411) for one rank,
-    per ray class.  Returns (rays, target_s, target_depth, ray_weights, n_rgb_local)."""
+    per ray class.  Returns (rays, target_s, target_depth, ray_weights, n_rgb_local); with ``target_semantic`` (one
+    class index per RGB ray, run_nerf.py:1331-1332) its slice is appended as a sixth entry."""
     n = batch_rays.shape[1]
     a0, a1 = shard_bounds(n_rgb, rank, world)
     b0, b1 = shard_bounds(n - n_rgb, rank, world)
     rays = torch.cat([batch_rays[:, a0:a1], batch_rays[:, n_rgb + b0:n_rgb + b1]], dim=1)
     td = None if target_depth is None else target_depth[b0:b1]
     rw = None if ray_weights is None else ray_weights[b0:b1]
+    if target_semantic is not None:
+        return rays, target_s[a0:a1], td, rw, a1 - a0, target_semantic[a0:a1]
     return rays, target_s[a0:a1], td, rw, a1 - a0
 
 

@@ -146,7 +146,16 @@ def mlp_forward_emulated(params, x, spec: O.MLPSpec):
     b2 = Wv[:, :W] @ params["feature_linear.bias"] + params["views_linears.0.bias"]
     hv32 = torch.relu(h_q @ _ste(M).T + xd_q @ _ste(Wv[:, W:]).T + b2)
     rgb = hv32 @ params["rgb_linear.weight"].T + params["rgb_linear.bias"]
-    return torch.cat([rgb, sigma], -1)
+    out = torch.cat([rgb, sigma], -1)
+    if spec.semantic_num_classes:
+        # semantic head (csrc/semantic_kernels.cu): fp32 folded operands Sw = W_s2 W_s1 W_f, sc applied to the bf16
+        # activations the chain keeps for wgrad
+        A = params["semantic_linear.0.weight"] @ params["feature_linear.weight"]
+        a = params["semantic_linear.0.weight"] @ params["feature_linear.bias"] + params["semantic_linear.0.bias"]
+        Sw = params["semantic_linear.1.weight"] @ A
+        sc = params["semantic_linear.1.weight"] @ a + params["semantic_linear.1.bias"]
+        out = torch.cat([out, h_q @ Sw.T + sc], -1)
+    return out
 
 
 def compare_grads(named_got, ref_emul, ref_fp32, tag=""):
@@ -170,13 +179,13 @@ def compare_grads(named_got, ref_emul, ref_fp32, tag=""):
     return stats
 
 
-def make_net(D, use_viewdirs=True, seed=0, device="cuda", sigma_bias=0.0, input_ch_views=27):
+def make_net(D, use_viewdirs=True, seed=0, device="cuda", sigma_bias=0.0, input_ch_views=27, semantic=0):
     """(package NeRF on device, oracle params dict on CPU, MLPSpec) with identical parameters."""
-    spec = O.MLPSpec(D=D, use_viewdirs=use_viewdirs, input_ch_views=input_ch_views)
+    spec = O.MLPSpec(D=D, use_viewdirs=use_viewdirs, input_ch_views=input_ch_views, semantic_num_classes=semantic)
     p = O.init_params(spec, seed=3407 + D + seed)
     if sigma_bias and use_viewdirs:
         p = O.trained_like(p, sigma_bias)
     net = dn().NeRF(D=D, W=256, input_ch=63, input_ch_views=input_ch_views, output_ch=5, skips=[4],
-                    use_viewdirs=use_viewdirs)
+                    use_viewdirs=use_viewdirs, semantic_num_classes=semantic or None)
     net.load_state_dict(p)
     return net.to(device), p, spec

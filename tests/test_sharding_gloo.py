@@ -88,3 +88,8 @@ def test_shard_keeps_class_order():
         seen_rgb.append(r[:, :n_loc])
         seen_dep.append(r[:, n_loc:])
     assert torch.equal(torch.cat(seen_rgb, 1), rays[:, :10]) and torch.equal(torch.cat(seen_dep, 1), rays[:, 10:])
+    # semantic targets (one class index per RGB ray) follow the RGB slice
+    tsem = torch.arange(10)
+    parts = [dn.shard_ray_batch(rays, tgt, dep, 10, rank, 4, target_semantic=tsem) for rank in range(4)]
+    assert all(len(p) == 6 and p[5].shape[0] == p[4] for p in parts)
+    assert torch.equal(torch.cat([p[5] for p in parts]), tsem)
