@@ -3,11 +3,13 @@
 
     colour target  = 0.5 + 0.5 * unit view direction      (a view-dependent "sky")
     depth  target  = 0.7 in NDC for the depth rays         (a fronto-parallel wall)
+    class  target  = quadrant of the view direction        (--semantic: 4 classes, cross-entropy on sem_preds / sem_preds0
+                                                            with semantic_lambda = 0.01, fern_dsnerf.txt:55-56)
 
 It uses the optional swaps of INTEGRATION.md: DeviceRayLoader for RayDataset + DataLoader, FlatAdam for
 torch.optim.Adam, GraphedTrainStep for render + loss + backward.  Prints loss / PSNR every 50 iterations.
 
-    python examples/train_synthetic.py [--iters 300] [--n-rand 1024] [--drop-in]
+    python examples/train_synthetic.py [--iters 300] [--n-rand 1024] [--drop-in] [--semantic]
 """
 import argparse
 import os
@@ -43,11 +45,13 @@ def main(argv=None):
     ap.add_argument("--n-rand", type=int, default=1024)
     ap.add_argument("--lrate", type=float, default=5e-4)
     ap.add_argument("--drop-in", action="store_true", help="render() + img2mse + loss.backward() instead of the graphed step")
+    ap.add_argument("--semantic", action="store_true", help="networks with a 4-class semantic head + cross-entropy loss")
     args = ap.parse_args(argv)
+    K, slam = (4, 0.01) if args.semantic else (None, 0.)
     dev = torch.device("cuda")
     torch.manual_seed(3407)
-    model = dn.NeRF(D=4, W=256, input_ch=63, input_ch_views=27, use_viewdirs=True).to(dev)
-    model_fine = dn.NeRF(D=8, W=256, input_ch=63, input_ch_views=27, use_viewdirs=True).to(dev)
+    model = dn.NeRF(D=4, W=256, input_ch=63, input_ch_views=27, use_viewdirs=True, semantic_num_classes=K).to(dev)
+    model_fine = dn.NeRF(D=8, W=256, input_ch=63, input_ch_views=27, use_viewdirs=True, semantic_num_classes=K).to(dev)
     optimizer = dn.FlatAdam([model, model_fine], lr=args.lrate, betas=(0.9, 0.999))
     n_rgb = args.n_rand // 2
     n_dep = args.n_rand - n_rgb
@@ -57,6 +61,8 @@ def main(argv=None):
     rgb_it, dep_it = iter(rgb_loader), iter(dep_loader)
     target_depth = torch.full((n_dep,), 0.7, device=dev)
     kw = dict(N_samples=64, N_importance=64, perturb=1., raw_noise_std=1., depth_lambda=0.1, depth_importance=1.)
+    if K:
+        kw["semantic_lambda"] = slam
     step = None if args.drop_in else dn.GraphedTrainStep(H, W, FOCAL, args.n_rand, n_rgb, model, model_fine, **kw)
     q = dn.FusedQuery(dn.get_embedder(10, 0)[0], dn.get_embedder(4, 0)[0], 65536, 10, 4, 0)
     losses = []
@@ -74,18 +80,27 @@ def main(argv=None):
         b_dep, dep_it = nxt(dep_it, dep_loader)
         batch = torch.cat([b_rgb, b_dep], 0).transpose(0, 1)         # [3, N_rand, 3]
         batch_rays, target_s = batch[:2].contiguous(), batch[2, :n_rgb].contiguous()
+        target_sem = None
+        if K:                                   # the loader of run_nerf.py:1202 yields (rays, class index) pairs
+            rd = batch_rays[1, :n_rgb]
+            target_sem = (rd[:, 0] > 0).long() + 2 * (rd[:, 1] > 0).long()
+        sem_ce = None
         if step is not None:
-            out = step(batch_rays, target_s, target_depth)
+            out = step(batch_rays, target_s, target_depth, target_semantic=target_sem)
             loss, psnr = out["loss"], out["psnr"]
+            sem_ce = out.get("semantic_loss")
         else:
             rgb, disp, acc, depth, extras = dn.render(H, W, FOCAL, chunk=1 << 20, rays=batch_rays, retraw=True,
                                                       network_query_fn=q, perturb=1., N_importance=64,
                                                       network_fine=model_fine, N_samples=64, network_fn=model,
                                                       use_viewdirs=True, white_bkgd=False, raw_noise_std=1., ndc=True,
-                                                      near=0., far=1.)
+                                                      near=0., far=1., semantic_loss=bool(K))
             optimizer.zero_grad()
             img_loss = dn.img2mse(rgb[:n_rgb], target_s)
             loss = img_loss + 0.1 * dn.img2mse(depth[n_rgb:], target_depth) + dn.img2mse(extras['rgb0'][:n_rgb], target_s)
+            if K:                               # run_nerf.py:1541-1548
+                sem_ce = torch.nn.functional.cross_entropy(extras['sem_preds'][:n_rgb], target_sem)
+                loss = loss + slam * (sem_ce + torch.nn.functional.cross_entropy(extras['sem_preds0'][:n_rgb], target_sem))
             loss.backward()
             psnr = dn.mse2psnr(img_loss)
         optimizer.step()
@@ -93,8 +108,9 @@ def main(argv=None):
         for g in optimizer.param_groups:
             g['lr'] = new_lrate
         if i % 50 == 0 or i == args.iters - 1:
-            losses.append((float(loss.detach()), float(psnr.detach())))
-            print("iter %4d  loss %.5f  psnr %.2f" % (i, losses[-1][0], losses[-1][1]), flush=True)
+            losses.append((float(loss.detach()), float(psnr.detach())) + ((float(sem_ce.detach()),) if K else ()))
+            print("iter %4d  loss %.5f  psnr %.2f%s" % (i, losses[-1][0], losses[-1][1],
+                                                       "  semantic CE %.4f" % losses[-1][2] if K else ""), flush=True)
     return losses
 
 

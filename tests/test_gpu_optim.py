@@ -125,3 +125,20 @@ def test_synthetic_scene_training_converges(route):
     log = mod.main(["--iters", "120", "--n-rand", "1024"] + route)
     print("  (loss, psnr) every 50 iterations:", log)
     assert log[0][1] < 15.0 and log[-1][1] > 27.0 and log[-1][0] < 0.1 * log[0][0]
+
+
+@pytest.mark.parametrize("route", [[], ["--drop-in"]])
+def test_synthetic_scene_training_with_semantic_head_converges(route):
+    """The same loop with the semantic head on (4 classes = quadrant of the view direction, semantic_lambda 0.01 as
+    in fern_dsnerf.txt:55-56): colour still converges and the cross-entropy of the fine per-ray logits falls well
+    below its initial value -- the whole chain fold -> head -> cross-entropy -> dgrad row -> unfold -> Adam works."""
+    import importlib.util
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "train_synthetic.py")
+    spec = importlib.util.spec_from_file_location("train_synthetic", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    log = mod.main(["--iters", "150", "--n-rand", "1024", "--semantic"] + route)
+    print("  (loss, psnr, semantic CE) every 50 iterations:", log)
+    assert log[-1][1] > 25.0
+    assert log[-1][2] < 0.7 * log[0][2]
