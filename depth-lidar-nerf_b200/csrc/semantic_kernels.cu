@@ -184,9 +184,12 @@ __global__ void __launch_bounds__(256)
                                             (((chunk ^ r) & 7u) << 4));
     };
     long long p = p0;
-    for (; p + 4 <= p1; p += 4) {           // four independent 16-byte loads in flight per lane
-      const uint4 v0 = __ldg(addr(p)), v1 = __ldg(addr(p + 1)), v2 = __ldg(addr(p + 2)), v3 = __ldg(addr(p + 3));
-      acc_bf16x8(h, v0), acc_bf16x8(h, v1), acc_bf16x8(h, v2), acc_bf16x8(h, v3);
+    for (; p + 8 <= p1; p += 8) {           // eight independent 16-byte loads in flight per lane
+      uint4 v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = __ldg(addr(p + i));
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc_bf16x8(h, v[i]);
     }
     for (; p < p1; ++p) acc_bf16x8(h, __ldg(addr(p)));
     if (hsum != nullptr) {
@@ -207,6 +210,85 @@ __global__ void __launch_bounds__(256)
         if (lane == k) mine = a + cnt * __ldg(sc + k);
       }
       if (lane < K) out[(size_t)g * out_ld + lane] = mine;
+    }
+  }
+}
+
+// Per-point logits (S = 1, no Hsum wanted: the semantic columns of a returned `raw`).  A warp per point would spend
+// K shuffle reductions per point; here a 256-thread block takes a 128-point tile, thread = (point, half of the
+// class PAIRS), the point's 512-byte row comes in 16-byte chunks (neighbouring threads read neighbouring 128-byte
+// rows of the slab image) and Sw sits in shared memory interleaved by class pair, {Sw[2q][f], Sw[2q+1][f]}, so one
+// packed fma.rn.f32x2 (two fp32 FMAs per issue slot) advances both classes of a pair: 19 x 256 MACs per point at
+// ~1.2 issue slots per 2 MACs.
+constexpr int kPtPairs = kMaxK / 4;      // class pairs per thread (half of the at most kMaxK / 2 pairs)
+
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void fma2(unsigned long long& acc, unsigned long long a, unsigned long long b) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
+
+__global__ void __launch_bounds__(256)
+    sem_point_logits_kernel(const uint8_t* __restrict__ stash, int fwd_slots, int h_slot, long long P,
+                            const float* __restrict__ Sw, const float* __restrict__ sc, int K,
+                            float* __restrict__ out, int out_ld, long long n_tiles) {
+  __shared__ __align__(16) float2 sw2[(kMaxK / 2) * kW];      // 32 KB
+  __shared__ float sb[kMaxK];
+  const int n_pairs = (K + 1) / 2;
+  for (int i = threadIdx.x; i < n_pairs * kW; i += 256) {
+    const int q = i / kW, f = i % kW;
+    sw2[i] = make_float2(__ldg(Sw + (size_t)(2 * q) * kW + f), 2 * q + 1 < K ? __ldg(Sw + (size_t)(2 * q + 1) * kW + f) : 0.f);
+  }
+  if ((int)threadIdx.x < kMaxK) sb[threadIdx.x] = (int)threadIdx.x < K ? __ldg(sc + threadIdx.x) : 0.f;
+  __syncthreads();
+  const uint32_t r = threadIdx.x & 127u;
+  const int half = threadIdx.x >> 7;                 // warp-uniform
+  const int q0 = half ? (n_pairs + 1) / 2 : 0;
+  const int qn = half ? n_pairs - q0 : (n_pairs + 1) / 2;        // <= kPtPairs
+  const size_t tile_bytes = (size_t)fwd_slots * DLN_SLAB_BYTES;
+  const uint32_t row_off = (r >> 3) * 1024u + (r & 7u) * 128u;
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long p = tile * DLN_TILE_ROWS + r;
+    const uint8_t* base = stash + (size_t)tile * tile_bytes + (size_t)h_slot * DLN_SLAB_BYTES + row_off;
+    unsigned long long acc[kPtPairs];
+#pragma unroll
+    for (int q = 0; q < kPtPairs; ++q) acc[q] = 0ull;
+#pragma unroll 2
+    for (int c = 0; c < 32; ++c) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + (size_t)(c >> 3) * DLN_SLAB_BYTES +
+                                                           ((((uint32_t)c ^ r) & 7u) << 4)));
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+      unsigned long long hh[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float lo = __uint_as_float(w[i] << 16), hi = __uint_as_float(w[i] & 0xffff0000u);
+        hh[2 * i] = pack2(lo, lo), hh[2 * i + 1] = pack2(hi, hi);
+      }
+#pragma unroll
+      for (int q = 0; q < kPtPairs; ++q)
+        if (q < qn) {
+          const ulonglong2* wp = reinterpret_cast<const ulonglong2*>(sw2 + (q0 + q) * kW + 8 * c);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const ulonglong2 ww = wp[i];            // features 8c + 2i, 8c + 2i + 1 of the class pair
+            fma2(acc[q], hh[2 * i], ww.x);
+            fma2(acc[q], hh[2 * i + 1], ww.y);
+          }
+        }
+    }
+    if (p < P) {
+#pragma unroll
+      for (int q = 0; q < kPtPairs; ++q)
+        if (q < qn) {
+          const int k = 2 * (q0 + q);
+          float lo, hi;
+          asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc[q]));
+          out[(size_t)p * out_ld + k] = lo + sb[k];
+          if (k + 1 < K) out[(size_t)p * out_ld + k + 1] = hi + sb[k + 1];
+        }
     }
   }
 }
@@ -352,6 +434,14 @@ int dln_sem_head_fwd(const void* stash_fwd, int fwd_slots, int h_slot, long long
   DLN_CHECK_ARG((hsum || out) && (!out || out_ld >= off->K));
   DLN_CHECK_ARG((reinterpret_cast<uintptr_t>(stash_fwd) & 15) == 0 && (reinterpret_cast<uintptr_t>(hsum) & 15) == 0);
   if (P == 0) return DLN_OK;
+  if (S == 1 && hsum == nullptr) {       // per-point logits only: tile-per-block kernel
+    const long long n_tiles = (P + DLN_TILE_ROWS - 1) / DLN_TILE_ROWS;
+    const long long nb = n_tiles > 148 * 4 ? 148 * 4 : n_tiles;
+    sem_point_logits_kernel<<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const uint8_t*>(stash_fwd), fwd_slots, h_slot, P, params_flat + off->Sw, params_flat + off->sc,
+        off->K, out, out_ld, n_tiles);
+    return dln_launch_status();
+  }
   const long long n_groups = (P + S - 1) / S;
   long long blocks = (n_groups + 7) / 8;
   blocks = blocks > 148 * 8 ? 148 * 8 : blocks;
