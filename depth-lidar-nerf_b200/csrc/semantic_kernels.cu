@@ -163,21 +163,30 @@ __device__ __forceinline__ void acc_bf16x8(float (&h)[8], const uint4 v) {
   }
 }
 
+// WPR warps share a group: each sums a quarter of the samples (4x the loads in flight per ray, which is what a
+// latency-bound stream of 16-byte loads needs), the partial sums meet in shared memory.
+template <int WPR>
 __global__ void __launch_bounds__(256)
     sem_head_fwd_kernel(const uint8_t* __restrict__ stash, int fwd_slots, int h_slot, long long P, int S,
                         const float* __restrict__ Sw, const float* __restrict__ sc, int K,
                         float* __restrict__ hsum, float* __restrict__ out, int out_ld, long long n_groups) {
-  const int lane = threadIdx.x & 31;
-  const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const long long n_warps = (long long)gridDim.x * (blockDim.x >> 5);
+  constexpr int GPB = 8 / WPR;                       // groups per block
+  __shared__ __align__(16) float part[WPR > 1 ? 8 : 1][kW];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int gib = wib / WPR, sub = wib % WPR;        // group in block, share of the group's samples
   const size_t tile_bytes = (size_t)fwd_slots * DLN_SLAB_BYTES;
   const uint8_t* base = stash + (size_t)(h_slot + (lane >> 3)) * DLN_SLAB_BYTES;
   const uint32_t chunk = lane & 7;
-  for (long long g = warp0; g < n_groups; g += n_warps) {
+  const int per = (S + WPR - 1) / WPR;
+  for (long long gb = (long long)blockIdx.x * GPB; gb < n_groups; gb += (long long)gridDim.x * GPB) {   // block-uniform
+    const long long g = gb + gib;
     float h[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    const long long p0 = g * S;
-    long long p1 = p0 + S;
-    if (p1 > P) p1 = P;
+    const long long q0 = g * S;
+    long long q1 = q0 + S;
+    if (q1 > P) q1 = P;
+    long long p0 = q0 + (long long)sub * per, p1 = p0 + per;
+    if (p1 > q1) p1 = q1;
+    if (g >= n_groups) p1 = p0;
     auto addr = [&](long long p) {
       const uint32_t r = (uint32_t)(p & (DLN_TILE_ROWS - 1));
       return reinterpret_cast<const uint4*>(base + (size_t)(p >> 7) * tile_bytes + (r >> 3) * 1024u + (r & 7u) * 128u +
@@ -192,13 +201,29 @@ __global__ void __launch_bounds__(256)
       for (int i = 0; i < 8; ++i) acc_bf16x8(h, v[i]);
     }
     for (; p < p1; ++p) acc_bf16x8(h, __ldg(addr(p)));
+    if (WPR > 1) {
+      float4* ps = reinterpret_cast<float4*>(&part[wib][8 * lane]);
+      ps[0] = make_float4(h[0], h[1], h[2], h[3]);
+      ps[1] = make_float4(h[4], h[5], h[6], h[7]);
+      __syncthreads();
+      if (sub == 0) {
+#pragma unroll
+        for (int w = 1; w < WPR; ++w) {
+          const float4 a = *reinterpret_cast<const float4*>(&part[wib + w][8 * lane]);
+          const float4 b = *reinterpret_cast<const float4*>(&part[wib + w][8 * lane + 4]);
+          h[0] += a.x, h[1] += a.y, h[2] += a.z, h[3] += a.w, h[4] += b.x, h[5] += b.y, h[6] += b.z, h[7] += b.w;
+        }
+      }
+      __syncthreads();                       // part[] is rewritten by the next round
+    }
+    if (sub != 0 || g >= n_groups) continue;
     if (hsum != nullptr) {
       float4* hs = reinterpret_cast<float4*>(hsum + (size_t)g * kW + 8 * lane);
       hs[0] = make_float4(h[0], h[1], h[2], h[3]);
       hs[1] = make_float4(h[4], h[5], h[6], h[7]);
     }
     if (out != nullptr) {
-      const float cnt = (float)(p1 - p0);
+      const float cnt = (float)(q1 - q0);
       float mine = 0.f;                      // lane k keeps logit k
       for (int k = 0; k < K; ++k) {
         const float4 w0 = __ldg(reinterpret_cast<const float4*>(Sw + (size_t)k * kW + 8 * lane));
@@ -443,11 +468,18 @@ int dln_sem_head_fwd(const void* stash_fwd, int fwd_slots, int h_slot, long long
     return dln_launch_status();
   }
   const long long n_groups = (P + S - 1) / S;
-  long long blocks = (n_groups + 7) / 8;
-  blocks = blocks > 148 * 8 ? 148 * 8 : blocks;
-  sem_head_fwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const uint8_t*>(stash_fwd), fwd_slots, h_slot, P, S, params_flat + off->Sw, params_flat + off->sc,
-      off->K, hsum, out, out_ld, n_groups);
+  const bool split = S >= 32;            // rays: four warps per ray; points / tiny groups: a warp per group
+  const int gpb = split ? 2 : 8;
+  long long blocks = (n_groups + gpb - 1) / gpb;
+  blocks = blocks > 148 * 16 ? 148 * 16 : blocks;
+  if (split)
+    sem_head_fwd_kernel<4><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const uint8_t*>(stash_fwd), fwd_slots, h_slot, P, S, params_flat + off->Sw,
+        params_flat + off->sc, off->K, hsum, out, out_ld, n_groups);
+  else
+    sem_head_fwd_kernel<1><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const uint8_t*>(stash_fwd), fwd_slots, h_slot, P, S, params_flat + off->Sw,
+        params_flat + off->sc, off->K, hsum, out, out_ld, n_groups);
   return dln_launch_status();
 }
 
