@@ -193,10 +193,14 @@ __global__ void __launch_bounds__(256)
                                             (((chunk ^ r) & 7u) << 4));
     };
     long long p = p0;
-    for (; p + 8 <= p1; p += 8) {           // eight independent 16-byte loads in flight per lane
+    for (; p < p1 && (p & 7); ++p) acc_bf16x8(h, __ldg(addr(p)));
+    // 8 consecutive points from a multiple of 8 are the 8 rows of one 1 KB swizzle atom: row i of the atom keeps this
+    // lane's chunk at i * 128 + ((chunk ^ i) << 4) -- constant offsets, so the eight 16-byte loads go out back to back
+    for (; p + 8 <= p1; p += 8) {
+      const uint8_t* atom = base + (size_t)(p >> 7) * tile_bytes + (((uint32_t)p & 127u) >> 3) * 1024u;
       uint4 v[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = __ldg(addr(p + i));
+      for (int i = 0; i < 8; ++i) v[i] = __ldg(reinterpret_cast<const uint4*>(atom + i * 128 + (((chunk ^ i) & 7u) << 4)));
 #pragma unroll
       for (int i = 0; i < 8; ++i) acc_bf16x8(h, v[i]);
     }
@@ -206,35 +210,35 @@ __global__ void __launch_bounds__(256)
       ps[0] = make_float4(h[0], h[1], h[2], h[3]);
       ps[1] = make_float4(h[4], h[5], h[6], h[7]);
       __syncthreads();
-      if (sub == 0) {
+      // every warp of the group takes the total: the K logits are then split over the WPR warps
+      float4 a = *reinterpret_cast<const float4*>(&part[gib * WPR][8 * lane]);
+      float4 b = *reinterpret_cast<const float4*>(&part[gib * WPR][8 * lane + 4]);
 #pragma unroll
-        for (int w = 1; w < WPR; ++w) {
-          const float4 a = *reinterpret_cast<const float4*>(&part[wib + w][8 * lane]);
-          const float4 b = *reinterpret_cast<const float4*>(&part[wib + w][8 * lane + 4]);
-          h[0] += a.x, h[1] += a.y, h[2] += a.z, h[3] += a.w, h[4] += b.x, h[5] += b.y, h[6] += b.z, h[7] += b.w;
-        }
+      for (int w = 1; w < WPR; ++w) {
+        const float4 c = *reinterpret_cast<const float4*>(&part[gib * WPR + w][8 * lane]);
+        const float4 d = *reinterpret_cast<const float4*>(&part[gib * WPR + w][8 * lane + 4]);
+        a.x += c.x, a.y += c.y, a.z += c.z, a.w += c.w, b.x += d.x, b.y += d.y, b.z += d.z, b.w += d.w;
       }
+      h[0] = a.x, h[1] = a.y, h[2] = a.z, h[3] = a.w, h[4] = b.x, h[5] = b.y, h[6] = b.z, h[7] = b.w;
       __syncthreads();                       // part[] is rewritten by the next round
     }
-    if (sub != 0 || g >= n_groups) continue;
-    if (hsum != nullptr) {
+    if (g >= n_groups) continue;
+    if (hsum != nullptr && sub == 0) {
       float4* hs = reinterpret_cast<float4*>(hsum + (size_t)g * kW + 8 * lane);
       hs[0] = make_float4(h[0], h[1], h[2], h[3]);
       hs[1] = make_float4(h[4], h[5], h[6], h[7]);
     }
     if (out != nullptr) {
       const float cnt = (float)(q1 - q0);
-      float mine = 0.f;                      // lane k keeps logit k
-      for (int k = 0; k < K; ++k) {
+      for (int k = sub; k < K; k += WPR) {
         const float4 w0 = __ldg(reinterpret_cast<const float4*>(Sw + (size_t)k * kW + 8 * lane));
         const float4 w1 = __ldg(reinterpret_cast<const float4*>(Sw + (size_t)k * kW + 8 * lane + 4));
-        float a = h[0] * w0.x;
-        a = fmaf(h[1], w0.y, a), a = fmaf(h[2], w0.z, a), a = fmaf(h[3], w0.w, a);
-        a = fmaf(h[4], w1.x, a), a = fmaf(h[5], w1.y, a), a = fmaf(h[6], w1.z, a), a = fmaf(h[7], w1.w, a);
-        a = dln::warp_sum(a);
-        if (lane == k) mine = a + cnt * __ldg(sc + k);
+        float acc = h[0] * w0.x;
+        acc = fmaf(h[1], w0.y, acc), acc = fmaf(h[2], w0.z, acc), acc = fmaf(h[3], w0.w, acc);
+        acc = fmaf(h[4], w1.x, acc), acc = fmaf(h[5], w1.y, acc), acc = fmaf(h[6], w1.z, acc), acc = fmaf(h[7], w1.w, acc);
+        acc = dln::warp_sum(acc);
+        if (lane == 0) out[(size_t)g * out_ld + k] = acc + cnt * __ldg(sc + k);
       }
-      if (lane < K) out[(size_t)g * out_ld + lane] = mine;
     }
   }
 }
