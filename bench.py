@@ -414,6 +414,28 @@ def run_ours(args):
         e2e["graph_route"] = {"value": args.n_rand * world / (ms_g * 1e-3), "unit": "rays/s", "ms_per_step": ms_g,
                               "api": "dlnerf_b200.GraphedTrainStep(...)(host_rays, host_target_s, host_target_depth)"}
 
+    # ---- the same step with the semantic head on, reported next to the headline (one GPU only) ---------------
+    variants = None
+    if not semK and world == 1 and not args.no_variants:
+        K = 19                                         # KITTI-360 label set of fern_dsnerf.txt:55-56
+        torch.manual_seed(3407)
+        vc = dn.NeRF(D=COARSE_D, W=256, input_ch=63, input_ch_views=27, use_viewdirs=True, semantic_num_classes=K).to(dev)
+        vf = dn.NeRF(D=FINE_D, W=256, input_ch=63, input_ch_views=27, use_viewdirs=True, semantic_num_classes=K).to(dev)
+        v_sem = torch.randint(0, K, (n_rgb,), generator=torch.Generator().manual_seed(3407)).to(dev)
+        vg = dn.GraphedTrainStep(H, W, FOCAL, args.n_rand, n_rgb, vc, vf, N_samples=N_SAMPLES, N_importance=N_IMPORTANCE,
+                                 perturb=1., raw_noise_std=1., depth_lambda=DEPTH_LAMBDA, depth_importance=1.,
+                                 semantic_lambda=SEMANTIC_LAMBDA)
+        v_step = lambda: vg(d_rays, d_tgt, d_dep, target_semantic=v_sem)      # noqa: E731
+        for _ in range(3):
+            v_step()
+        ms_v = timed(v_step, args.steps)
+        variants = {"semantic_head_19_classes": {
+            "value": args.n_rand / (ms_v * 1e-3), "unit": "rays/s", "ms_per_step": ms_v,
+            "what": "same step with semantic_loss = True as fern_dsnerf.txt:55-56 ships it: 19-class semantic_linear head on "
+                    "both nets, cross-entropy of the fine and coarse per-ray logits (semantic_lambda 0.01), "
+                    "GraphedTrainStep; `bench.py --semantic 19` gives the full line for it"}}
+        del vg, vc, vf
+
     cb = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cb = cpu_baseline()
@@ -426,7 +448,8 @@ def run_ours(args):
                 "off (headline workload: RGB + LiDAR-depth loss)" if not semK else
                 "on: %d classes, cross-entropy of fine + coarse per-ray logits, lambda %g (fern_dsnerf.txt:55-56)" % (semK, SEMANTIC_LAMBDA)),
                 value_route={"graph": "dlnerf_b200.GraphedTrainStep (CUDA graph of train_step)", "fused": "dlnerf_b200.train_step", "dropin": "render()+loss.backward()"}[args.path]), "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches,
-            "roofline": roofline, "cpu_baseline": cb, "kernels": kern, "kernel_times_from": kernel_times_from}))
+            "roofline": roofline, "cpu_baseline": cb, "variants": variants, "kernels": kern,
+            "kernel_times_from": kernel_times_from}))
     if world > 1:
         dist.destroy_process_group()
 
@@ -439,6 +462,7 @@ def main():
     ap.add_argument("--n-rand", type=int, default=4096, help="rays per step per GPU (config B: 4096)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-variants", action="store_true", help="skip the semantic-head variant of the step")
     ap.add_argument("--semantic", type=int, default=0,
                     help="classes of the semantic head (fern_dsnerf.txt:55 turns it on with the KITTI-360 label set, 19); "
                          "0 = the headline workload (RGB + depth loss)")

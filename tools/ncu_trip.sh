@@ -1,7 +1,7 @@
 #!/bin/bash
 # ncu evidence: launch list of one bench run + full captures of the chain and wgrad kernels.
 mkdir -p gpurun_out
-CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --path fused"
+CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-variants --path fused"
 $CMD > gpurun_out/plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -s 300 -c 400 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
 echo "launch list exit=$?"
