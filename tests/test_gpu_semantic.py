@@ -312,3 +312,33 @@ def test_fullsize_semantic_step_properties():
         worst = max(worst, rel_l2(3.0 * da, db))
     print("  worst rel-L2 of 3 x (grad at lambda) vs (grad at 3 lambda), semantic share: %.3e" % worst)
     assert worst <= 5e-3
+
+
+@pytest.mark.parametrize("classes", [1, 2, 32])
+def test_class_count_edges(classes):
+    """K = 1, 2 and the maximum 32: per-point logits through NeRF.forward (warp-per-point kernel, keeps Hsum for the
+    backward) and through forward_rays(point_logits=True) (tile-per-block packed-FMA kernel), per-ray logits as their
+    sum, and the gradients of the head's own parameters."""
+    net, p, spec = make_net(8, seed=40 + classes, semantic=classes)
+    N, S = 5, 64                                                   # 320 points: two full tiles and a half-filled one
+    ro, rd = O.synth_rays(N, seed=3, H=H, W=W, focal=FOCAL)
+    rb = O.pack_rays(H, W, FOCAL, ro, rd)
+    z = O.stratified_z(rb[:, 6:7], rb[:, 7:8], S, None)
+    pts = rb[:, None, 0:3] + rb[:, None, 3:6] * z[:, :, None]
+    x = torch.cat([O.posenc(pts.reshape(-1, 3), 10), O.posenc(rb[:, None, -3:].expand(N, S, 3).reshape(-1, 3), 4)], -1)
+    p32 = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    y32 = O.mlp_forward(p32, x, spec)
+    y = net(x.to(DEV))
+    assert y.shape == (N * S, 4 + classes)
+    tol = dict(atol=2e-2, rtol=1e-2)
+    report("K=%d forward(x) logits" % classes, y[:, 4:], y32[:, 4:], **tol)
+    with torch.no_grad():
+        raw, sem, logits = net.forward_rays(rb.to(DEV), z.to(DEV), semantic=True, point_logits=True)
+    report("K=%d forward_rays point logits" % classes, logits.reshape(N * S, classes), y32[:, 4:], **tol)
+    report("K=%d per-ray logits" % classes, sem, y32[:, 4:].reshape(N, S, classes).sum(1), atol=5e-2, rtol=1e-2)
+    cot = torch.randn(N * S, classes, generator=torch.Generator().manual_seed(classes))
+    (y[:, 4:] * cot.to(DEV)).sum().backward()
+    (y32[:, 4:] * cot).sum().backward()
+    for name in ("semantic_linear.1.weight", "semantic_linear.1.bias", "semantic_linear.0.weight", "feature_linear.bias"):
+        g = dict(net.named_parameters())[name].grad
+        assert rel_l2(g, p32[name].grad) <= 2e-2, (name, rel_l2(g, p32[name].grad))
