@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "../../include/dlnerf_b200.h"
 #include <math.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -243,6 +244,87 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// Rays with S % 32 == 0 (every shipped config: 64 coarse / 128 fine samples): the 32-row blocks of a ray are 4 KB
+// contiguous in each of the four slabs, so they are staged with bulk copies (TMA engine) instead of per-lane 16-byte
+// loads -- a warp keeps two 16 KB blocks in flight without holding a single register for them.  Four warps per CTA,
+// one CTA per SM (128 KB of staging), each warp walks its own stream of (ray, block) items: wait for the block,
+// add its 32 rows (conflict-free swizzled LDS.128), hand the buffer back to the copy engine, and at the end of a ray
+// write Hsum and the K logits while the next ray's blocks are already landing.
+constexpr int kBulkWarps = 4;                    // measured: 7 warps (224 KB of staging) are 3 % slower than 4
+constexpr int kBulkBlockBytes = 4 * 4096;            // 32 rows x 128 B in each of the 4 slabs
+constexpr size_t kBulkSmemBytes = (size_t)kBulkWarps * 2 * kBulkBlockBytes + kBulkWarps * 2 * sizeof(uint64_t) + 128;
+
+__global__ void __launch_bounds__(kBulkWarps * 32, 1)
+    sem_head_fwd_bulk_kernel(const uint8_t* __restrict__ stash, int fwd_slots, int h_slot, int S,
+                             const float* __restrict__ Sw, const float* __restrict__ sc, int K,
+                             float* __restrict__ hsum, float* __restrict__ out, int out_ld, long long n_groups) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((128u - (dln::smem_u32(smem_raw) & 127u)) & 127u);
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  uint8_t* buf = smem + (size_t)wib * 2 * kBulkBlockBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kBulkWarps * 2 * kBulkBlockBytes) + wib * 2;
+  if (lane == 0) {
+    dln::mbar_init(&bars[0], 1), dln::mbar_init(&bars[1], 1);
+    dln::mbar_fence_init();
+  }
+  __syncthreads();
+  const long long total_warps = (long long)gridDim.x * kBulkWarps;
+  const long long gw = (long long)blockIdx.x * kBulkWarps + wib;
+  const int n = S >> 5;                                            // blocks per ray
+  const long long my_rays = gw < n_groups ? (n_groups - gw + total_warps - 1) / total_warps : 0;
+  const long long n_items = my_rays * n;
+  const size_t tile_bytes = (size_t)fwd_slots * DLN_SLAB_BYTES;
+  auto issue = [&](long long t, int b) {                           // lane 0 only
+    const long long ray = gw + (t / n) * total_warps;
+    const long long p0 = ray * S + (t % n) * 32;
+    const uint8_t* src = stash + (size_t)(p0 >> 7) * tile_bytes + (size_t)h_slot * DLN_SLAB_BYTES +
+                         (((uint32_t)p0 & 127u) >> 3) * 1024u;
+    dln::mbar_expect_tx(&bars[b], kBulkBlockBytes);
+#pragma unroll
+    for (int sl = 0; sl < 4; ++sl)
+      dln::bulk_g2s(buf + b * kBulkBlockBytes + sl * 4096, src + (size_t)sl * DLN_SLAB_BYTES, 4096, &bars[b]);
+  };
+  if (lane == 0) {
+    if (n_items > 0) issue(0, 0);
+    if (n_items > 1) issue(1, 1);
+  }
+  uint32_t phase = 0;                                              // bit b = parity to wait for on buffer b
+  float h[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const uint32_t chunk = lane & 7;
+  for (long long t = 0; t < n_items; ++t) {
+    const int b = (int)(t & 1);
+    dln::mbar_wait(&bars[b], (phase >> b) & 1u);
+    phase ^= 1u << b;
+    const uint8_t* rows = buf + b * kBulkBlockBytes + (lane >> 3) * 4096;
+#pragma unroll 8
+    for (int row = 0; row < 32; ++row)
+      acc_bf16x8(h, *reinterpret_cast<const uint4*>(rows + row * 128 + (((chunk ^ (uint32_t)row) & 7u) << 4)));
+    __syncwarp();                                                  // every lane has read buffer b
+    if (lane == 0 && t + 2 < n_items) issue(t + 2, b);
+    if ((t % n) != n - 1) continue;
+    const long long g = gw + (t / n) * total_warps;                // the ray is complete
+    if (hsum != nullptr) {
+      float4* hs = reinterpret_cast<float4*>(hsum + (size_t)g * kW + 8 * lane);
+      hs[0] = make_float4(h[0], h[1], h[2], h[3]);
+      hs[1] = make_float4(h[4], h[5], h[6], h[7]);
+    }
+    if (out != nullptr) {
+      const float cnt = (float)S;
+      for (int k = 0; k < K; ++k) {
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(Sw + (size_t)k * kW + 8 * lane));
+        const float4 w1 = __ldg(reinterpret_cast<const float4*>(Sw + (size_t)k * kW + 8 * lane + 4));
+        float acc = h[0] * w0.x;
+        acc = fmaf(h[1], w0.y, acc), acc = fmaf(h[2], w0.z, acc), acc = fmaf(h[3], w0.w, acc);
+        acc = fmaf(h[4], w1.x, acc), acc = fmaf(h[5], w1.y, acc), acc = fmaf(h[6], w1.z, acc), acc = fmaf(h[7], w1.w, acc);
+        acc = dln::warp_sum(acc);
+        if (lane == 0) out[(size_t)g * out_ld + k] = acc + cnt * __ldg(sc + k);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) h[i] = 0.f;
+  }
+}
+
 // Per-point logits (S = 1, no Hsum wanted: the semantic columns of a returned `raw`).  A warp per point would spend
 // K shuffle reductions per point; here a 256-thread block takes a 128-point tile, thread = (point, half of the
 // class PAIRS), the point's 512-byte row comes in 16-byte chunks (neighbouring threads read neighbouring 128-byte
@@ -433,6 +515,8 @@ __global__ void __launch_bounds__(256)
   d_raw[idx] = c >= c0 ? g[n * (C - c0) + c - c0] : 0.f;
 }
 
+long long n_groups_exact(long long P, int S) { return P / S; }
+
 bool offsets_ok(const DlnSemOffsets* o) {
   return o && o->K >= 1 && o->K <= kMaxK && o->w_f >= 0 && o->b_f >= 0 && o->w_s1 >= 0 && o->b_s1 >= 0 &&
          o->w_s2 >= 0 && o->b_s2 >= 0 && o->A >= 0 && o->a >= 0 && o->Sw >= 0 && o->sc >= 0 && (o->Sw & 3) == 0;
@@ -472,6 +556,23 @@ int dln_sem_head_fwd(const void* stash_fwd, int fwd_slots, int h_slot, long long
     return dln_launch_status();
   }
   const long long n_groups = (P + S - 1) / S;
+  static const bool no_bulk = getenv("DLN_SEM_NO_BULK") != nullptr;      // A/B switch for the per-lane-load kernels
+  if (S % 32 == 0 && P == n_groups_exact(P, S) * S && !no_bulk) {         // whole rays of 32-row blocks
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(sem_head_fwd_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)kBulkSmemBytes);
+      if (e != cudaSuccess) return (int)e;
+      attr_set = true;
+    }
+    const long long ng = P / S;
+    long long nb = (ng + kBulkWarps - 1) / kBulkWarps;
+    nb = nb > 148 ? 148 : nb;
+    sem_head_fwd_bulk_kernel<<<(unsigned)nb, kBulkWarps * 32, kBulkSmemBytes, (cudaStream_t)stream>>>(
+        reinterpret_cast<const uint8_t*>(stash_fwd), fwd_slots, h_slot, S, params_flat + off->Sw, params_flat + off->sc,
+        off->K, hsum, out, out_ld, ng);
+    return dln_launch_status();
+  }
   const bool split = S >= 32;            // rays: four warps per ray; points / tiny groups: a warp per group
   const int gpb = split ? 2 : 8;
   long long blocks = (n_groups + gpb - 1) / gpb;
