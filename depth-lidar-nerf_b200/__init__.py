@@ -18,11 +18,12 @@ from .run_nerf import (FusedQuery, batchify, batchify_rays, batchify_rays_featur
 from .data import DeviceRayLoader, RayDataset
 from .optim import FlatAdam
 from .loss import InverseDepthSmoothnessLoss
-from .train import (GraphedTrainStep, allreduce_gradients, default_ray_chunk, pack_ray_batch, shard_bounds, shard_ray_batch,
-                    train_step)
+from .train import (GraphedTrainStep, allreduce_gradients, default_ray_chunk, pack_ray_batch,
+                    render_patch_nograd_sharded, shard_bounds, shard_ray_batch, train_step)
 
 __all__ = ["build", "lib", "ops", "Embedder", "NeRF", "get_embedder", "img2mse", "mse2psnr", "ndc_rays",
            "raw2outputs", "sample_pdf", "to8b", "FusedQuery", "batchify", "batchify_rays", "create_nerf",
            "get_rays", "render", "render_rays", "run_network", "allreduce_gradients", "pack_ray_batch",
            "shard_bounds", "shard_ray_batch", "train_step", "GraphedTrainStep", "default_ray_chunk", "FlatAdam",
-           "render_path", "DeviceRayLoader", "RayDataset", "render_feature_loss", "batchify_rays_feature_loss", "InverseDepthSmoothnessLoss"]
+           "render_path", "DeviceRayLoader", "RayDataset", "render_feature_loss", "batchify_rays_feature_loss", "InverseDepthSmoothnessLoss",
+           "render_patch_nograd_sharded"]

@@ -85,6 +85,38 @@ def allreduce_gradients(params: Sequence[Tensor], world: int, group=None) -> Non
             o += g.numel()
 
 
+def render_patch_nograd_sharded(H, W, focal, rays, rank: int, world: int, group=None, keep_keys=None, chunk=1024 * 32,
+                                render_fn=None, **kwargs):
+    """The no-grad part of a patch render (run_nerf.py:1600-1605: the ~31 k pixels of a 94x352 patch that carry no
+    gradient) split over the ranks of a data-parallel job: every rank renders an equal contiguous slice of the rays
+    under ``torch.no_grad()`` (forward-only kernels, no stash) and one all_gather per kept map assembles the full
+    patch on every rank, in ray order.  The gradient-carrying block of the patch (32x64 rays) is rendered by every
+    rank itself, so the patch losses and their gradients are identical on all ranks and the usual gradient average
+    leaves them unchanged.  ``rays`` = (rays_o[N,3], rays_d[N,3]); returns {key: [N, ...]} for ``keep_keys``."""
+    import torch.distributed as dist
+    if render_fn is None:
+        from .run_nerf import render_feature_loss as render_fn
+    rays_o, rays_d = rays
+    n = rays_o.shape[0]
+    lo, hi = shard_bounds(n, rank, world)
+    with torch.no_grad():
+        local = render_fn(H, W, focal, chunk=chunk, rays=(rays_o[lo:hi], rays_d[lo:hi]), keep_keys=keep_keys,
+                          **kwargs)[-1]
+    if world <= 1:
+        return dict(local)
+    width = -(-n // world)                       # the largest shard; shorter ones are padded for the collective
+    out = {}
+    for k in sorted(local):
+        v = local[k]
+        pad = torch.zeros((width,) + tuple(v.shape[1:]), device=v.device, dtype=v.dtype)
+        pad[: hi - lo] = v
+        parts = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(parts, pad, group=group)
+        out[k] = torch.cat([parts[r][: shard_bounds(n, r, world)[1] - shard_bounds(n, r, world)[0]]
+                            for r in range(world)], 0)
+    return out
+
+
 # ----------------------------------------------------------------------------------------------------
 # fused training step
 # ----------------------------------------------------------------------------------------------------

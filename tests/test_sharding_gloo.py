@@ -93,3 +93,39 @@ def test_shard_keeps_class_order():
     parts = [dn.shard_ray_batch(rays, tgt, dep, 10, rank, 4, target_semantic=tsem) for rank in range(4)]
     assert all(len(p) == 6 and p[5].shape[0] == p[4] for p in parts)
     assert torch.equal(torch.cat([p[5] for p in parts]), tsem)
+
+
+def _fake_patch_render(H, W, focal, chunk, rays, keep_keys=None, **kw):
+    """Stands in for render_feature_loss (GPU only): per-ray maps that identify the ray."""
+    o, d = rays
+    out = {"rgb_map": o * 2.0 + d, "depth_map": o[:, 0] - d[:, 2], "acc_map": d[:, 1]}
+    return [{k: v for k, v in out.items() if not keep_keys or k in keep_keys}]
+
+
+def _patch_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(4)
+    rays = (torch.randn(37, 3, generator=g), torch.randn(37, 3, generator=g))        # ragged: 19 + 18 rays
+    got = dn.render_patch_nograd_sharded(94, 352, 138.14, rays, rank, world, keep_keys=["rgb_map", "depth_map"],
+                                         render_fn=_fake_patch_render)
+    if rank == 1:
+        torch.save(got, out)
+    dist.destroy_process_group()
+
+
+def test_sharded_patch_render_gathers_the_full_patch_in_ray_order(tmp_path):
+    """SURVEY 8(f) rank 3, multi-GPU part: the no-grad rays of a patch are split over the ranks and all-gathered."""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    out = str(tmp_path / "patch.pt")
+    mp.spawn(_patch_worker, args=(2, port, out), nprocs=2, join=True)
+    got = torch.load(out)
+    g = torch.Generator().manual_seed(4)
+    rays = (torch.randn(37, 3, generator=g), torch.randn(37, 3, generator=g))
+    ref = _fake_patch_render(94, 352, 138.14, 1, rays, keep_keys=["rgb_map", "depth_map"])[-1]
+    assert set(got) == {"rgb_map", "depth_map"}
+    for k in ref:
+        assert torch.equal(got[k], ref[k]), k
