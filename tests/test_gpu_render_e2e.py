@@ -468,3 +468,22 @@ def test_kitti360_patch_iteration_against_oracle():
     agg = (num / den) ** 0.5
     print("  aggregate rel-L2 of the parameter gradients vs the bf16-emulating oracle: %.3e" % agg)
     assert agg <= 5e-2
+
+
+def test_sharded_patch_render_single_rank_equals_render_feature_loss():
+    """render_patch_nograd_sharded with one rank is render_feature_loss under no_grad (the world-size-2 collective
+    path is covered by the gloo test on the CPU)."""
+    n = 96
+    net_c, pc, spec_c, net_f, pf, spec_f, ro, rd, rng, tgt, dep = _case(n, 0, 77, False, False)
+    d = dn()
+    q = d.FusedQuery(d.get_embedder(10, 0)[0], d.get_embedder(4, 0)[0], 1 << 16, 10, 4, 0)
+    kw = dict(network_query_fn=q, perturb=0., N_importance=64, network_fine=net_f, N_samples=64, network_fn=net_c,
+              use_viewdirs=True, white_bkgd=False, raw_noise_std=0., ndc=True, near=0., far=1.)
+    keep = ['rgb_map', 'depth_map', 'rgb0', 'depth_map0']
+    rays = (ro.to(DEV), rd.to(DEV))
+    got = d.render_patch_nograd_sharded(H, W, FOCAL, rays, 0, 1, keep_keys=keep, chunk=40, **kw)
+    with torch.no_grad():
+        ref = d.render_feature_loss(H, W, FOCAL, chunk=1 << 20, rays=rays, keep_keys=keep, **kw)[-1]
+    assert set(got) == set(keep)
+    for k in keep:
+        assert not got[k].requires_grad and torch.equal(got[k], ref[k]), k
