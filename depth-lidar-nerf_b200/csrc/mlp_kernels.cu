@@ -572,6 +572,12 @@ __global__ void __launch_bounds__(kThreads, 1)
       float dsig = 0.f;
       const float* const semrow =
           (kBwd && kSem && valid) ? args.sem_g + (size_t)(p / args.sem_g_div) * 256 : nullptr;   // padded rows: dZ = 0
+      if (kBwd && kSem && semrow != nullptr) {
+        // the row is read once per tile, one step into the chain: start the two 128-byte lines this thread will need
+        // on their way now so the epilogue of that step does not wait for L2
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(semrow + 32 * g));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(semrow + 128 + 32 * g));
+      }
       uint8_t* const gtile = keep ? reinterpret_cast<uint8_t*>(args.stash) + (size_t)tile * prog.stash_slots * kSlab : nullptr;
       auto gslot = [&](int slot) -> uint8_t* { return (kDirectStash && keep) ? gtile + (size_t)slot * kSlab : nullptr; };
       // ------------------------------------------------------------------ prologue
