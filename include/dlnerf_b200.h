@@ -259,7 +259,10 @@ int dln_sem_fold(float* params_flat, const DlnSemOffsets* off_host, void* stream
 int dln_sem_unfold_grads(const float* params_flat, float* grads_flat, const DlnSemOffsets* off_host, void* stream);
 /* Groups of S consecutive points (a ray; S = 1: a point): hsum[g, 256] = sum of the kept last-trunk-layer activations
  * (slabs h_slot..h_slot+3 of every tile of the forward stash; may be null) and out[g*out_ld + k] = Sw hsum + n_g sc
- * (may be null).  Replaces semantic_linear's forward and `torch.sum(raw[..., 4:], -2)` (run_nerf_helpers.py:589). */
+ * (may be null).  Replaces semantic_linear's forward and `torch.sum(raw[..., 4:], -2)` (run_nerf_helpers.py:589).
+ * Three kernels behind it: whole rays with S % 32 == 0 stage their 32-row blocks with bulk copies (HBM-bound, 71 % of
+ * the measured copy bandwidth at 4096 x 128 points); S == 1 without hsum is the per-point packed-FMA kernel that fills
+ * raw[..., 4:]; anything else uses per-lane 16-byte loads (a warp, or four for S >= 32, per group). */
 int dln_sem_head_fwd(const void* stash_fwd, int fwd_slots, int h_slot, long long P, int S, const float* params_flat,
                      const DlnSemOffsets* off_host, float* hsum, float* out, int out_ld, void* stream);
 /* dsem[g*dsem_ld + k] = d loss / d out of dln_sem_head_fwd.  Writes G[g, 256] = dsem Sw (hand it to the dgrad chain as
