@@ -98,6 +98,8 @@ def render_patch_nograd_sharded(H, W, focal, rays, rank: int, world: int, group=
         from .run_nerf import render_feature_loss as render_fn
     rays_o, rays_d = rays
     n = rays_o.shape[0]
+    if n < world:
+        raise ValueError("render_patch_nograd_sharded: %d rays cannot be split over %d ranks" % (n, world))
     lo, hi = shard_bounds(n, rank, world)
     with torch.no_grad():
         local = render_fn(H, W, focal, chunk=chunk, rays=(rays_o[lo:hi], rays_d[lo:hi]), keep_keys=keep_keys,
