@@ -68,13 +68,20 @@ class SemOffsets(C.Structure):
                 ("Sw", C.c_int64), ("sc", C.c_int64), ("K", C.c_int32), ("pad_", C.c_int32)]
 
 
-_P, _I, _F, _LL, _D = C.c_void_p, C.c_int, C.c_float, C.c_longlong, C.c_double
+_P, _I, _F, _LL, _D, _U64 = C.c_void_p, C.c_int, C.c_float, C.c_longlong, C.c_double, C.c_ulonglong
 
 # name -> argtypes; every function returns int.  Must list EVERY symbol include/dlnerf_b200.h declares
 # (tests/test_abi.py parses the header and compares).
 SIGNATURES = {
     "dln_pack_rays": [_P, _P, _I, _I, _I, _I, _D, _F, _F, _F, _I, _P, _P],
     "dln_stratified_z": [_P, _I, _P, _P, _I, _I, _I, _P],
+    "dln_rng_advance": [_P, _U64, _P],
+    "dln_rng_fill": [_P, _U64, _I, _P, _LL, _I, _P],
+    "dln_stratified_z_rng": [_P, _I, _P, _U64, _P, _I, _I, _I, _P],
+    "dln_composite_fwd_rng": [_P, _I, _P, _P, _P, _U64, _F, _I, _P, _P, _P, _P, _P, _I, _I, _P],
+    "dln_composite_bwd_rng": [_P, _I, _P, _P, _P, _U64, _F, _I, _P, _P, _P, _P, _P, _P, _I, _I, _P],
+    "dln_composite_bwd_fused_loss_dev": [_P, _I, _P, _P, _P, _P, _U64, _F, _I, _P, _P, _P, _I, _P, _I, _P, _P, _I, _I, _P],
+    "dln_sample_pdf_rng": [_P, _I, _I, _P, _I, _I, _P, _U64, _I, _P, _P, _I, _P, _P, _P, _I, _P],
     "dln_posenc": [_P, _P, _LL, _I, _P],
     "dln_composite_fwd": [_P, _I, _P, _P, _P, _F, _I, _P, _P, _P, _P, _P, _I, _I, _P],
     "dln_composite_bwd": [_P, _I, _P, _P, _P, _F, _I, _P, _P, _P, _P, _P, _P, _I, _I, _P],

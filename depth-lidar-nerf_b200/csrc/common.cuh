@@ -21,6 +21,26 @@ static inline int dln_launch_status() {
   return e == cudaSuccess ? DLN_OK : (int)e;
 }
 
+// Per-device "already configured" flags (cudaFuncSetAttribute and the SM count belong to a device / context, not to
+// the process): slot `which` of the current device.
+static inline bool& dln_device_flag(int which) {
+  static bool flags[64][8] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return flags[dev & 63][which & 7];
+}
+static inline int dln_sm_count() {
+  static int sms[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& s = sms[dev & 63];
+  if (!s) {
+    cudaDeviceGetAttribute(&s, cudaDevAttrMultiProcessorCount, dev);
+    if (s <= 0) s = 148;
+  }
+  return s;
+}
+
 namespace dln {
 
 constexpr unsigned FULL = 0xffffffffu;
@@ -38,6 +58,75 @@ __device__ __forceinline__ float linspace01(int i, int n) {
   const float step = __fdiv_rn(1.0f, (float)(n - 1));
   // ATen evaluates both branches as one fused multiply-add (single rounding)
   return (i < n / 2) ? __fmul_rn(step, (float)i) : __fmaf_rn(-step, (float)(n - 1 - i), 1.0f);
+}
+
+// ------------------------------------------------------------------ counter-based random numbers
+// Philox4x32-10 (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3"): the draws the reference takes from
+// torch.rand / torch.randn (run_nerf.py:585, run_nerf_helpers.py:509, :565) are generated inside the consuming
+// kernels instead of being written to and re-read from HBM.  key = the 64-bit seed, counter = (block index of the
+// element, 64-bit word w) with w = state[1] + offset: state[1] is a device-resident step counter (so a captured
+// CUDA graph draws fresh numbers on every replay), `offset` identifies the tensor within the step.
+struct RngRef {
+  const unsigned long long* state;   // device {seed, base}; null = no in-kernel generation
+  unsigned long long offset;
+};
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u, k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+struct RngKey {
+  uint2 key;
+  uint32_t w_lo, w_hi;
+};
+__device__ __forceinline__ RngKey rng_key(const RngRef& r) {
+  RngKey k;
+  const unsigned long long seed = __ldg(r.state), w = __ldg(r.state + 1) + r.offset;
+  k.key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+  k.w_lo = (uint32_t)w, k.w_hi = (uint32_t)(w >> 32);
+  return k;
+}
+__device__ __forceinline__ uint4 rng_block(const RngKey& k, unsigned long long block) {
+  return philox4x32_10(make_uint4((uint32_t)block, (uint32_t)(block >> 32), k.w_lo, k.w_hi), k.key);
+}
+// 32 random bits -> uniform in [0, 1) with 24 bits (the grid torch.rand draws fp32 from)
+__device__ __forceinline__ float rng_uniform(uint32_t x) { return (float)(x >> 8) * 5.9604644775390625e-08f; }
+// Box-Muller on (x0, x1): two independent N(0,1) values.  u1 in (0, 1], angle in [-pi, pi).
+__device__ __forceinline__ void rng_normal2(uint32_t x0, uint32_t x1, float& n0, float& n1) {
+  const float u1 = (float)((x0 >> 8) + 1u) * 5.9604644775390625e-08f;
+  const float r = sqrtf(-2.0f * __logf(u1));
+  const float th = fmaf((float)(x1 >> 8), 3.7450704e-07f /* 2 pi / 2^24 */, -3.14159265358979f);
+  float sn, cs;
+  __sincosf(th, &sn, &cs);
+  n0 = r * cs, n1 = r * sn;
+}
+// K consecutive elements e0 .. e0+K-1 of a random tensor: element e is component (e & 3) of Philox block (e >> 2);
+// normal tensors turn components (0,1) and (2,3) into Box-Muller pairs.
+template <int K, bool NORMAL>
+__device__ __forceinline__ void rng_fill(const RngKey& key, unsigned long long e0, float (&out)[K]) {
+  unsigned long long cur = ~0ull;
+  float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const unsigned long long e = e0 + k, b = e >> 2;
+    if (b != cur) {
+      const uint4 x = rng_block(key, b);
+      if (NORMAL) {
+        rng_normal2(x.x, x.y, v0, v1);
+        rng_normal2(x.z, x.w, v2, v3);
+      } else {
+        v0 = rng_uniform(x.x), v1 = rng_uniform(x.y), v2 = rng_uniform(x.z), v3 = rng_uniform(x.w);
+      }
+      cur = b;
+    }
+    const int j = (int)(e & 3);
+    out[k] = j == 0 ? v0 : j == 1 ? v1 : j == 2 ? v2 : v3;
+  }
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

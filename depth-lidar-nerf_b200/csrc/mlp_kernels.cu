@@ -981,7 +981,7 @@ int dln_mlp_chain(const DlnChainProgram* prog, const DlnChainArgs* args, int num
   if (args->stash && prog->stash_slots > 0) DLN_CHECK_ARG((reinterpret_cast<uintptr_t>(args->stash) & 15) == 0);
   if (args->P == 0) return DLN_OK;
   const long long n_tiles = (args->P + DLN_TILE_ROWS - 1) / DLN_TILE_ROWS;
-  static bool attr_set = false;
+  bool& attr_set = dln_device_flag(0);     // the attribute is per device (context), not per process
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemBytes);
     if (e != cudaSuccess) return (int)e;
@@ -1005,7 +1005,7 @@ int dln_mlp_wgrad(const DlnWgradItem* items_dev, int n_items, int splits, const 
                   const void* stash_bwd, int bwd_slots, long long n_tiles, float* grads_flat, void* stream) {
   DLN_CHECK_ARG(items_dev && n_items >= 1 && splits >= 1 && stash_fwd && stash_bwd && grads_flat && n_tiles >= 0);
   if (n_tiles == 0) return DLN_OK;
-  static bool attr_set = false;
+  bool& attr_set = dln_device_flag(1);
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWgradSmemBytes);
     if (e != cudaSuccess) return (int)e;

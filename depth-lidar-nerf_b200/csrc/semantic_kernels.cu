@@ -558,7 +558,7 @@ int dln_sem_head_fwd(const void* stash_fwd, int fwd_slots, int h_slot, long long
   const long long n_groups = (P + S - 1) / S;
   static const bool no_bulk = getenv("DLN_SEM_NO_BULK") != nullptr;      // A/B switch for the per-lane-load kernels
   if (S % 32 == 0 && P == n_groups_exact(P, S) * S && !no_bulk) {         // whole rays of 32-row blocks
-    static bool attr_set = false;
+    bool& attr_set = dln_device_flag(2);
     if (!attr_set) {
       cudaError_t e = cudaFuncSetAttribute(sem_head_fwd_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)kBulkSmemBytes);

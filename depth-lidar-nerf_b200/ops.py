@@ -19,6 +19,28 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+def on_device_of(argpos: int = 0, kw: Optional[str] = None):
+    """Decorator for the public entry points: run the body with the CUDA device of a tensor argument current, so
+    that kernel launches, `_stream()` and the per-device kernel attributes all refer to the tensors' device even
+    when the caller's current device is another GPU (one process driving several GPUs)."""
+    import functools
+
+    def deco(fn):
+        @functools.wraps(fn)
+        def wrapped(*args, **kwargs):
+            t = kwargs.get(kw) if kw is not None and kw in kwargs else (args[argpos] if len(args) > argpos else None)
+            if isinstance(t, (tuple, list)) and t:
+                t = t[0]
+            if isinstance(t, torch.nn.Module):
+                t = next(t.parameters(), None)
+            if torch.is_tensor(t) and t.is_cuda and t.device.index != torch.cuda.current_device():
+                with torch.cuda.device(t.device):
+                    return fn(*args, **kwargs)
+            return fn(*args, **kwargs)
+        return wrapped
+    return deco
+
+
 def _f32(t: Tensor, what: str) -> Tensor:
     if not t.is_cuda:
         raise RuntimeError("dlnerf_b200.%s: tensor is on %s; the B200 path has no CPU fallback" % (what, t.device))
@@ -29,6 +51,67 @@ def _f32(t: Tensor, what: str) -> Tensor:
 
 def _ptr(t: Optional[Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
+
+
+# ------------------------------------------------------------------------------------------------
+# In-kernel random numbers (include/dlnerf_b200.h, "In-kernel random numbers")
+# ------------------------------------------------------------------------------------------------
+class RngState:
+    """Device-resident {seed, base} pair of the Philox generator the sampling / compositing kernels carry.  A random
+    tensor is named by (seed, base + offset): ``offset`` is passed by value with each launch, ``base`` lives on the
+    device (``advance`` bumps it in-stream, so a captured CUDA graph draws fresh numbers on every replay)."""
+
+    def __init__(self, device, seed: Optional[int] = None):
+        self.device = torch.device(device)
+        self.seed = int(torch.initial_seed() if seed is None else seed) & ((1 << 63) - 1)
+        self.state = torch.tensor([self.seed, 0], dtype=torch.int64, device=self.device)
+        self.calls = 0                       # host-side tensor counter (drop-in route: offsets instead of `advance`)
+
+    def ptr(self) -> int:
+        return self.state.data_ptr()
+
+    def advance(self, inc: int) -> None:
+        L.call("dln_rng_advance", self.ptr(), int(inc), _stream(), tag="rng_advance")
+
+    def next_offsets(self, n: int) -> int:
+        """Reserve n tensor names; returns the first offset (host-side bookkeeping, no launch)."""
+        o = self.calls
+        self.calls += n
+        return o
+
+    def fill(self, offset: int, kind: str, rows: int, row_len: int) -> Tensor:
+        """The draws a kernel generates for tensor (base + offset), as a tensor (tests): kind 'u' uniform row-major,
+        'n' normal row-major, 'u_resample' uniform in the slot order of the <=64+64 importance_resample path."""
+        out = torch.empty(rows, row_len, device=self.device, dtype=torch.float32)
+        L.call("dln_rng_fill", self.ptr(), int(offset), {"u": 0, "n": 1, "u_resample": 2}[kind], out.data_ptr(),
+               rows, row_len, _stream(), tag="rng_fill")
+        return out
+
+
+Rng = Optional[Tuple[RngState, int]]         # (state, by-value offset) naming one random tensor
+_DEFAULT_RNG = {}
+
+
+def default_rng(device, stream_id: int = 0) -> RngState:
+    """Per-device generator state seeded from torch's (``torch.manual_seed`` re-seeds it; ranks of a distributed job
+    get distinct streams).  ``stream_id`` separates independent consumers (0: render_rays, 1: train_step)."""
+    device = torch.device(device)
+    if device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    rank = 0
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            rank = dist.get_rank()
+    except Exception:
+        rank = 0
+    key = (device, stream_id)
+    seed = (torch.initial_seed() * 0x9E3779B97F4A7C15 + rank * 0xD1B54A32D192ED03 + stream_id * 0x94D049BB133111EB) \
+        & ((1 << 63) - 1)
+    st = _DEFAULT_RNG.get(key)
+    if st is None or st.seed != seed:
+        st = _DEFAULT_RNG[key] = RngState(device, seed)
+    return st
 
 
 # ------------------------------------------------------------------------------------------------
@@ -47,11 +130,17 @@ def pack_rays(H: int, W: int, focal: float, rays_o: Tensor, rays_d: Tensor, ndc:
     return out
 
 
-def stratified_z(ray_batch: Tensor, n_samples: int, t_rand: Optional[Tensor] = None, lindisp: bool = False) -> Tensor:
-    """run_nerf.py:571-593.  ray_batch[N, >=8] with near/far at columns 6/7."""
+def stratified_z(ray_batch: Tensor, n_samples: int, t_rand: Optional[Tensor] = None, lindisp: bool = False,
+                 rng: Rng = None) -> Tensor:
+    """run_nerf.py:571-593.  ray_batch[N, >=8] with near/far at columns 6/7.  Jitter: ``t_rand`` (a tensor of U[0,1)
+    draws) or ``rng`` (drawn in-kernel) or neither (bin centres)."""
     rb = _f32(ray_batch, "stratified_z")
     N = rb.shape[0]
     z = torch.empty(N, n_samples, device=rb.device, dtype=torch.float32)
+    if rng is not None and t_rand is None:
+        L.call("dln_stratified_z_rng", rb.data_ptr(), rb.stride(0), rng[0].ptr(), int(rng[1]), z.data_ptr(), N,
+               n_samples, int(bool(lindisp)), _stream(), tag="stratified_z")
+        return z
     tr = None if t_rand is None else _f32(t_rand, "stratified_z")
     if tr is not None and tuple(tr.shape) != (N, n_samples):
         raise ValueError("t_rand must be [N, N_samples]")
@@ -78,19 +167,27 @@ class _Composite(torch.autograd.Function):
     z_samples is detached, run_nerf.py:634)."""
 
     @staticmethod
-    def forward(ctx, raw, z_vals, rays_d, noise, noise_std, white_bkgd):
+    def forward(ctx, raw, z_vals, rays_d, noise, noise_std, white_bkgd, rng):
         raw_c, z_c, d_c = _f32(raw, "raw2outputs"), _f32(z_vals, "raw2outputs"), _f32(rays_d, "raw2outputs")
         N, S, Cc = raw_c.shape
         nz = None if noise is None else _f32(noise, "raw2outputs")
+        if nz is not None:
+            rng = None
         dev = raw_c.device
         rgb = torch.empty(N, 3, device=dev)
         disp, acc, depth = torch.empty(N, device=dev), torch.empty(N, device=dev), torch.empty(N, device=dev)
         w = torch.empty(N, S, device=dev)
-        L.call("dln_composite_fwd", raw_c.data_ptr(), Cc, z_c.data_ptr(), d_c.data_ptr(), _ptr(nz),
-                                          float(noise_std), int(white_bkgd), rgb.data_ptr(), disp.data_ptr(),
-                                          acc.data_ptr(), w.data_ptr(), depth.data_ptr(), N, S, _stream(), tag="composite_fwd")
+        if rng is not None:
+            L.call("dln_composite_fwd_rng", raw_c.data_ptr(), Cc, z_c.data_ptr(), d_c.data_ptr(), rng[0].ptr(),
+                   int(rng[1]), float(noise_std), int(white_bkgd), rgb.data_ptr(), disp.data_ptr(), acc.data_ptr(),
+                   w.data_ptr(), depth.data_ptr(), N, S, _stream(), tag="composite_fwd")
+        else:
+            L.call("dln_composite_fwd", raw_c.data_ptr(), Cc, z_c.data_ptr(), d_c.data_ptr(), _ptr(nz),
+                   float(noise_std), int(white_bkgd), rgb.data_ptr(), disp.data_ptr(),
+                   acc.data_ptr(), w.data_ptr(), depth.data_ptr(), N, S, _stream(), tag="composite_fwd")
         ctx.save_for_backward(raw_c, z_c, d_c, nz if nz is not None else torch.empty(0, device=dev))
         ctx.cfg = (float(noise_std), int(white_bkgd), nz is not None)
+        ctx.rng = rng
         return rgb, disp, acc, w, depth
 
     @staticmethod
@@ -100,21 +197,28 @@ class _Composite(torch.autograd.Function):
         N, S, Cc = raw_c.shape
         gs = [None if g is None else _f32(g, "raw2outputs.backward") for g in (g_rgb, g_disp, g_acc, g_w, g_depth)]
         d_raw = torch.empty_like(raw_c)
-        L.call("dln_composite_bwd", raw_c.data_ptr(), Cc, z_c.data_ptr(), d_c.data_ptr(),
-                                          nz.data_ptr() if has_noise else None, noise_std, white,
-                                          _ptr(gs[0]), _ptr(gs[1]), _ptr(gs[2]), _ptr(gs[3]), _ptr(gs[4]),
-                                          d_raw.data_ptr(), N, S, _stream(), tag="composite_bwd")
-        return d_raw, None, None, None, None, None
+        if ctx.rng is not None:          # the same (seed, base + offset) as the forward: the draws are regenerated
+            L.call("dln_composite_bwd_rng", raw_c.data_ptr(), Cc, z_c.data_ptr(), d_c.data_ptr(), ctx.rng[0].ptr(),
+                   int(ctx.rng[1]), noise_std, white, _ptr(gs[0]), _ptr(gs[1]), _ptr(gs[2]), _ptr(gs[3]), _ptr(gs[4]),
+                   d_raw.data_ptr(), N, S, _stream(), tag="composite_bwd")
+        else:
+            L.call("dln_composite_bwd", raw_c.data_ptr(), Cc, z_c.data_ptr(), d_c.data_ptr(),
+                   nz.data_ptr() if has_noise else None, noise_std, white,
+                   _ptr(gs[0]), _ptr(gs[1]), _ptr(gs[2]), _ptr(gs[3]), _ptr(gs[4]),
+                   d_raw.data_ptr(), N, S, _stream(), tag="composite_bwd")
+        return d_raw, None, None, None, None, None, None
 
 
 def composite(raw: Tensor, z_vals: Tensor, rays_d: Tensor, noise: Optional[Tensor], noise_std: float,
-              white_bkgd: bool):
-    """(rgb_map, disp_map, acc_map, weights, depth_map); `noise` are UNSCALED N(0,1) draws or None."""
+              white_bkgd: bool, rng: Rng = None):
+    """(rgb_map, disp_map, acc_map, weights, depth_map); `noise` are UNSCALED N(0,1) draws or None; with ``rng`` (and
+    no ``noise``) the draws are generated in-kernel -- the backward regenerates them, so the device-side ``base`` of
+    the state must not be advanced between the two (the drop-in route names its tensors by offset only)."""
     if raw.dim() != 3 or raw.shape[-1] < 4:
         raise ValueError("raw must be [N, S, >=4]")
     if raw.shape[1] > 256:
         raise NotImplementedError("composite kernels handle up to 256 samples per ray")
-    return _Composite.apply(raw, z_vals, rays_d, noise, noise_std, white_bkgd)
+    return _Composite.apply(raw, z_vals, rays_d, noise, noise_std, white_bkgd, rng if noise_std > 0. else None)
 
 
 class _SampleSum(torch.autograd.Function):
@@ -163,12 +267,26 @@ def semantic_ce(sem: Tensor, target: Tensor, n_rgb: int, coef: float, loss_sum: 
 def composite_bwd_fused_loss(raw: Tensor, z_vals: Tensor, rays_d: Tensor, noise: Optional[Tensor], noise_std: float,
                              white_bkgd: bool, target_rgb: Optional[Tensor], target_depth: Optional[Tensor],
                              ray_weights: Optional[Tensor], n_rgb: int, coef_rgb: float, coef_depth: float,
-                             depth_mode: int, depth_norm: float, loss_sums: Tensor) -> Tensor:
-    """north_star part 5: d raw with the RGB-MSE / LiDAR-depth loss gradient formed in-kernel."""
+                             depth_mode: int, depth_norm: float, loss_sums: Tensor, rng: Rng = None,
+                             coefs_dev: Optional[Tensor] = None) -> Tensor:
+    """north_star part 5: d raw with the RGB-MSE / LiDAR-depth loss gradient formed in-kernel.  ``coefs_dev`` (device
+    fp32 [coef_rgb, coef_depth, depth_norm]) replaces the three by-value scalars; ``rng`` draws the density noise
+    in-kernel (the same tensor name as the forward compositing of this pass)."""
     raw_c, z_c, d_c = _f32(raw, "fused_loss"), _f32(z_vals, "fused_loss"), _f32(rays_d, "fused_loss")
     N, S, Cc = raw_c.shape
     nz = None if noise is None else _f32(noise, "fused_loss")
     d_raw = torch.empty_like(raw_c)
+    if nz is not None or not noise_std > 0.:
+        rng = None
+    if rng is not None or coefs_dev is not None:
+        if coefs_dev is None:
+            coefs_dev = torch.tensor([coef_rgb, coef_depth, depth_norm], dtype=torch.float32).to(raw_c.device)
+        L.call("dln_composite_bwd_fused_loss_dev", raw_c.data_ptr(), Cc, z_c.data_ptr(), d_c.data_ptr(), _ptr(nz),
+               rng[0].ptr() if rng is not None else None, int(rng[1]) if rng is not None else 0, float(noise_std),
+               int(white_bkgd), _ptr(target_rgb), _ptr(target_depth), _ptr(ray_weights), int(n_rgb),
+               coefs_dev.data_ptr(), int(depth_mode), loss_sums.data_ptr(), d_raw.data_ptr(), N, S, _stream(),
+               tag="composite_bwd_fused_loss")
+        return d_raw
     L.call("dln_composite_bwd_fused_loss", 
         raw_c.data_ptr(), Cc, z_c.data_ptr(), d_c.data_ptr(), _ptr(nz), float(noise_std), int(white_bkgd),
         _ptr(target_rgb), _ptr(target_depth), _ptr(ray_weights), int(n_rgb), float(coef_rgb), float(coef_depth),
@@ -178,8 +296,9 @@ def composite_bwd_fused_loss(raw: Tensor, z_vals: Tensor, rays_d: Tensor, noise:
 
 # ------------------------------------------------------------------------------------------------
 def sample_pdf(bins: Tensor, weights: Tensor, n_samples: int, u: Optional[Tensor] = None,
-               return_debug: bool = False):
-    """sample_pdf, run_nerf_helpers.py:497-540.  u=None -> deterministic linspace (det=True)."""
+               return_debug: bool = False, rng: Rng = None):
+    """sample_pdf, run_nerf_helpers.py:497-540.  u=None -> deterministic linspace (det=True) unless ``rng`` (the
+    uniforms are then drawn in-kernel)."""
     b, w = _f32(bins, "sample_pdf"), _f32(weights, "sample_pdf")
     lead = b.shape[:-1]
     B = b.shape[-1]
@@ -193,8 +312,12 @@ def sample_pdf(bins: Tensor, weights: Tensor, n_samples: int, u: Optional[Tensor
     out = torch.empty(N, n_samples, device=b.device)
     cdf = torch.empty(N, B, device=b.device) if return_debug else None
     inds = torch.empty(N, n_samples, device=b.device, dtype=torch.int64) if return_debug else None
-    L.call("dln_sample_pdf", b2.data_ptr(), B, 0, w2.data_ptr(), B - 1, B, _ptr(uu), n_samples, out.data_ptr(),
-                                   None, 0, None, _ptr(cdf), _ptr(inds), N, _stream(), tag="sample_pdf")
+    if rng is not None and uu is None:
+        L.call("dln_sample_pdf_rng", b2.data_ptr(), B, 0, w2.data_ptr(), B - 1, B, rng[0].ptr(), int(rng[1]), n_samples,
+               out.data_ptr(), None, 0, None, _ptr(cdf), _ptr(inds), N, _stream(), tag="sample_pdf")
+    else:
+        L.call("dln_sample_pdf", b2.data_ptr(), B, 0, w2.data_ptr(), B - 1, B, _ptr(uu), n_samples, out.data_ptr(),
+               None, 0, None, _ptr(cdf), _ptr(inds), N, _stream(), tag="sample_pdf")
     out = out.reshape(*lead, n_samples)
     if return_debug:
         return out, cdf.reshape(*lead, B), inds.reshape(*lead, n_samples)
@@ -202,7 +325,7 @@ def sample_pdf(bins: Tensor, weights: Tensor, n_samples: int, u: Optional[Tensor
 
 
 def importance_resample(z_vals: Tensor, weights: Tensor, n_importance: int, u: Optional[Tensor] = None,
-                        return_debug: bool = False):
+                        return_debug: bool = False, rng: Rng = None):
     """run_nerf.py:632-636 in one kernel: bins = midpoints of z_vals, pdf from weights[..., 1:-1],
     CDF inversion, and the sorted union with z_vals.  Returns (z_samples, z_merged)."""
     z, w = _f32(z_vals, "importance_resample"), _f32(weights, "importance_resample")
@@ -214,8 +337,14 @@ def importance_resample(z_vals: Tensor, weights: Tensor, n_importance: int, u: O
     zm = torch.empty(N, S + n_importance, device=z.device)
     cdf = torch.empty(N, S - 1, device=z.device) if return_debug else None
     inds = torch.empty(N, n_importance, device=z.device, dtype=torch.int64) if return_debug else None
-    L.call("dln_sample_pdf", z.data_ptr(), S, 1, w.data_ptr() + 4, S, S - 1, _ptr(uu), n_importance,
-                                   zs.data_ptr(), z.data_ptr(), S, zm.data_ptr(), _ptr(cdf), _ptr(inds), N, _stream(), tag="importance_resample")
+    if rng is not None and uu is None:
+        L.call("dln_sample_pdf_rng", z.data_ptr(), S, 1, w.data_ptr() + 4, S, S - 1, rng[0].ptr(), int(rng[1]),
+               n_importance, zs.data_ptr(), z.data_ptr(), S, zm.data_ptr(), _ptr(cdf), _ptr(inds), N, _stream(),
+               tag="importance_resample")
+    else:
+        L.call("dln_sample_pdf", z.data_ptr(), S, 1, w.data_ptr() + 4, S, S - 1, _ptr(uu), n_importance,
+               zs.data_ptr(), z.data_ptr(), S, zm.data_ptr(), _ptr(cdf), _ptr(inds), N, _stream(),
+               tag="importance_resample")
     if return_debug:
         return zs, zm, cdf, inds
     return zs, zm

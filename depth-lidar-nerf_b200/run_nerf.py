@@ -188,12 +188,15 @@ def get_rays(H, W, focal, c2w):
     return rays_o, rays_d
 
 
+@ops.on_device_of(0)
 def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False, lindisp=False, perturb=0.,
                 N_importance=0, network_fine=None, white_bkgd=False, raw_noise_std=0., verbose=False, pytest=False,
                 sigma_loss=None, semantic_loss=False, _rng=None):
-    """run_nerf.py:520-675.  Random draws happen in the reference's order on the rays' device:
-    rand[N,S] (jitter) -> randn[N,S] (coarse density noise) -> rand[N,Ni] (u) -> randn[N,S+Ni].
-    ``_rng`` (private, tests only) injects those four tensors: dict(t_rand, noise0, u, noise1)."""
+    """run_nerf.py:520-675.  The reference's four random tensors -- rand[N,S] (jitter, :585), randn[N,S] (coarse
+    density noise, helpers:565), rand[N,Ni] (u, helpers:509), randn[N,S+Ni] -- are drawn INSIDE the consuming kernels
+    (Philox4x32-10 keyed by torch's seed; tensor k of call c is named by the offset 4c + k, and the compositing
+    backward regenerates its noise from the same name).  ``_rng`` (private, tests only) injects tensors instead:
+    dict(t_rand, noise0, u, noise1); ``_rng['state']`` = an ``ops.RngState`` to draw from."""
     if sigma_loss is not None:
         raise NotImplementedError("sigma_loss reads an undefined variable in the reference train loop "
                                   "(run_nerf.py:1527) and is not part of the hot path")
@@ -205,11 +208,14 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
     rays_o, rays_d = rb[:, 0:3], rb[:, 3:6]
     viewdirs = rb[:, -3:] if rb.shape[-1] > 9 else None
     rng = _rng or {}
+    gen = rng.get("state") or ops.default_rng(dev, 0)
+    off = gen.next_offsets(4)
 
-    def draw(name, kind, shape):
+    def draw(name, k):
+        """(injected tensor | None, in-kernel generator reference | None)"""
         if name in rng:
-            return rng[name]
-        return (torch.rand if kind == "u" else torch.randn)(shape, device=dev)
+            return rng[name], None
+        return None, (gen, off + k)
 
     def query(net, z):
         """(raw for compositing, per-ray semantic logits | None, raw as the reference returns it).  Fused route: the
@@ -229,23 +235,23 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
         raw = network_query_fn(pts, viewdirs, net)
         return raw, (ops.sample_sum(raw, 4) if semantic_loss else None), raw
 
-    def composite(raw, z, noise_name):
-        noise = draw(noise_name, "n", (N, z.shape[1])) if raw_noise_std > 0. else None
-        return ops.composite(raw, z, rays_d, noise, float(raw_noise_std), bool(white_bkgd))
+    def composite(raw, z, noise_name, k):
+        noise, g = draw(noise_name, k) if raw_noise_std > 0. else (None, None)
+        return ops.composite(raw, z, rays_d, noise, float(raw_noise_std), bool(white_bkgd), rng=g)
 
-    t_rand = draw("t_rand", "u", (N, N_samples)) if perturb > 0. else None
-    z_vals = ops.stratified_z(rb, N_samples, t_rand, lindisp)
+    t_rand, g = draw("t_rand", 0) if perturb > 0. else (None, None)
+    z_vals = ops.stratified_z(rb, N_samples, t_rand, lindisp, rng=g)
     raw, sem, raw_ret = query(network_fn, z_vals)
-    rgb_map, disp_map, acc_map, weights, depth_map = composite(raw, z_vals, "noise0")
+    rgb_map, disp_map, acc_map, weights, depth_map = composite(raw, z_vals, "noise0", 1)
 
     ret = {}
     if N_importance > 0:
         rgb_map_0, disp_map_0, acc_map_0, depth_map0, sem0 = rgb_map, disp_map, acc_map, depth_map, sem
-        u = draw("u", "u", (N, N_importance)) if perturb != 0. else None        # det = (perturb == 0)
-        z_samples, z_vals = ops.importance_resample(z_vals, weights.detach(), N_importance, u)
+        u, g = draw("u", 2) if perturb != 0. else (None, None)                  # det = (perturb == 0)
+        z_samples, z_vals = ops.importance_resample(z_vals, weights.detach(), N_importance, u, rng=g)
         run_fn = network_fn if network_fine is None else network_fine
         raw, sem, raw_ret = query(run_fn, z_vals)
-        rgb_map, disp_map, acc_map, weights, depth_map = composite(raw, z_vals, "noise1")
+        rgb_map, disp_map, acc_map, weights, depth_map = composite(raw, z_vals, "noise1", 3)
     ret.update(rgb_map=rgb_map, disp_map=disp_map, acc_map=acc_map, depth_map=depth_map)
     if retraw:
         ret['raw'] = raw_ret

@@ -76,9 +76,10 @@ class _MLP(torch.autograd.Function):
     only: on the reference's training path the network inputs never require grad."""
 
     @staticmethod
-    def forward(ctx, net: "NeRF", mode, a, b, P, *params):
-        train = any(ctx.needs_input_grad[5:])
-        out, saved = net._run_forward(mode, a, b, P, keep=train)
+    def forward(ctx, net: "NeRF", mode, a, b, P, keep, *params):
+        # `keep` is decided by the caller, where the grad mode is still visible: inside forward() grad mode is
+        # off and needs_input_grad reports requires_grad of the parameters even under torch.no_grad()
+        out, saved = net._run_forward(mode, a, b, P, keep=keep)
         ctx.net, ctx.saved, ctx.P = net, saved, P
         return out
 
@@ -87,7 +88,7 @@ class _MLP(torch.autograd.Function):
         net: "NeRF" = ctx.net
         grads = net._run_backward(d_out, ctx.saved, ctx.P)
         ctx.saved = None
-        return (None, None, None, None, None) + tuple(grads)
+        return (None, None, None, None, None, None) + tuple(grads)
 
 
 class _MLPSem(torch.autograd.Function):
@@ -96,9 +97,8 @@ class _MLPSem(torch.autograd.Function):
     point); ``point_logits`` only fills the semantic columns of a returned ``raw`` and carries no gradient."""
 
     @staticmethod
-    def forward(ctx, net: "NeRF", mode, a, b, P, S, want_points, *params):
-        train = any(ctx.needs_input_grad[7:])
-        out, saved, sem, pts = net._run_forward(mode, a, b, P, keep=train, sem_group=S, sem_points=want_points)
+    def forward(ctx, net: "NeRF", mode, a, b, P, S, want_points, keep, *params):
+        out, saved, sem, pts = net._run_forward(mode, a, b, P, keep=keep, sem_group=S, sem_points=want_points)
         ctx.net, ctx.saved, ctx.P = net, saved, P
         if pts is None:
             pts = out.new_empty(0)
@@ -113,7 +113,7 @@ class _MLPSem(torch.autograd.Function):
         net: "NeRF" = ctx.net
         grads = net._run_backward(d_out, ctx.saved, ctx.P, d_sem=d_sem)
         ctx.saved = None
-        return (None,) * 7 + tuple(grads)
+        return (None,) * 8 + tuple(grads)
 
 
 class NeRF(nn.Module):
@@ -322,7 +322,13 @@ class NeRF(nn.Module):
             grads.append(gflat[o: o + p.numel()].view(p.shape) if p.requires_grad else None)
         return grads
 
+    def _keep(self) -> bool:
+        """Whether a forward pass must write the activation stash / ReLU masks: only when autograd will come back
+        for the parameter gradients."""
+        return torch.is_grad_enabled() and any(p.requires_grad for p in self._ordered_params())
+
     # ------------------------------------------------------------------ public interface
+    @ops.on_device_of(1)
     def forward(self, x: Tensor) -> Tensor:
         """(:113-145) x[..., input_ch + input_ch_views] -> [..., 4] (view dirs) or [..., output_ch]."""
         n_in = self.input_ch + (self.input_ch_views if self.use_viewdirs else 0)
@@ -331,12 +337,13 @@ class NeRF(nn.Module):
         xs = ops._f32(x, "NeRF.forward").reshape(-1, x.shape[-1])
         P = xs.shape[0]
         if self.sem_K:                  # [rgb, alpha, semantic logits] (:139-140); S = 1: per-point logits
-            out, sem, _ = _MLPSem.apply(self, "x", xs, None, P, 1, False, *self._ordered_params())
+            out, sem, _ = _MLPSem.apply(self, "x", xs, None, P, 1, False, self._keep(), *self._ordered_params())
             out = torch.cat([out, sem], -1)
         else:
-            out = _MLP.apply(self, "x", xs, None, P, *self._ordered_params())
+            out = _MLP.apply(self, "x", xs, None, P, self._keep(), *self._ordered_params())
         return out.reshape(*x.shape[:-1], out.shape[-1])
 
+    @ops.on_device_of(1)
     def forward_rays(self, ray_batch: Tensor, z_vals: Tensor, semantic: bool = False, point_logits: bool = False):
         """Fused path of run_nerf.py:595 + run_network (:60-74) + forward: points o + d*z are formed,
         encoded (positions per sample, the unit view direction once per ray) and pushed through the MLP
@@ -353,10 +360,10 @@ class NeRF(nn.Module):
             raise RuntimeError("this NeRF has no semantic head (semantic_num_classes / use_viewdirs)")
         if semantic or point_logits:
             out, sem, pts = _MLPSem.apply(self, "rays", rb, z, N * S, S if semantic else 0, bool(point_logits),
-                                          *self._ordered_params())
+                                          self._keep(), *self._ordered_params())
             return (out.reshape(N, S, 4), sem if semantic else None,
                     pts.reshape(N, S, -1) if point_logits else None)
-        out = _MLP.apply(self, "rays", rb, z, N * S, *self._ordered_params())
+        out = _MLP.apply(self, "rays", rb, z, N * S, self._keep(), *self._ordered_params())
         return out.reshape(N, S, out.shape[-1])
 
     def load_weights_from_keras(self, weights):
@@ -398,34 +405,38 @@ def ndc_rays(H, W, focal, near, rays_o, rays_d):
 # --------------------------------------------------------------------------------------------------
 # Hierarchical sampling (run_nerf_helpers.py:497-540)
 # --------------------------------------------------------------------------------------------------
+@ops.on_device_of(0)
 def sample_pdf(bins, weights, N_samples, det=False, pytest=False):
-    """Same signature as the reference.  Draw order is unchanged: one torch.rand([..., N_samples]) on the
-    inputs' device unless det.  The result carries no gradient (the reference detaches it at
-    run_nerf.py:634 before any use)."""
+    """Same signature as the reference.  Unless det, the uniforms u[..., N_samples] (:509) are drawn inside the
+    kernel (Philox, seeded from torch's seed) instead of by torch.rand.  The result carries no gradient (the reference
+    detaches it at run_nerf.py:634 before any use)."""
     lead = list(bins.shape[:-1])
-    u = None
+    u, rng = None, None
     if not det:
-        u = torch.rand(lead + [N_samples], device=bins.device)
+        st = ops.default_rng(bins.device, 2)
+        rng = (st, st.next_offsets(1))
     if pytest:
         np.random.seed(0)
         u = None if det else torch.tensor(np.random.rand(*(lead + [N_samples])), dtype=torch.float32,
                                          device=bins.device)
-    return ops.sample_pdf(bins.detach(), weights.detach(), N_samples, u)
+    return ops.sample_pdf(bins.detach(), weights.detach(), N_samples, u, rng=rng)
 
 
 # --------------------------------------------------------------------------------------------------
 # Compositing (run_nerf_helpers.py:542-595)
 # --------------------------------------------------------------------------------------------------
+@ops.on_device_of(0)
 def raw2outputs(raw, z_vals, rays_d, raw_noise_std=0, white_bkgd=False, pytest=False, semantic_loss=False):
     """Returns (rgb_map, disp_map, acc_map, weights, depth_map[, semantic_class_preds]), differentiable w.r.t.
     raw.  semantic_loss: the per-ray logits are the UNWEIGHTED sum of raw[..., 4:] over the samples (:586-593)."""
-    noise = None
+    noise, rng = None, None
     if raw_noise_std > 0.:
-        noise = torch.randn(raw[..., 3].shape, device=raw.device)
+        st = ops.default_rng(raw.device, 2)       # N(0,1) drawn in-kernel (:565), regenerated by the backward
+        rng = (st, st.next_offsets(1))
         if pytest:       # the reference's hook draws UNIFORM numbers here (:567-571)
             np.random.seed(0)
             noise = torch.tensor(np.random.rand(*list(raw[..., 3].shape)), dtype=torch.float32, device=raw.device)
-    maps = ops.composite(raw, z_vals, rays_d, noise, float(raw_noise_std), bool(white_bkgd))
+    maps = ops.composite(raw, z_vals, rays_d, noise, float(raw_noise_std), bool(white_bkgd), rng=rng)
     if semantic_loss:
         return tuple(maps) + (ops.sample_sum(raw, 4),)
     return maps

@@ -54,11 +54,13 @@ def shard_ray_batch(batch_rays: Tensor, target_s: Tensor, target_depth: Optional
     return rays, target_s[a0:a1], td, rw, a1 - a0
 
 
-def allreduce_gradients(params: Sequence[Tensor], world: int, group=None) -> None:
+def allreduce_gradients(params: Sequence[Tensor], world: int, group=None, average: bool = True) -> None:
     """Average the gradients over the ranks: ONE collective per flat gradient buffer (the kernels hand every
     network's gradients back as views of one fp32 buffer, 2.4 MB for an 8x256 net), issued in place -- on
     NVLink 5 / NVSwitch this is latency-bound, so few large buckets beat many small ones and no staging copy is
-    needed.  Gradients that do not share a buffer (foreign parameters) go through one concatenated bucket."""
+    needed.  Only the span of the buffer the parameters' gradients cover is reduced (the kernels' scratch tail behind
+    them is rank-local).  Gradients that do not share a buffer (foreign parameters) go through one concatenated
+    bucket.  ``average=False``: plain sum (the caller folded 1/world into its loss coefficients)."""
     if world <= 1:
         return
     import torch.distributed as dist
@@ -68,17 +70,22 @@ def allreduce_gradients(params: Sequence[Tensor], world: int, group=None) -> Non
     bases, loose = {}, []
     for g in grads:
         b = g._base
-        if b is not None and b.is_contiguous() and b.dtype == g.dtype:
-            bases[id(b)] = b
+        if b is not None and b.is_contiguous() and b.dtype == g.dtype and b.dim() == 1:
+            lo = g.storage_offset() - b.storage_offset()
+            ent = bases.setdefault(id(b), [b, lo, lo + g.numel()])
+            ent[1], ent[2] = min(ent[1], lo), max(ent[2], lo + g.numel())
         else:
             loose.append(g)
-    for b in bases.values():
-        dist.all_reduce(b, op=dist.ReduceOp.SUM, group=group)
-        b.div_(world)
+    for b, lo, hi in bases.values():
+        span = b[lo:hi]
+        dist.all_reduce(span, op=dist.ReduceOp.SUM, group=group)
+        if average:
+            span.div_(world)
     if loose:
         flat = torch.cat([g.reshape(-1) for g in loose])
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-        flat.div_(world)
+        if average:
+            flat.div_(world)
         o = 0
         for g in loose:
             g.copy_(flat[o:o + g.numel()].view_as(g))
@@ -165,6 +172,7 @@ def _side_stream(dev) -> "torch.cuda.Stream":
     return _SIDE_STREAMS[dev]
 
 
+@ops.on_device_of(3)
 @torch.no_grad()
 def train_step(H, W, focal, batch_rays: Tensor, target_s: Tensor, target_depth: Optional[Tensor], n_rgb: int,
                network_fn: NeRF, network_fine: NeRF, N_samples: int = 64, N_importance: int = 64,
@@ -174,7 +182,9 @@ def train_step(H, W, focal, batch_rays: Tensor, target_s: Tensor, target_depth: 
                coarse_loss: bool = True, world_size: int = 1, group=None, ray_chunk: Optional[int] = None,
                overlap_coarse_backward: bool = True, coarse_sms: Optional[int] = None,
                target_semantic: Optional[Tensor] = None, semantic_lambda: float = 0.,
-               _rng: Optional[Dict[str, Tensor]] = None, _force_pack: bool = False) -> Dict[str, Tensor]:
+               rng_state: Optional["ops.RngState"] = None, global_counts=None,
+               _rng: Optional[Dict[str, Tensor]] = None, _force_pack: bool = False,
+               _coefs: Optional[Tensor] = None, _sem_den: Optional[float] = None) -> Dict[str, Tensor]:
     """render + loss + backward for one ray batch; fills ``.grad`` of both networks (averaged over
     ``world_size`` ranks when > 1) and returns the loss terms as 0-d tensors (no host sync).
 
@@ -188,8 +198,20 @@ def train_step(H, W, focal, batch_rays: Tensor, target_s: Tensor, target_depth: 
     come from one pass over the kept last-trunk-layer activations, the cross-entropy gradient is formed in one small
     kernel and enters the dgrad chain as one fp32 row per ray.
 
-    Random draws follow the reference's order (rand jitter, randn coarse noise, rand u, randn fine noise);
-    ``_rng`` (tests) injects them."""
+    The reference's four random tensors (rand jitter, randn coarse noise, rand u, randn fine noise) are drawn inside
+    the consuming kernels from ``rng_state`` (default: a per-device Philox state seeded from torch's seed); the
+    state's device-side counter is advanced in-stream at the end of the step, so a captured graph draws fresh
+    numbers on every replay.  ``_rng`` (tests) injects tensors instead.
+
+    ``world_size`` > 1: 1/world_size is folded into the loss-gradient coefficients and the gradients are SUMMED over
+    the ranks (one all-reduce per network; the coarse network's is issued from the side stream as soon as its
+    backward finishes, under the fine backward).  ``global_counts`` = (n_rgb, n_depth) of the whole batch makes the
+    per-rank means exact when the classes do not divide evenly over the ranks.  ``depth_mode='weighted_norm'``
+    normalises by max(target_depth) taken on the device (all-reduced MAX over the ranks): no host sync.
+
+    ``_coefs`` (GraphedTrainStep): device fp32[8] = [coef_rgb, coef_depth, depth_norm, depth_lambda*depth_importance,
+    coef_rgb(coarse), 0, 1, -] (``loss_coefs``) read by the kernels instead of by-value scalars, so a replayed graph
+    follows the depth_importance schedule of run_nerf.py:1527-1532."""
     if network_fine is None or N_importance <= 0:
         raise NotImplementedError("train_step implements the coarse + fine configuration every shipped config uses")
     rb = pack_ray_batch(H, W, focal, batch_rays, ndc, near, far, network_fn.use_viewdirs)
@@ -198,23 +220,32 @@ def train_step(H, W, focal, batch_rays: Tensor, target_s: Tensor, target_depth: 
     n_dep = N - n_rgb
     mode = _DEPTH_MODES[depth_mode]
     use_depth = target_depth is not None and n_dep > 0 and depth_lambda != 0.
-    depth_norm = float(target_depth.max()) if (use_depth and mode == 2) else 1.0
-    coef_rgb = 2.0 / (3.0 * max(n_rgb, 1))
-    coef_dep = 2.0 * depth_lambda * depth_importance / max(n_dep, 1) if use_depth else 0.0
+    # per-rank mean coefficients; with world_size > 1 the all-reduce SUMS, so 1/world is folded in here -- and with
+    # the global class counts the sum over the ranks is exactly the mean over the whole batch
+    den_rgb, den_dep = _denominators(n_rgb, n_dep, world_size, global_counts)
     use_sem = target_semantic is not None and semantic_lambda != 0. and n_rgb > 0
     if use_sem and not (network_fn.sem_K and network_fine.sem_K):
         raise RuntimeError("target_semantic needs networks built with semantic_num_classes")
-    coef_sem = semantic_lambda / max(n_rgb, 1)
+    coef_sem = semantic_lambda / (_sem_den or den_rgb)
     tsem = target_semantic.to(device=dev, dtype=torch.int64) if use_sem else None
     sums = torch.zeros(8, device=dev)
     tgt = ops._f32(target_s, "train_step")
     tdep = ops._f32(target_depth, "train_step") if use_depth else None
+    if _coefs is not None:
+        coefs = _coefs
+    else:
+        coefs = torch.tensor(loss_coefs(den_rgb, den_dep, depth_lambda if use_depth else 0., depth_importance,
+                                        coarse_loss), dtype=torch.float32).to(dev)
+        if use_depth and mode == 2:          # max over the WHOLE batch (run_nerf.py:1518), kept on the device
+            coefs[2:3] = batch_depth_max(tdep, world_size, group)
     rw = ops._f32(ray_weights, "train_step") if (use_depth and ray_weights is not None) else None
     S1 = N_samples + N_importance
     if ray_chunk is None:
         ray_chunk = default_ray_chunk(network_fn, network_fine, N_samples, N_importance)
     n_chunks = max(1, -(-N // max(int(ray_chunk), 1)))
     gacc = [torch.zeros(net._plan.n_flat, device=dev, dtype=torch.float32) for net in (network_fn, network_fine)]
+    gen = rng_state if rng_state is not None else ops.default_rng(dev, 1)
+    main = torch.cuda.current_stream(dev)
 
     for c in range(n_chunks):
         if n_chunks == 1:
@@ -234,66 +265,102 @@ def train_step(H, W, focal, batch_rays: Tensor, target_s: Tensor, target_depth: 
         Nc = rb_c.shape[0]
         rays_d = rb_c[:, 3:6].contiguous()
 
-        def draw(name, kind, shape):
+        def draw(name, k):
+            """(injected tensor | None, in-kernel generator reference | None): tensor k of chunk c"""
             if name in rng:
-                return rng[name]
-            return (torch.rand if kind == "u" else torch.randn)(shape, device=dev)
+                return rng[name], None
+            return None, (gen, 4 * c + k)
 
-        t_rand = draw("t_rand", "u", (Nc, N_samples)) if perturb > 0. else None
-        z0 = ops.stratified_z(rb_c, N_samples, t_rand, lindisp)
+        t_rand, g_t = draw("t_rand", 0) if perturb > 0. else (None, None)
+        z0 = ops.stratified_z(rb_c, N_samples, t_rand, lindisp, rng=g_t)
         sem_kw = lambda S: dict(sem_group=S) if use_sem else {}          # noqa: E731
         raw0, saved0, *sem0 = network_fn._run_forward("rays", rb_c, z0, Nc * N_samples, keep=True,
                                                       force_pack=_force_pack and c == 0, **sem_kw(N_samples))
         raw0 = raw0.view(Nc, N_samples, -1)
-        noise0 = draw("noise0", "n", (Nc, N_samples)) if raw_noise_std > 0. else None
+        noise0, g_n0 = draw("noise0", 1) if raw_noise_std > 0. else (None, None)
         rgb0, disp0, acc0, w0, depth0 = ops.composite(raw0, z0, rays_d, noise0, float(raw_noise_std),
-                                                      bool(white_bkgd))
-        u = draw("u", "u", (Nc, N_importance)) if perturb != 0. else None
-        z_samples, z1 = ops.importance_resample(z0, w0, N_importance, u)
+                                                      bool(white_bkgd), rng=g_n0)
+        u, g_u = draw("u", 2) if perturb != 0. else (None, None)
+        z_samples, z1 = ops.importance_resample(z0, w0, N_importance, u, rng=g_u)
         raw1, saved1, *sem1 = network_fine._run_forward("rays", rb_c, z1, Nc * S1, keep=True,
                                                         force_pack=_force_pack and c == 0, **sem_kw(S1))
         raw1 = raw1.view(Nc, S1, -1)
-        noise1 = draw("noise1", "n", (Nc, S1)) if raw_noise_std > 0. else None
+        noise1, g_n1 = draw("noise1", 3) if raw_noise_std > 0. else (None, None)
         # fine pass: colour loss on the RGB rays, depth loss on the depth rays (run_nerf.py:1461, :1500-1524)
         d_raw1 = ops.composite_bwd_fused_loss(raw1, z1, rays_d, noise1, raw_noise_std, white_bkgd, tgt_c, tdep_c,
-                                              rw_c, nr_c, coef_rgb, coef_dep, mode, depth_norm, sums[0:2])
+                                              rw_c, nr_c, 0., 0., mode, 1., sums[0:2], rng=g_n1, coefs_dev=coefs[0:3])
         d_sem1 = ops.semantic_ce(sem1[0], tsem_c, nr_c, coef_sem, sums[4:5]) if use_sem else None
         side = None
         if coarse_loss or use_sem:
             # coarse pass: colour loss only (run_nerf.py:1759-1761); depth_map0 is unsupervised.  It depends on the
             # coarse forward alone, so it runs on a second stream next to the fine backward: its CTAs fill the SMs
             # the persistent fine-net kernels leave idle at their tails and under the HBM-bound wgrad.
-            main = torch.cuda.current_stream(dev)
             side = _side_stream(dev) if overlap_coarse_backward else main
             if side is not main:
                 side.wait_stream(main)
             with torch.cuda.stream(side):
                 d_raw0 = ops.composite_bwd_fused_loss(raw0, z0, rays_d, noise0, raw_noise_std, white_bkgd, tgt_c,
-                                                      None, None, nr_c, coef_rgb if coarse_loss else 0.0, 0.0, 0, 1.0,
-                                                      sums[2:4])
+                                                      None, None, nr_c, 0., 0., 0, 1., sums[2:4], rng=g_n0,
+                                                      coefs_dev=coefs[4:7])
                 # the coarse logits are supervised too (run_nerf.py:1545-1546), whatever no_coarse says
                 d_sem0 = ops.semantic_ce(sem0[0], tsem_c, nr_c, coef_sem, sums[5:6]) if use_sem else None
                 grads_c = network_fn._run_backward(d_raw0, saved0, Nc * N_samples, gflat=gacc[0],
                                                    sms=coarse_sms if side is not main else None, d_sem=d_sem0)
+                if world_size > 1 and c == n_chunks - 1:
+                    # the coarse network's gradients are complete: reduce them from the side stream, under the
+                    # fine backward still running on the main stream
+                    _assign_grads(network_fn, grads_c)
+                    allreduce_gradients(list(network_fn.parameters()), world_size, group, average=False)
         grads_f = network_fine._run_backward(d_raw1, saved1, Nc * S1, gflat=gacc[1], d_sem=d_sem1)
-        if side is not None and side is not torch.cuda.current_stream(dev):
-            torch.cuda.current_stream(dev).wait_stream(side)
+        if world_size > 1 and c == n_chunks - 1:
+            _assign_grads(network_fine, grads_f)
+            allreduce_gradients(list(network_fine.parameters()), world_size, group, average=False)
+        if side is not None and side is not main:
+            main.wait_stream(side)
         del saved1, d_raw1, raw1, saved0
+    if not _rng:
+        gen.advance(4 * n_chunks)             # the next step (or graph replay) names fresh tensors
     _assign_grads(network_fine, grads_f)
     if coarse_loss or use_sem:
         _assign_grads(network_fn, grads_c)
-    if world_size > 1:
-        allreduce_gradients(list(network_fn.parameters()) + list(network_fine.parameters()), world_size, group)
     img_loss = sums[0] / (3.0 * max(n_rgb, 1))
     img_loss0 = sums[2] / (3.0 * max(n_rgb, 1))
     depth_loss = sums[1] / max(n_dep, 1)
-    loss = img_loss + depth_lambda * depth_importance * depth_loss + (img_loss0 if coarse_loss else 0.)
+    loss = img_loss + coefs[3] * depth_loss + (img_loss0 if coarse_loss else 0.)
     out = {"img_loss": img_loss, "img_loss0": img_loss0, "depth_loss": depth_loss, "psnr": -10. * torch.log10(img_loss)}
     if use_sem:
         out["semantic_loss"], out["semantic_loss0"] = sums[4] / n_rgb, sums[5] / n_rgb
         loss = loss + semantic_lambda * (out["semantic_loss"] + out["semantic_loss0"])
     out["loss"] = loss
     return out
+
+
+def _denominators(n_rgb: int, n_dep: int, world_size: int, global_counts):
+    """Divisors of the two loss means as the gradient coefficients see them: the all-reduce SUMS over the ranks, so
+    they are the whole batch's class counts (given, or local count x world size)."""
+    if global_counts and world_size > 1:
+        return float(max(global_counts[0], 1)), float(max(global_counts[1], 1))
+    return float(max(n_rgb, 1) * world_size), float(max(n_dep, 1) * world_size)
+
+
+def loss_coefs(den_rgb: float, den_dep: float, depth_lambda: float, depth_importance: float, coarse_loss: bool):
+    """The 8 floats the fused-loss kernels read from device memory: fine pass [0:3] = d(mean sq. colour error) /
+    d(colour) scale 2/(3 n_rgb), depth scale 2 lambda importance / n_depth (run_nerf.py:1500-1536), depth_norm
+    (patched on the device for 'weighted_norm'); [3] = the depth term's weight in the reported loss; coarse pass
+    [4:7] = colour only (:1759-1761)."""
+    c_rgb = 2.0 / (3.0 * den_rgb)
+    return [c_rgb, 2.0 * depth_lambda * depth_importance / den_dep, 1.0, depth_lambda * depth_importance,
+            c_rgb if coarse_loss else 0.0, 0.0, 1.0, 0.0]
+
+
+def batch_depth_max(target_depth: Tensor, world_size: int = 1, group=None) -> Tensor:
+    """max(target_depth) over the whole batch (run_nerf.py:1518) as a 1-element device tensor; all ranks' shards
+    contribute (all-reduce MAX).  No host sync."""
+    m = torch.amax(target_depth.reshape(-1), 0, keepdim=True).float()
+    if world_size > 1:
+        import torch.distributed as dist
+        dist.all_reduce(m, op=dist.ReduceOp.MAX, group=group)
+    return m
 
 
 def _assign_grads(net: NeRF, grads) -> None:
@@ -304,31 +371,49 @@ def _assign_grads(net: NeRF, grads) -> None:
 
 class GraphedTrainStep:
     """``train_step`` captured once into a CUDA graph and replayed per iteration (static shapes: N_rand is fixed
-    in the reference's loop).  The ~25 launches of a step (our kernels, the four torch.rand/randn draws, the
-    weight re-pack, memsets) then cost one graph launch; the fp32 -> bf16 weight re-pack is part of the graph,
-    so an ``optimizer.step()`` between replays is picked up.  The gradient all-reduce (world_size > 1) runs
-    after the replay, outside the graph.
+    in the reference's loop).  The ~20 launches of a step (our kernels, the weight re-pack, memsets, the generator's
+    counter bump) then cost one graph launch; the fp32 -> bf16 weight re-pack is part of the graph, so an
+    ``optimizer.step()`` between replays is picked up; the random tensors are drawn in-kernel from a device-side
+    counter the graph itself advances, so every replay sees fresh numbers.  The loss coefficients live in a small
+    device tensor: ``__call__(..., depth_importance=...)`` follows the reference's per-iteration decay
+    (run_nerf.py:1527-1532), and ``depth_mode='weighted_norm'`` takes max(target_depth) on the device before the
+    replay.  With ``world_size`` > 1 the two gradient all-reduces are captured in the graph (NCCL supports stream
+    capture), the coarse network's under the fine backward; ``capture_allreduce=False`` runs them after the replay.
 
         step = GraphedTrainStep(H, W, focal, n_rays, n_rgb, net_c, net_f, depth_lambda=0.01, ...)
         out = step(batch_rays, target_s, target_depth)        # fills .grad, returns 0-d loss tensors
     """
 
     def __init__(self, H, W, focal, n_rays: int, n_rgb: int, network_fn: NeRF, network_fine: NeRF,
-                 world_size: int = 1, group=None, warmup: int = 3, **kw):
-        if kw.get("depth_mode") == "weighted_norm":
-            raise NotImplementedError("weighted_norm needs max(target_depth) on the host; use train_step")
+                 world_size: int = 1, group=None, warmup: int = 3, capture_allreduce: bool = True,
+                 global_counts=None, **kw):
         dev = next(network_fn.parameters()).device
         self.world_size, self.group = world_size, group
+        self.capture_allreduce = bool(capture_allreduce) and world_size > 1
         self.nets = (network_fn, network_fine)
         self.rays = torch.zeros(2, n_rays, 3, device=dev)
         self.rays[1, :, 2] = -1.0                                  # any valid direction for the warm-up passes
         self.target_s = torch.zeros(n_rgb, 3, device=dev)
-        self.target_depth = torch.zeros(n_rays - n_rgb, device=dev)
+        self.target_depth = torch.ones(n_rays - n_rgb, device=dev)
         self.ray_weights = torch.ones(n_rays - n_rgb, device=dev) if kw.pop("use_ray_weights", False) else None
         self.target_semantic = (torch.zeros(n_rgb, device=dev, dtype=torch.int64)
                                 if kw.get("semantic_lambda", 0.) != 0. else None)
+        self.rng = kw.pop("rng_state", None) or ops.RngState(dev, ops.default_rng(dev, 1).seed)
+        self._norm = kw.get("depth_mode") == "weighted_norm"
+        self._lambda = float(kw.get("depth_lambda", 0.))
+        self._importance = float(kw.pop("depth_importance", 1.))
+        self._coarse = bool(kw.get("coarse_loss", True))
+        ws = world_size if (self.capture_allreduce or world_size == 1) else 1
+        self._den = _denominators(n_rgb, n_rays - n_rgb, world_size, global_counts)
+        self.coefs = torch.tensor(loss_coefs(*self._den, self._lambda, self._importance, self._coarse),
+                                  dtype=torch.float32).to(dev)
         args = (H, W, focal, self.rays, self.target_s, self.target_depth, n_rgb, network_fn, network_fine)
-        kw = dict(kw, ray_weights=self.ray_weights, target_semantic=self.target_semantic, world_size=1, _force_pack=True)
+        kw = dict(kw, ray_weights=self.ray_weights, target_semantic=self.target_semantic, world_size=ws, group=group,
+                  global_counts=global_counts if ws > 1 else None, _force_pack=True, _coefs=self.coefs,
+                  rng_state=self.rng)
+        if ws == 1 and world_size > 1:
+            # all-reduce after the replay: the kernels still see the whole-batch divisors through `coefs`
+            kw["_sem_den"] = self._den[0]
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
@@ -340,8 +425,19 @@ class GraphedTrainStep:
             self.out = train_step(*args, **kw)
         self._grads = [(p, p.grad) for net in self.nets for p in net.parameters()]
 
+    def set_depth_importance(self, depth_importance: float) -> None:
+        """run_nerf.py:1527-1532: the decayed weight of the depth term, for the following replays (two scalar
+        fills on the stream, no host sync)."""
+        if depth_importance == self._importance:
+            return
+        self._importance = float(depth_importance)
+        c = loss_coefs(*self._den, self._lambda, self._importance, self._coarse)
+        self.coefs[1:2].fill_(c[1])
+        self.coefs[3:4].fill_(c[3])
+
     def __call__(self, batch_rays: Tensor, target_s: Tensor, target_depth: Optional[Tensor] = None,
-                 ray_weights: Optional[Tensor] = None, target_semantic: Optional[Tensor] = None) -> Dict[str, Tensor]:
+                 ray_weights: Optional[Tensor] = None, target_semantic: Optional[Tensor] = None,
+                 depth_importance: Optional[float] = None) -> Dict[str, Tensor]:
         self.rays.copy_(batch_rays, non_blocking=True)
         self.target_s.copy_(target_s, non_blocking=True)
         if target_depth is not None:
@@ -350,9 +446,13 @@ class GraphedTrainStep:
             self.ray_weights.copy_(ray_weights, non_blocking=True)
         if target_semantic is not None and self.target_semantic is not None:
             self.target_semantic.copy_(target_semantic, non_blocking=True)
+        if depth_importance is not None:
+            self.set_depth_importance(depth_importance)
+        if self._norm:
+            self.coefs[2:3] = batch_depth_max(self.target_depth, self.world_size, self.group)
         self.graph.replay()
         for p, g in self._grads:          # survive optimizer.zero_grad(set_to_none=True)
             p.grad = g
-        if self.world_size > 1:
-            allreduce_gradients([p for p, _ in self._grads], self.world_size, self.group)
+        if self.world_size > 1 and not self.capture_allreduce:
+            allreduce_gradients([p for p, _ in self._grads], self.world_size, self.group, average=False)
         return self.out

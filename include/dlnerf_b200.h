@@ -34,6 +34,26 @@ int dln_pack_rays(const float* rays_o, const float* rays_d, int N, int ndc, int 
 int dln_stratified_z(const float* rays, int ray_stride, const float* t_rand, float* z, int N, int S, int lindisp,
                      void* stream);
 
+/* ----------------------------------------------------------------------------------------------
+ * In-kernel random numbers.  The reference draws four tensors per render with torch.rand / torch.randn (stratified
+ * jitter run_nerf.py:585, density noise run_nerf_helpers.py:565 twice, sample_pdf's u :509).  The `_rng` entry points
+ * below generate those draws inside the consuming kernel with Philox4x32-10 instead of reading them from HBM:
+ *   rng_state : DEVICE pointer to two uint64 {seed, base}
+ *   rng_offset: by-value word added to `base`; the pair (seed, base + rng_offset) names one random tensor
+ * Element e of a tensor is component (e & 3) of Philox block (e >> 2) with counter (block, base + rng_offset) and key
+ * seed; uniforms are (x >> 8) * 2^-24 in [0, 1), normals are Box-Muller pairs of components (0,1) and (2,3).
+ * The compositing forward and backward of one pass must be given the same pair.  `base` lives on the device so that
+ * a captured CUDA graph draws fresh numbers on every replay: dln_rng_advance(state, inc) adds inc to it in-stream.
+ * dln_rng_fill writes the very draws a kernel would use as a tensor (kind 0 uniform row-major, 1 normal row-major,
+ * 2 uniform in the per-ray slot order of the <=64+64-sample fast path of dln_sample_pdf_rng) -- test infrastructure.
+ * -------------------------------------------------------------------------------------------- */
+int dln_rng_advance(unsigned long long* rng_state, unsigned long long inc, void* stream);
+int dln_rng_fill(const unsigned long long* rng_state, unsigned long long rng_offset, int kind, float* out,
+                 long long rows, int row_len, void* stream);
+/* dln_stratified_z with the jitter t_rand ~ U[0,1) drawn in-kernel (run_nerf.py:585). */
+int dln_stratified_z_rng(const float* rays, int ray_stride, const unsigned long long* rng_state,
+                         unsigned long long rng_offset, float* z, int N, int S, int lindisp, void* stream);
+
 /* Positional encoding gamma(x): [P,3] -> [P, 3+6L].  Replaces Embedder.embed, run_nerf_helpers.py:25-73. */
 int dln_posenc(const float* x, float* out, long long P, int L, void* stream);
 
@@ -65,6 +85,26 @@ int dln_composite_bwd_fused_loss(const float* raw, int raw_ch, const float* z_va
                                  float coef_depth, int depth_mode, float depth_norm, float* loss_sums, float* d_raw,
                                  int N, int S, void* stream);
 
+/* The three entry points above with the density noise N(0,1) drawn in-kernel (run_nerf_helpers.py:565) instead of read
+ * from `noise`; dln_composite_bwd_fused_loss_dev additionally takes its three loss scalars from DEVICE memory
+ * (coefs_dev = [coef_rgb, coef_depth, depth_norm], so a captured graph follows the depth_importance schedule of
+ * run_nerf.py:1527-1532 and a device-side max(target_depth)) and accepts either a noise tensor, or rng_state, or
+ * neither. */
+int dln_composite_fwd_rng(const float* raw, int raw_ch, const float* z_vals, const float* rays_d,
+                          const unsigned long long* rng_state, unsigned long long rng_offset, float noise_std,
+                          int white_bkgd, float* rgb_map, float* disp_map, float* acc_map, float* weights,
+                          float* depth_map, int N, int S, void* stream);
+int dln_composite_bwd_rng(const float* raw, int raw_ch, const float* z_vals, const float* rays_d,
+                          const unsigned long long* rng_state, unsigned long long rng_offset, float noise_std,
+                          int white_bkgd, const float* g_rgb, const float* g_disp, const float* g_acc,
+                          const float* g_weights, const float* g_depth, float* d_raw, int N, int S, void* stream);
+int dln_composite_bwd_fused_loss_dev(const float* raw, int raw_ch, const float* z_vals, const float* rays_d,
+                                     const float* noise, const unsigned long long* rng_state,
+                                     unsigned long long rng_offset, float noise_std, int white_bkgd,
+                                     const float* target_rgb, const float* target_depth, const float* ray_weights,
+                                     int n_rgb, const float* coefs_dev, int depth_mode, float* loss_sums, float* d_raw,
+                                     int N, int S, void* stream);
+
 /* ----------------------------------------------------------------------------------------------
  * Hierarchical sampling
  * -------------------------------------------------------------------------------------------- */
@@ -80,6 +120,12 @@ int dln_composite_bwd_fused_loss(const float* raw, int raw_ch, const float* z_va
 int dln_sample_pdf(const float* bins, int bins_stride, int mid_from_z, const float* weights, int weights_stride,
                    int n_bins, const float* u, int n_samples, float* samples, const float* z_coarse, int S,
                    float* z_merged, float* cdf_out, long long* inds_out, int N, void* stream);
+
+/* dln_sample_pdf with u ~ U[0,1) drawn in-kernel (run_nerf_helpers.py:509). */
+int dln_sample_pdf_rng(const float* bins, int bins_stride, int mid_from_z, const float* weights, int weights_stride,
+                       int n_bins, const unsigned long long* rng_state, unsigned long long rng_offset, int n_samples,
+                       float* samples, const float* z_coarse, int S, float* z_merged, float* cdf_out,
+                       long long* inds_out, int N, void* stream);
 
 /* Batched row-wise search with row broadcast: the contract of the vendored extension
  * torchsearchsorted/src/cuda/searchsorted_cuda_kernel.cu:110-142 (searchsorted.py:20-53). */

@@ -46,7 +46,13 @@ def _worker(rank, world, port, out, flat_views=False):
         extra = torch.nn.Parameter(torch.zeros(3))          # a foreign parameter with its own gradient tensor
         extra.grad = torch.full((3,), float(rank + 1))
         dn.allreduce_gradients(ps + [extra], world)
-        assert torch.allclose(extra.grad, torch.full((3,), 1.5)) and torch.allclose(flat[-5:], torch.full((5,), 0.5))
+        # the foreign gradient is averaged; the scratch tail behind the parameters' span is rank-local and untouched
+        assert torch.allclose(extra.grad, torch.full((3,), 1.5)) and torch.equal(flat[-5:], torch.full((5,), float(rank)))
+        probe = torch.nn.Parameter(torch.zeros(2))
+        buf = torch.full((4,), float(rank + 1))
+        probe.grad = buf[1:3]
+        dn.allreduce_gradients([probe], world, average=False)       # plain sum (1/world folded into the loss scale)
+        assert torch.equal(buf, torch.tensor([rank + 1.0, 3.0, 3.0, rank + 1.0]))
     else:
         dn.allreduce_gradients(list(model.parameters()), world)
     if rank == 0:
