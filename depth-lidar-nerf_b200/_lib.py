@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
 CSRC = os.path.join(_HERE, "csrc")
 SO_PATH = os.environ.get("DLN_SO_PATH") or os.path.join(_HERE, "libdlnerf_b200.so")   # override: A/B builds of the kernels
-SOURCES = ["render_kernels.cu", "mlp_kernels.cu", "optim_kernels.cu", "semantic_kernels.cu"]
+SOURCES = ["render_kernels.cu", "mlp_kernels.cu", "optim_kernels.cu", "semantic_kernels.cu", "raygen_kernels.cu"]
 
 MAX_STEPS = 12
 MAX_KSLABS = 6
@@ -103,6 +103,9 @@ SIGNATURES = {
     "dln_sample_sum_bwd": [_P, _I, _I, _I, _I, _P, _P],
     "dln_sem_ce_loss": [_P, _I, _P, _I, _I, _I, _F, _P, _P, _P],
     "dln_adam_step": [_P, _P, _P, _P, _LL, _D, _D, _D, _D, _I, _F, _P],
+    "dln_gen_rays": [_P, _I, _I, _I, _D, _P, _P, _LL, _P],
+    "dln_gen_rays_by_coord": [_P, _P, _LL, _I, _I, _D, _I, _P, _P, _LL, _P],
+    "dln_gen_rays_patch": [_P, _I, _I, _D, _I, _I, _I, _I, _P, _I, _P, _P, _P, _P],
     "dln_abi_sizes": [C.POINTER(C.c_int)],
 }
 

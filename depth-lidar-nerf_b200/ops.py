@@ -8,6 +8,7 @@ from __future__ import annotations
 import ctypes as C
 from typing import Optional, Tuple
 
+import numpy as np
 import torch
 
 from . import _lib as L
@@ -147,6 +148,89 @@ def stratified_z(ray_batch: Tensor, n_samples: int, t_rand: Optional[Tensor] = N
     L.call("dln_stratified_z", rb.data_ptr(), rb.stride(0), _ptr(tr), z.data_ptr(), N, n_samples,
                                      int(bool(lindisp)), _stream(), tag="stratified_z")
     return z
+
+
+def _cuda_device(device, like=None) -> torch.device:
+    """An indexed CUDA device: `device` if given, else the device of the CUDA tensor `like`, else the current one."""
+    if device is not None:
+        dev = torch.device(device)
+    elif torch.is_tensor(like) and like.is_cuda:
+        dev = like.device
+    else:
+        dev = torch.device("cuda")
+    if dev.type != "cuda":
+        raise RuntimeError("dlnerf_b200: ray generation runs on the GPU; there is no CPU fallback")
+    return dev if dev.index is not None else torch.device("cuda", torch.cuda.current_device())
+
+
+def _pose34(c2w, dev, dtype) -> Tensor:
+    """[..., >=3, >=4] camera-to-world matrices -> contiguous [..., 3, 4] of `dtype` on `dev`."""
+    t = c2w if torch.is_tensor(c2w) else torch.as_tensor(np.asarray(c2w))
+    return t[..., :3, :4].to(device=dev, dtype=dtype).contiguous()
+
+
+def gen_rays(H: int, W: int, focal: float, c2w, out: Optional[Tensor] = None, device=None):
+    """get_rays_np (run_nerf_helpers.py:285-300) for one pose [3,4] or a stack [n,3,4] in ONE launch.  Returns
+    (rays_o, rays_d) of shape [(n,) H, W, 3]; with ``out`` = a [n*H*W, 3, 3] bank the rays are written straight into its
+    rows 0 (origin) and 1 (direction) (run_nerf.py:1126-1147 without the host round trip)."""
+    dev = _cuda_device(device, c2w)
+    with torch.cuda.device(dev):
+        p = _pose34(c2w, dev, torch.float32)
+        single = p.dim() == 2
+        p = p.reshape(-1, 3, 4)
+        n = p.shape[0]
+        if out is None:
+            o = torch.empty(n, H, W, 3, device=dev, dtype=torch.float32)
+            d = torch.empty_like(o)
+            po, pd, stride = o.data_ptr(), d.data_ptr(), 3
+        else:
+            if tuple(out.shape) != (n * H * W, 3, 3) or out.dtype != torch.float32 or not out.is_contiguous() or out.device != dev:
+                raise ValueError("out must be a contiguous fp32 [n*H*W, 3, 3] bank on the poses' device")
+            o, d = out[:, 0], out[:, 1]
+            po, pd, stride = out.data_ptr(), out.data_ptr() + 12, 9
+        L.call("dln_gen_rays", p.data_ptr(), n, int(H), int(W), float(focal), po, pd, stride, _stream(), tag="gen_rays")
+    if out is None and single:
+        return o[0], d[0]
+    return o, d
+
+
+def gen_rays_by_coord(H: int, W: int, focal: float, c2w, coords, device=None):
+    """get_rays_by_coord_np (run_nerf_helpers.py:303-318): coords[N,2] fractional (x, y) pixels -> (rays_o, rays_d)
+    [N,3] in the coordinates' floating dtype (numpy's promotion: float64 coordinates give float64 rays)."""
+    ct = coords if torch.is_tensor(coords) else torch.as_tensor(np.asarray(coords))
+    dev = _cuda_device(device, ct)
+    dtype = torch.float64 if ct.dtype == torch.float64 else torch.float32
+    with torch.cuda.device(dev):
+        ct = ct.to(device=dev, dtype=dtype).reshape(-1, 2).contiguous()
+        p = _pose34(c2w, dev, dtype)
+        if p.dim() != 2:
+            raise ValueError("get_rays_by_coord takes one [3,4] pose")
+        N = ct.shape[0]
+        o = torch.empty(N, 3, device=dev, dtype=dtype)
+        d = torch.empty_like(o)
+        if N == 0:
+            return o, d
+        L.call("dln_gen_rays_by_coord", p.data_ptr(), ct.data_ptr(), N, int(H), int(W), float(focal),
+               int(dtype == torch.float64), o.data_ptr(), d.data_ptr(), 3, _stream(), tag="gen_rays_by_coord")
+    return o, d
+
+
+def gen_rays_patch(H: int, W: int, focal: float, c2w, start_w: int, start_h: int, nH: int, nW: int, perm: Tensor):
+    """The permuted crop of get_rays_cropped_feature_loss_new (run_nerf_helpers.py:430-494): rays and (row, col)
+    crop positions of the pixels perm[0], perm[1], ... (flat row-major indices into the nH x nW crop)."""
+    dev = perm.device
+    if not perm.is_cuda:
+        raise ValueError("perm must live on the GPU")
+    with torch.cuda.device(dev):
+        p = _pose34(c2w, dev, torch.float32)
+        pm = perm.to(torch.int64).contiguous()
+        n = pm.numel()
+        o = torch.empty(n, 3, device=dev, dtype=torch.float32)
+        d = torch.empty_like(o)
+        pts = torch.empty(n, 2, device=dev, dtype=torch.int64)
+        L.call("dln_gen_rays_patch", p.data_ptr(), int(H), int(W), float(focal), int(start_w), int(start_h), int(nH),
+               int(nW), pm.data_ptr(), n, o.data_ptr(), d.data_ptr(), pts.data_ptr(), _stream(), tag="gen_rays_patch")
+    return o, d, pts
 
 
 def posenc(x: Tensor, n_freqs: int) -> Tensor:

@@ -402,6 +402,42 @@ def ndc_rays(H, W, focal, near, rays_o, rays_d):
     return o, d
 
 
+def get_rays_np(H, W, focal, c2w):
+    """run_nerf_helpers.py:285-300 on the device: (rays_o, rays_d), each [H, W, 3] fp32 CUDA tensors (a stack of poses
+    [n, 3, 4] gives [n, H, W, 3] in one launch -- the list comprehension of run_nerf.py:1126).  Values are bit-identical
+    to the numpy function; call ``.cpu().numpy()`` on them where an array is really needed."""
+    return ops.gen_rays(int(H), int(W), float(focal), c2w)
+
+
+def get_rays_by_coord_np(H, W, focal, c2w, coords):
+    """run_nerf_helpers.py:303-318 on the device: rays through the fractional pixel positions coords[N, 2] = (x, y) of the
+    LiDAR / COLMAP depth points, in the coordinates' dtype (float64 coordinates -> float64 rays, as numpy promotes)."""
+    return ops.gen_rays_by_coord(int(H), int(W), float(focal), c2w, coords)
+
+
+def get_rays_cropped_feature_loss_new(H, W, focal, c2w, nH=32, nW=32, gradH=2, gradW=2, device=None, _start=None,
+                                      _perm=None):
+    """run_nerf_helpers.py:430-494: a random nH x nW crop, its pixels randomly split into gradH*gradW rays rendered with
+    gradients and the rest without.  Returns the reference's three lists
+    ``[grad_rays_o, grad_rays_d, grad_points], [no_grad_rays_o, no_grad_rays_d, no_grad_points], [start_w, end_w,
+    start_h, end_h]`` with every tensor on the device.  Randomness as in the reference: the crop corner from
+    ``np.random.randint`` (:436-437, same two draws in the same order), the split from ``torch.randperm`` (:466, drawn on
+    the device); ``_start=(start_w, start_h)`` / ``_perm`` inject them (parity tests)."""
+    H, W = int(H), int(W)
+    num_w, num_h = W - nW + 1, H - nH + 1
+    if _start is None:
+        start_w = int(np.random.randint(0, num_w))
+        start_h = int(np.random.randint(0, num_h))
+    else:
+        start_w, start_h = int(_start[0]), int(_start[1])
+    end_w, end_h = start_w + nW - 1, start_h + nH - 1
+    device = ops._cuda_device(device, c2w)
+    perm = torch.randperm(nH * nW, device=device) if _perm is None else torch.as_tensor(_perm).to(device)
+    o, d, pts = ops.gen_rays_patch(H, W, float(focal), c2w, start_w, start_h, nH, nW, perm)
+    k = gradH * gradW
+    return [o[:k], d[:k], pts[:k]], [o[k:], d[k:], pts[k:]], [start_w, end_w, start_h, end_h]
+
+
 # --------------------------------------------------------------------------------------------------
 # Hierarchical sampling (run_nerf_helpers.py:497-540)
 # --------------------------------------------------------------------------------------------------

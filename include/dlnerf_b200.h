@@ -335,6 +335,29 @@ int dln_sem_ce_loss(const float* logits, int ld, const long long* target, int n_
 int dln_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, double lr,
                   double beta1, double beta2, double eps, int step, float grad_scale, void* stream);
 
+/* ----------------------------------------------------------------------------------------------
+ * Ray generation: the pinhole-camera rays the reference builds on the host.
+ * Arithmetic is the reference's, operation by operation and without FMA contraction (bit-identical to numpy / CPU
+ * torch): dirs = ((x - W*.5)/focal, -(y - H*.5)/focal, -1), rays_d[k] = (dirs0 R[k][0] + dirs1 R[k][1]) + dirs2 R[k][2],
+ * rays_o = c2w[:, 3].  `out_stride` is the distance in elements between consecutive rays of rays_o / rays_d (3 for
+ * packed [N,3] outputs, 9 to write straight into the rows of the [N, 3, 3] (o, d, rgb) training bank).
+ * -------------------------------------------------------------------------------------------- */
+
+/* get_rays_np, run_nerf_helpers.py:285-300, for n_poses cameras at once (the list comprehension of
+ * run_nerf.py:1126): c2w[n_poses, 3, 4] fp32 -> ray (pose, y, x) at index (pose*H + y)*W + x. */
+int dln_gen_rays(const float* c2w, int n_poses, int H, int W, double focal, float* rays_o, float* rays_d,
+                 long long out_stride, void* stream);
+/* get_rays_by_coord_np, run_nerf_helpers.py:303-318: coords[N, 2] = fractional (x, y) pixel positions of the
+ * LiDAR / COLMAP depth points (run_nerf.py:1171).  is_f64 = 0: c2w, coords and outputs fp32; 1: all fp64 (numpy
+ * promotes to the coordinates' dtype, which is float64 in the reference's loaders). */
+int dln_gen_rays_by_coord(const void* c2w, const void* coords, long long N, int H, int W, double focal, int is_f64,
+                          void* rays_o, void* rays_d, long long out_stride, void* stream);
+/* get_rays_cropped_feature_loss_new, run_nerf_helpers.py:430-494: the nH x nW crop at (start_w, start_h) in the
+ * order of perm[n] (int64, a permutation of the flat crop indices row*nW + col, :466): rays_o / rays_d [n, 3] and
+ * points[n, 2] = (row, col) inside the crop (int64, :461-470).  The caller splits at gradH*gradW (:468, :481). */
+int dln_gen_rays_patch(const float* c2w, int H, int W, double focal, int start_w, int start_h, int nH, int nW,
+                       const long long* perm, int n, float* rays_o, float* rays_d, long long* points, void* stream);
+
 /* Host-only: sizeof of the six ABI structs, in the order ChainStep, ChainProgram, ChainArgs, WgradItem,
  * PackJob, SemOffsets, so a binding can verify its mirror of this header without touching a GPU. */
 int dln_abi_sizes(int* out6_host);

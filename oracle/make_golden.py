@@ -13,6 +13,8 @@ torch.rand / torch.randn for the duration of each reference call, and
 
 Usage:  python oracle/make_golden.py                    (re-writes tests/golden/)
         python oracle/make_golden.py --only-semantic    (re-writes tests/golden/semantic.npz only)
+        python oracle/make_golden.py --only-raygen      (re-writes tests/golden/raygen.npz only)
+        python oracle/make_golden.py --only-w256        (re-writes tests/golden/mlp_w256.npz only)
 """
 from __future__ import annotations
 
@@ -230,12 +232,103 @@ def semantic_section(H, R, out_dir):
     np.savez_compressed(os.path.join(out_dir, "semantic.npz"), **fix)
 
 
+def raygen_section(H, R, out_dir):
+    """Ray generators: get_rays_np, get_rays_by_coord_np (fp32 and fp64 coordinates),
+    get_rays_cropped_feature_loss_new with its three random draws recorded."""
+    print("ray generation")
+    rs = np.random.RandomState(11)
+    Hh, Ww, focal = 47, 61, 52.37
+    fix = {"HWf": np.array([Hh, Ww, focal], np.float64)}
+
+    def pose(seed):
+        q, _ = np.linalg.qr(np.random.RandomState(seed).randn(3, 3))
+        return np.concatenate([q, np.random.RandomState(seed + 100).randn(3, 1)], 1).astype(np.float32)
+
+    poses = np.stack([pose(s) for s in range(3)], 0)
+    fix["poses"] = poses
+    for n, p in enumerate(poses):
+        o, d = H.get_rays_np(Hh, Ww, np.float32(focal), p)
+        oo, od = O.get_rays_np(Hh, Ww, focal, p)
+        assert o.dtype == np.float32 and d.dtype == np.float32
+        close(torch.from_numpy(oo.copy()), torch.from_numpy(np.ascontiguousarray(o)), 0.0, "get_rays_np o %d" % n)
+        close(torch.from_numpy(od.copy()), torch.from_numpy(np.ascontiguousarray(d)), 0.0, "get_rays_np d %d" % n)
+        fix["grid_d%d" % n] = np.ascontiguousarray(d)
+    # fractional LiDAR coordinates, float64 as the loaders deliver them and float32
+    c64 = np.stack([rs.uniform(0, Ww, 333), rs.uniform(0, Hh, 333)], -1)
+    for tag, c, f in (("64", c64, focal), ("32", c64.astype(np.float32), np.float32(focal))):
+        o, d = H.get_rays_by_coord_np(Hh, Ww, f, poses[1], c)
+        oo, od = O.get_rays_by_coord_np(Hh, Ww, focal, poses[1], c)
+        assert d.dtype == c.dtype, (d.dtype, c.dtype)
+        close(torch.from_numpy(od.copy()), torch.from_numpy(np.ascontiguousarray(d)), 0.0, "get_rays_by_coord_np d " + tag)
+        close(torch.from_numpy(oo.copy()), torch.from_numpy(np.ascontiguousarray(o)), 0.0, "get_rays_by_coord_np o " + tag)
+        fix["coord" + tag], fix["coord_d" + tag], fix["coord_o" + tag] = c, np.ascontiguousarray(d), np.ascontiguousarray(o)
+    # the crop generator: record the reference's own draws (np.random.randint x2, torch.randperm) and replay them
+    for n, (nH, nW, gH, gW) in enumerate([(8, 8, 2, 2), (5, 12, 3, 2), (32, 32, 2, 2)]):
+        np.random.seed(100 + n)
+        torch.manual_seed(200 + n)
+        grad, nograd, crop = H.get_rays_cropped_feature_loss_new(Hh, Ww, focal, torch.from_numpy(poses[2]), nH=nH, nW=nW,
+                                                                 gradH=gH, gradW=gW)
+        np.random.seed(100 + n)
+        torch.manual_seed(200 + n)
+        sw, sh = np.random.randint(0, Ww - nW + 1), np.random.randint(0, Hh - nH + 1)
+        perm = torch.randperm(nH * nW)
+        assert crop == [sw, sw + nW - 1, sh, sh + nH - 1], (crop, sw, sh)
+        og, on, oc = O.rays_cropped_feature_loss_new(Hh, Ww, focal, poses[2], nH, nW, gH, gW, sw, sh, perm.numpy())
+        assert oc == crop
+        for a, b, what in ((og, grad, "grad"), (on, nograd, "no_grad")):
+            close(torch.from_numpy(a[0].copy()), b[0], 0.0, "crop %d %s o" % (n, what))
+            close(torch.from_numpy(a[1].copy()), b[1], 0.0, "crop %d %s d" % (n, what))
+            assert b[2].dtype == torch.int64 and np.array_equal(a[2], b[2].numpy()), "crop %d %s points" % (n, what)
+        fix["crop%d_cfg" % n] = np.array([nH, nW, gH, gW, sw, sh], np.int64)
+        fix["crop%d_perm" % n] = perm.numpy()
+        fix["crop%d_d" % n] = np.concatenate([np_(grad[1]), np_(nograd[1])], 0)
+        fix["crop%d_pts" % n] = np.concatenate([grad[2].numpy(), nograd[2].numpy()], 0)
+    fix["n_crops"] = np.array([3])
+    np.savez_compressed(os.path.join(out_dir, "raygen.npz"), **fix)
+
+
+def mlp_w256_section(H, R, out_dir):
+    """A full-width (W = 256, D = 8, view directions) case the CUDA MLP can evaluate directly: the UNMODIFIED reference
+    module's forward and parameter gradients on 160 points (one full 128-point tile + a partial one).  Parameters are
+    regenerated from the seed (tests/golden/param_guard.npz pins the generator); big gradient tensors are kept as every
+    16th row."""
+    print("mlp W=256")
+    g = torch.Generator().manual_seed(77)
+    spec = O.MLPSpec(D=8)
+    params = O.trained_like(O.init_params(spec, seed=3407 + 8), 1.0)
+    net = H.NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True)
+    net.load_state_dict(params)
+    pts = (torch.rand(160, 3, generator=g) * 2 - 1) * 1.2
+    dirs = torch.nn.functional.normalize(torch.randn(160, 3, generator=g), dim=-1)
+    xin = torch.cat([H.get_embedder(10, 0)[0](pts), H.get_embedder(4, 0)[0](dirs)], -1)
+    y_ref = net(xin)
+    close(O.mlp_forward(params, xin, spec), y_ref, 5e-6, "mlp fwd W=256")
+    cot = torch.randn(y_ref.shape, generator=g)
+    net.zero_grad()
+    (y_ref * cot).sum().backward()
+    pl = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    (O.mlp_forward(pl, xin, spec) * cot).sum().backward()
+    fix = {"x": np_(xin), "y": np_(y_ref), "cot": np_(cot), "seed": np.array([3407 + 8]), "sigma_bias": np.array([1.0])}
+    for k, v in net.named_parameters():
+        close(pl[k].grad, v.grad, 1e-4, "  grad " + k)
+        gr = np_(v.grad)
+        fix["g_" + k] = gr[::16] if gr.ndim == 2 and gr.shape[0] >= 128 else gr
+        fix["gn_" + k] = np.array([float(v.grad.double().norm())])
+    np.savez_compressed(os.path.join(out_dir, "mlp_w256.npz"), **fix)
+
+
 def main():
     H, R = import_reference()
     out_dir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
     if "--only-semantic" in sys.argv:
         semantic_section(H, R, out_dir)
+        return
+    if "--only-raygen" in sys.argv:
+        raygen_section(H, R, out_dir)
+        return
+    if "--only-w256" in sys.argv:
+        mlp_w256_section(H, R, out_dir)
         return
     torch.manual_seed(3407)
     g = torch.Generator().manual_seed(3407)
@@ -451,6 +544,8 @@ def main():
     cases["n"] = np.array([i])
     np.savez_compressed(os.path.join(out_dir, "searchsorted.npz"), **cases)
     semantic_section(H, R, out_dir)
+    raygen_section(H, R, out_dir)
+    mlp_w256_section(H, R, out_dir)
     print("golden vectors written to", out_dir)
 
 

@@ -23,6 +23,7 @@ import math
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence
 
+import numpy as np
 import torch
 
 Tensor = torch.Tensor
@@ -358,6 +359,49 @@ def pack_rays(H: int, W: int, focal: float, rays_o: Tensor, rays_d: Tensor, ndc:
 # --------------------------------------------------------------------------- #
 # patch loss   loss.py:55-133
 # --------------------------------------------------------------------------- #
+# ---------------------------------------------------------------------------
+# Ray generation
+# ---------------------------------------------------------------------------
+def pixel_rays(H: int, W: int, focal, c2w, x, y):
+    """Rays through pixel positions (x, y) (numpy arrays of one floating dtype T): the shared arithmetic of
+    get_rays_np (run_nerf_helpers.py:285-300), get_rays_by_coord_np (:303-318) and the crop generators (:430-494),
+    every operation rounded once in T, the 3-term dot product summed left to right as numpy / CPU torch do."""
+    T = x.dtype
+    R = np.asarray(c2w)[:3, :4].astype(T)
+    f = T.type(focal)
+    d0 = (x - T.type(W * .5)) / f
+    d1 = -((y - T.type(H * .5)) / f)
+    d2 = -np.ones_like(d0)
+    d = np.stack([(d0 * R[k, 0] + d1 * R[k, 1]) + d2 * R[k, 2] for k in range(3)], -1).astype(T)
+    o = np.broadcast_to(R[:, 3], d.shape).astype(T)
+    return o, d
+
+
+def get_rays_np(H: int, W: int, focal, c2w):
+    """run_nerf_helpers.py:285-300: all pixels of one camera, [H, W, 3] each, fp32."""
+    i, j = np.meshgrid(np.arange(W, dtype=np.float32), np.arange(H, dtype=np.float32), indexing='xy')
+    return pixel_rays(H, W, focal, c2w, i, j)
+
+
+def get_rays_by_coord_np(H: int, W: int, focal, c2w, coords):
+    """run_nerf_helpers.py:303-318: coords[N, 2] = (x, y), result in the coordinates' dtype."""
+    c = np.asarray(coords)
+    if c.dtype not in (np.float32, np.float64):
+        c = c.astype(np.float64)
+    return pixel_rays(H, W, focal, c2w, c[:, 0], c[:, 1])
+
+
+def rays_cropped_feature_loss_new(H: int, W: int, focal, c2w, nH: int, nW: int, gradH: int, gradW: int, start_w: int,
+                                  start_h: int, perm):
+    """run_nerf_helpers.py:430-494 with the three random draws (crop corner :436-437, randperm :466) injected."""
+    perm = np.asarray(perm).astype(np.int64)
+    row, col = perm // nW, perm % nW
+    o, d = pixel_rays(H, W, focal, c2w, (start_w + col).astype(np.float32), (start_h + row).astype(np.float32))
+    pts = np.stack([row, col], -1)
+    k = gradH * gradW
+    return [o[:k], d[:k], pts[:k]], [o[k:], d[k:], pts[k:]], [start_w, start_w + nW - 1, start_h, start_h + nH - 1]
+
+
 def inverse_depth_smoothness(idepth: Tensor, image: Tensor) -> Tensor:
     """InverseDepthSmoothnessLoss.forward (loss.py:87-133): forward differences a[.., j] - a[.., j+1] (:78-85),
     image weights exp(-mean_c |d image|) (:121-124), loss = mean|d_x idepth * w_x| + mean|d_y idepth * w_y| (:127-129).

@@ -5,10 +5,14 @@ tests/gpu_util.mlp_reference) for tight per-layer checks, and the fp32 oracle (o
 pinned to the reference) for the stated bf16 tolerances:
     raw outputs      |err| <= 3e-2 * max|ref|  against the fp32 oracle
     gradients        per tensor, against autograd through the bf16-emulating torch forward (the function the
-                     kernels evaluate; ReLU masks of the bf16 pass): cosine >= 0.999, rel-L2 <= 3e-2;
-                     against fp32 autograd (different ReLU masks where a pre-activation is within bf16
-                     rounding of 0): cosine >= 0.99, rel-L2 <= 0.15
+                     kernels evaluate; ReLU masks of the bf16 pass): per tensor cosine >= 0.9995, rel-L2 <= 2.5e-2
+                     (measured 0.99992 / 1.2e-2); against fp32 autograd (different ReLU masks where a pre-activation
+                     is within bf16 rounding of 0): aggregate rel-L2 over all tensors <= 8e-2 (measured <= 3.8e-2),
+                     per tensor cosine >= 0.99, rel-L2 <= 0.16 (measured 0.9916 / 0.13 on the first layers' biases)
 """
+import os
+
+import numpy as np
 import pytest
 import torch
 
@@ -125,8 +129,8 @@ def test_backward_gradients(D, P, vd):
     y = net(x.to(DEV))
     (y * cot.to(DEV)).sum().backward()
     st = compare_grads([(n, p.grad) for n, p in net.named_parameters()], refem, ref32)
-    assert st["worst_cos_e"] >= 0.999 and st["worst_l2_e"] <= 3e-2
-    assert st["worst_cos_f"] >= 0.99 and st["worst_l2_f"] <= 0.15
+    assert st["worst_cos_e"] >= 0.9995 and st["worst_l2_e"] <= 2.5e-2      # measured 0.99992 / 1.2e-2
+    assert st["worst_cos_f"] >= 0.99 and st["worst_l2_f"] <= 0.16 and st["agg_f"] <= 8e-2   # measured 0.9916 / 0.13 / 3.8e-2
 
 
 def test_backward_dz_per_layer():
@@ -234,3 +238,31 @@ def test_full_size_backward_is_additive_over_points():
     print("  run-to-run rel-L2 %.2e, halves-vs-whole rel-L2 %.2e" % (worst_rep, worst_add))
     assert worst_rep <= 1e-4 and worst_add <= 1e-4
     assert all(torch.isfinite(x).all() for x in full)
+
+
+def test_reference_generated_w256_case(golden_dir):
+    """tests/golden/mlp_w256.npz: forward and parameter gradients of the UNMODIFIED reference NeRF(D=8, W=256) on 160
+    points, pushed through the CUDA MLP directly (no test-side twin in between).  Tolerances as in the header."""
+    g = np.load(os.path.join(golden_dir, "mlp_w256.npz"))
+    spec = O.MLPSpec(D=8)
+    params = O.trained_like(O.init_params(spec, seed=int(g["seed"][0])), float(g["sigma_bias"][0]))
+    net = dn().NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True)
+    net.load_state_dict(params)
+    net = net.to(DEV)
+    y = net(torch.from_numpy(g["x"]).to(DEV))
+    ref = torch.from_numpy(g["y"])
+    report("NeRF(W=256) forward vs the reference module", y, ref, atol=3e-2 * ref.abs().max().item())
+    (y * torch.from_numpy(g["cot"]).to(DEV)).sum().backward()
+    worst_cos, worst_l2, num, den = 1.0, 0.0, 0.0, 0.0
+    for k, p in net.named_parameters():
+        gr = p.grad.detach().cpu()
+        got = gr[::16] if gr.dim() == 2 and gr.shape[0] >= 128 else gr
+        r = torch.from_numpy(g["g_" + k])
+        c, l = cosine(got, r), rel_l2(got, r)
+        print("  %-26s cos %.5f relL2 %.3e |ref| %.3e" % (k, c, l, r.norm()))
+        worst_cos, worst_l2 = min(worst_cos, c), max(worst_l2, l)
+        num += float((got.double() - r.double()).pow(2).sum())
+        den += float(r.double().pow(2).sum())
+    agg = (num / den) ** 0.5
+    print("  worst cosine %.5f, worst rel-L2 %.3e, aggregate rel-L2 %.3e" % (worst_cos, worst_l2, agg))
+    assert worst_cos >= 0.99 and worst_l2 <= 0.16 and agg <= 2.6e-2      # measured 0.9925 / 0.127 / 1.3e-2

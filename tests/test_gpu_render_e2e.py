@@ -6,10 +6,10 @@ Stated tolerances (bf16 MLP against an fp32 reference):
     rgb_map / depth_map / acc_map   abs <= 2e-2
     loss                            rel <= 2e-2
     gradients   against autograd through the oracle renderer with the bf16-emulating MLP forward (the
-                function the kernels evaluate): per tensor cosine >= 0.995, aggregate rel-L2 <= 3e-2;
-                against the pure fp32 oracle: aggregate rel-L2 over all tensors <= 0.15 (ReLU masks flip
+                function the kernels evaluate): per tensor cosine >= 0.999, aggregate rel-L2 <= 3e-3 (measured 0.99997 / 7e-4);
+                against the pure fp32 oracle: aggregate rel-L2 over all tensors <= 2e-2 (measured 3e-3 ... 9e-3; ReLU masks flip
                 where a pre-activation lies within bf16 rounding of zero; first-layer weight gradients of a
-                randomly initialised net are ~1e-6 in norm and dominated by those flips)
+                randomly initialised net are ~1e-6 in norm and dominated by those flips))
 """
 import pytest
 import torch
@@ -76,8 +76,8 @@ def test_render_loss_backward_parity(perturb, noise):
     for net, p32, pem, tag in ((net_f, pfg, pfe, "fine   "), (net_c, pcg, pce, "coarse ")):
         st = compare_grads([(n, p.grad) for n, p in net.named_parameters()],
                            {k: v.grad for k, v in pem.items()}, {k: v.grad for k, v in p32.items()}, tag)
-        assert st["worst_cos_e"] >= 0.995 and st["agg_e"] <= 3e-2, tag
-        assert st["agg_f"] <= 0.15, tag
+        assert st["worst_cos_e"] >= 0.999 and st["agg_e"] <= 3e-3, tag       # measured 0.99997 / 7.2e-4
+        assert st["agg_f"] <= 2e-2, tag
 
 
 def test_render_against_reference_golden(golden_dir):
@@ -467,7 +467,7 @@ def test_kitti360_patch_iteration_against_oracle():
         den += float(r.double().pow(2).sum())
     agg = (num / den) ** 0.5
     print("  aggregate rel-L2 of the parameter gradients vs the bf16-emulating oracle: %.3e" % agg)
-    assert agg <= 5e-2
+    assert agg <= 2e-3      # measured 3.2e-4
 
 
 def test_sharded_patch_render_single_rank_equals_render_feature_loss():

@@ -5,8 +5,8 @@ Stated tolerances (bf16 trunk, fp32 head on the bf16 activations the chain keeps
     per-point logits            abs <= 2e-2 + 1e-2 |ref|
     per-ray logits (sum of 64 / 128 samples)      abs <= 5e-2 + 1e-2 |ref|
     losses                      rel <= 2e-2
-    gradients                   as in test_gpu_render_e2e.py: per tensor cosine >= 0.995 and aggregate rel-L2 <= 3e-2
-                                against autograd through the bf16-emulating twin, aggregate rel-L2 <= 0.15 against
+    gradients                   as in test_gpu_render_e2e.py: per tensor cosine >= 0.995 and aggregate rel-L2 <= 5e-3 (measured 1.4e-3)
+                                against autograd through the bf16-emulating twin, aggregate rel-L2 <= 3e-2 against
                                 the fp32 oracle
     fp32-only kernels (sample sums, cross-entropy)   rtol 1e-5 / atol 1e-6
 """
@@ -46,7 +46,7 @@ def test_module_forward_and_backward_with_semantic_logits():
     st = compare_grads([(n, q.grad) for n, q in net.named_parameters()], {k: v.grad for k, v in pe.items()},
                        {k: v.grad for k, v in p32.items()})
     assert len([1 for _, q in net.named_parameters() if q.grad is not None]) == 28
-    assert st["worst_cos_e"] >= 0.995 and st["agg_e"] <= 3e-2 and st["agg_f"] <= 0.15
+    assert st["worst_cos_e"] >= 0.995 and st["agg_e"] <= 5e-3 and st["agg_f"] <= 3e-2
 
 
 def test_raw2outputs_semantic_against_reference_golden(golden_dir):
@@ -145,8 +145,8 @@ def test_render_with_semantic_loss_and_backward_parity():
     for net, p32, pem, tag in ((net_f, pfg, pfe, "fine   "), (net_c, pcg, pce, "coarse ")):
         st = compare_grads([(n, q.grad) for n, q in net.named_parameters()],
                            {k: v.grad for k, v in pem.items()}, {k: v.grad for k, v in p32.items()}, tag)
-        assert st["worst_cos_e"] >= 0.995 and st["agg_e"] <= 3e-2, tag
-        assert st["agg_f"] <= 0.15, tag
+        assert st["worst_cos_e"] >= 0.995 and st["agg_e"] <= 5e-3, tag
+        assert st["agg_f"] <= 3e-2, tag
         for n, q in net.named_parameters():
             if n.startswith("semantic_linear"):
                 assert q.grad is not None and float(q.grad.abs().sum()) > 0, n
@@ -171,7 +171,7 @@ def test_semantic_only_loss_reaches_the_trunk():
     used = [(k, q.grad) for k, q in net_f.named_parameters()
             if not k.startswith(("views_linears", "rgb_linear", "alpha_linear"))]
     st = compare_grads(used, grads["emul"], grads["fp32"], "fine   ")
-    assert st["worst_cos_e"] >= 0.995 and st["agg_e"] <= 3e-2 and st["agg_f"] <= 0.15
+    assert st["worst_cos_e"] >= 0.995 and st["agg_e"] <= 5e-3 and st["agg_f"] <= 3e-2
     for k, q in net_f.named_parameters():            # the colour / density heads see no gradient from this loss
         if k.startswith(("views_linears", "rgb_linear", "alpha_linear")):
             assert float(q.grad.abs().max()) <= 1e-12, k

@@ -138,3 +138,43 @@ def test_inverse_depth_smoothness_golden(golden_dir):
     loss.backward()
     assert float(loss.detach()) == float(g["loss"])
     assert np.array_equal(d.grad.numpy(), g["g_idepth"]) and np.array_equal(im.grad.numpy(), g["g_image"])
+
+
+def test_ray_generators(golden_dir):
+    """get_rays_np / get_rays_by_coord_np / get_rays_cropped_feature_loss_new, bit for bit."""
+    g = load(golden_dir, "raygen.npz")
+    H, W, focal = int(g["HWf"][0]), int(g["HWf"][1]), float(g["HWf"][2])
+    for n in range(3):
+        o, d = O.get_rays_np(H, W, focal, g["poses"][n])
+        np.testing.assert_array_equal(d, g["grid_d%d" % n])
+        np.testing.assert_array_equal(o, np.broadcast_to(g["poses"][n][:, 3], d.shape))
+    for tag in ("64", "32"):
+        o, d = O.get_rays_by_coord_np(H, W, focal, g["poses"][1], g["coord" + tag])
+        assert d.dtype == g["coord_d" + tag].dtype
+        np.testing.assert_array_equal(d, g["coord_d" + tag])
+        np.testing.assert_array_equal(o, g["coord_o" + tag])
+    for n in range(int(g["n_crops"][0])):
+        nH, nW, gH, gW, sw, sh = (int(v) for v in g["crop%d_cfg" % n])
+        grad, nograd, crop = O.rays_cropped_feature_loss_new(H, W, focal, g["poses"][2], nH, nW, gH, gW, sw, sh,
+                                                             g["crop%d_perm" % n])
+        assert crop == [sw, sw + nW - 1, sh, sh + nH - 1]
+        np.testing.assert_array_equal(np.concatenate([grad[1], nograd[1]], 0), g["crop%d_d" % n])
+        np.testing.assert_array_equal(np.concatenate([grad[2], nograd[2]], 0), g["crop%d_pts" % n])
+        assert grad[0].shape == (gH * gW, 3) and nograd[0].shape == (nH * nW - gH * gW, 3)
+
+
+def test_mlp_w256_reference_case(golden_dir):
+    """The full-width case generated by the unmodified reference module (forward + every parameter gradient)."""
+    g = load(golden_dir, "mlp_w256.npz")
+    spec = O.MLPSpec(D=8)
+    params = O.trained_like(O.init_params(spec, seed=int(g["seed"][0])), float(g["sigma_bias"][0]))
+    pl = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    y = O.mlp_forward(pl, T(g["x"]), spec)
+    np.testing.assert_allclose(y.detach().numpy(), g["y"], atol=5e-6, rtol=0)
+    (y * T(g["cot"])).sum().backward()
+    for k, v in pl.items():
+        gr = v.grad.numpy()
+        ref = g["g_" + k]
+        got = gr[::16] if gr.ndim == 2 and gr.shape[0] >= 128 else gr
+        np.testing.assert_allclose(got, ref, atol=1e-4, rtol=0)
+        assert abs(float(v.grad.double().norm()) - g["gn_" + k][0]) <= 1e-4 * max(1.0, g["gn_" + k][0])

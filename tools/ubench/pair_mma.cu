@@ -1,0 +1,254 @@
+// Microbenchmark + known-answer test: tcgen05.mma issued for a CTA PAIR (cta_group::2: M = 256 rows, 128 per CTA,
+// each CTA stages HALF of the B operand) against the single-CTA form, A read from tensor memory, with and without
+// competing shared-memory traffic of the kind the chain kernel generates (weight refill by bulk global->shared
+// copies, stash staging by st.shared + bulk shared->global copies).
+//
+//   nvcc -gencode arch=compute_100a,code=sm_100a -std=c++17 -O3 -I depth-lidar-nerf_b200/csrc tools/ubench/pair_mma.cu -o tools/ubench/pair_mma.bin
+//
+// D[M x 256] = A[M x 256] * B[256 x 256]^T with small integers (exact in bf16 / fp32), M = 128 * (CTAs of the pair).
+#include <cstdio>
+#include <cstdint>
+#include <cstdlib>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include "common.cuh"
+using namespace dln;
+
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+      "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+      "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+      "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__host__ __device__ inline float a_val(int m, int k) { return (float)(((m + 2 * k) % 7) - 3); }
+__host__ __device__ inline float b_val(int n, int k) { return (float)(((3 * n + k) % 5) - 2); }
+
+template <int G> __device__ __forceinline__ void t_alloc(uint32_t* smem_out, uint32_t ncols) {
+  if (G == 1) asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_out)), "r"(ncols) : "memory");
+  else asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_out)), "r"(ncols) : "memory");
+}
+template <int G> __device__ __forceinline__ void t_relinquish() {
+  if (G == 1) asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  else asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int G> __device__ __forceinline__ void t_dealloc(uint32_t taddr, uint32_t ncols) {
+  if (G == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+  else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+template <int G> __device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  if (G == 1)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d), "r"(a), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+  else
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d), "r"(a), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+template <int G> __device__ __forceinline__ void commit(uint64_t* bar) {
+  if (G == 1)
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+  else
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cta_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+
+constexpr int kScratch = 32768, kStage = 16384;
+
+// G = CTAs per MMA (1 or 2).  B: G == 1 the whole [256 x 256] (4 K slabs x 32 KB), G == 2 this CTA's 128 rows of it
+// (4 x 16 KB).  traffic bit 0: bulk global->shared copies (32 KB, back to back); bit 1: four warps st.shared a 16 KB
+// slab image + one lane copies it out with bulk shared->global copies, back to back.
+template <int G, int CE>
+__global__ void __launch_bounds__(320, 1) k(int traffic, int reps, int layers, float* out, long long* cyc, const uint8_t* gsrc, uint8_t* gdst) {
+  extern __shared__ uint8_t raw[];
+  uint8_t* smem = raw + ((1024u - (smem_u32(raw) & 1023u)) & 1023u);
+  constexpr int kBSlab = 32768 / G;
+  uint8_t* sB = smem;                          // 4 x kBSlab
+  uint8_t* scratch = smem + 4 * 32768;         // 32 KB landing area of the competing loads
+  uint8_t* stagebuf = scratch + kScratch;      // 16 KB staging slab
+  __shared__ uint64_t bar_mma, bar_ld, bar_st, bar_dummy;
+  __shared__ uint32_t tbase_s;
+  __shared__ volatile int stop;
+  __shared__ volatile int stop2[2];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = G == 2 ? cta_rank() : 0;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar_mma, 1);
+    mbar_init(&bar_ld, 1);
+    mbar_init(&bar_st, 4);
+    mbar_init(&bar_dummy, 1);
+    mbar_fence_init();
+    stop = 0;
+  }
+  if (warp == 4) {
+    t_alloc<G>(&tbase_s, 512);
+    t_relinquish<G>();
+  }
+  const int nrows = 256 / G;                   // B rows (output features) staged by this CTA
+  for (int i = threadIdx.x; i < nrows * 256; i += blockDim.x) {
+    const int n = i >> 8, kq = i & 255;
+    *reinterpret_cast<__nv_bfloat16*>(sB + (kq >> 6) * kBSlab + slab_off(n, kq & 63)) = __float2bfloat16(b_val(n + rank * nrows, kq));
+  }
+  fence_async_smem();
+  tc_fence_before();
+  if (G == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = tbase_s;
+  if (warp < 4) {  // A -> tensor memory columns [0, 128): lane = row m (of this CTA), column c holds (A[m][2c], A[m][2c+1])
+    const int m = rank * 128 + warp * 32 + lane;
+    const uint32_t t = tbase + ((uint32_t)(warp * 32) << 16);
+    for (int c0 = 0; c0 < 128; c0 += 32) {
+      uint32_t v[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = pack_bf16(a_val(m, 2 * (c0 + i)), a_val(m, 2 * (c0 + i) + 1));
+      tmem_st32(t + c0, v);
+    }
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  if (G == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+
+  if (warp == 4) {
+    const uint64_t desc_k = umma_desc_sw128(0, 16, 1024);
+    const uint32_t idesc = umma_idesc_bf16(128 * G, 256, 0, 0);
+    const uint32_t d_tmem = tbase + 256;
+    long long t0 = clock64();
+    for (int r = 0; r < reps; ++r) {
+      if (rank == 0 && elect_one()) {
+        for (int l = 0; l < layers; ++l) {
+#pragma unroll
+          for (int ks = 0; ks < 16; ++ks) {
+            const uint64_t bd = (desc_k | (uint64_t)(smem_u32(sB + (ks >> 2) * kBSlab) >> 4)) + 2 * (ks & 3);
+            mma_ts<G>(d_tmem, tbase + ks * 8, bd, idesc, ks != 0);
+            if (CE > 0 && (ks + 1) % (CE > 0 ? CE : 1) == 0) commit<G>(&bar_dummy);     // nobody waits on it (compile-time)
+          }
+        }
+        commit<G>(&bar_mma);
+      }
+      __syncwarp();
+      mbar_wait(&bar_mma, r & 1);
+    }
+    long long t1 = clock64();
+    if (lane == 0) cyc[blockIdx.x] = t1 - t0, stop = 1;
+    tc_fence_before();
+  } else if (warp == 5 && (traffic & 1) && lane == 0) {
+    uint32_t ph = 0;
+    while (!stop) {
+      mbar_expect_tx(&bar_ld, kScratch);
+      bulk_g2s(scratch, gsrc + (size_t)blockIdx.x * kScratch, kScratch, &bar_ld);
+      mbar_wait(&bar_ld, ph);
+      ph ^= 1;
+    }
+  } else if (warp >= 6 && (traffic & 2)) {
+    // warps 6..9: write a slab image the way the epilogue stages it; lane 0 of warp 6 copies it out
+    const int w = warp - 6;
+    uint32_t ph = 0;
+    while (true) {
+      for (int q = 0; q < 4; ++q) {
+        const int rr = w * 32 + lane;
+        *reinterpret_cast<uint4*>(stagebuf + (rr >> 3) * 1024 + (rr & 7) * 128 + ((q ^ (rr & 7)) << 4)) = make_uint4(rr, q, ph, 0);
+        *reinterpret_cast<uint4*>(stagebuf + (rr >> 3) * 1024 + (rr & 7) * 128 + (((q + 4) ^ (rr & 7)) << 4)) = make_uint4(rr, q, ph, 1);
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_st);
+      if (w == 0 && lane == 0) {
+        mbar_wait(&bar_st, ph);
+        bulk_s2g(gdst + (size_t)blockIdx.x * kStage, stagebuf, kStage);
+        bulk_commit();
+        bulk_wait_read0();
+        stop2[ph] = stop;
+      }
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      if (stop2[ph]) break;      // one decision for the four warps
+      ph ^= 1;
+    }
+    if (w == 0 && lane == 0) bulk_wait_all0();
+  }
+  __syncthreads();
+  tc_fence_after();
+  if (warp < 4) {
+    const int m = rank * 128 + warp * 32 + lane;
+    const uint32_t t = tbase + ((uint32_t)(warp * 32) << 16) + 256;
+    for (int c0 = 0; c0 < 256; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(t + c0, v);
+      tmem_ld_wait();
+      if (blockIdx.x < G)
+        for (int i = 0; i < 32; ++i) out[m * 256 + c0 + i] = __uint_as_float(v[i]);
+    }
+  }
+  tc_fence_before();
+  if (G == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 4) t_dealloc<G>(tbase, 512);
+}
+
+template <int G, int CE>
+int run(const char* what, float* out, long long* cyc, uint8_t* gsrc, uint8_t* gdst) {
+  const size_t smem = 4 * 32768 + kScratch + kStage + 1024;
+  const int commit_every = CE;
+  cudaFuncSetAttribute(k<G, CE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static float h[256 * 256];
+  const int reps = 200, layers = 16;
+  const char* tn[4] = {"quiet", "+ refill loads", "+ staging stores", "+ loads + stores"};
+  for (int traffic = 0; traffic < 4; traffic += 3) {
+    for (int rep = 0; rep < 2; ++rep) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(148), cfg.blockDim = dim3(320), cfg.dynamicSmemBytes = smem;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = G, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
+      cfg.attrs = at, cfg.numAttrs = 1;
+      cudaError_t e = cudaLaunchKernelEx(&cfg, k<G, CE>, traffic, reps, layers, out, cyc, (const uint8_t*)gsrc, gdst);
+      if (e == cudaSuccess) e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) {
+        printf("%s traffic %d: %s\n", what, traffic, cudaGetErrorString(e));
+        return 1;
+      }
+    }
+    long long c;
+    cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost);
+    cudaMemcpy(h, out, sizeof(float) * 128 * G * 256, cudaMemcpyDeviceToHost);
+    int bad = 0;
+    double maxerr = 0;
+    for (int m = 0; m < 128 * G; ++m)
+      for (int n = 0; n < 256; ++n) {
+        double ref = 0;
+        for (int kk = 0; kk < 256; ++kk) ref += (double)a_val(m, kk) * b_val(n, kk);
+        const double err = fabs(ref - h[m * 256 + n]);
+        if (err > maxerr) maxerr = err;
+        if (err > 1e-3 && bad++ < 4) printf("   mismatch m=%d n=%d got %f want %f\n", m, n, h[m * 256 + n], ref);
+      }
+    printf("%-16s %-18s commit every %2d MMAs: %7.1f cycles per M%d N256 K16 instruction, KAT %s (max err %.3g, %d bad)\n", what,
+           tn[traffic], commit_every ? commit_every : 16 * layers, (double)c / reps / (16.0 * layers), 128 * G, bad ? "FAIL" : "ok", maxerr, bad);
+  }
+  return 0;
+}
+
+int main() {
+  setvbuf(stdout, nullptr, _IONBF, 0);
+  float* out;
+  long long* cyc;
+  uint8_t *gsrc, *gdst;
+  cudaMalloc(&out, 256 * 256 * 4);
+  cudaMalloc(&cyc, 148 * 8);
+  cudaMalloc(&gsrc, 148 * kScratch);
+  cudaMalloc(&gdst, 148 * kStage);
+  cudaMemset(gsrc, 0, 148 * kScratch);
+  if (run<1, 0>("cta_group::1", out, cyc, gsrc, gdst)) return 1;
+  if (run<2, 0>("cta_group::2", out, cyc, gsrc, gdst)) return 1;
+  if (run<1, 16>("cta_group::1", out, cyc, gsrc, gdst)) return 1;
+  if (run<1, 4>("cta_group::1", out, cyc, gsrc, gdst)) return 1;
+  if (run<2, 4>("cta_group::2", out, cyc, gsrc, gdst)) return 1;
+  if (run<1, 1>("cta_group::1", out, cyc, gsrc, gdst)) return 1;
+  return 0;
+}
