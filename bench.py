@@ -124,10 +124,48 @@ def make_batch(n_rand, seed):
     return ro.float(), rd.float(), tgt.float(), dep.float(), n_rgb, n_dep
 
 
-def run_reference(args):
-    """CPU arm: the oracle port of the reference's render + loss + backward on a bounded ray sample."""
+def _ref_step_fn(n_sample, semK=0, seed=3407):
+    """One step of the reference's CPU path (oracle port): render + loss + backward on n_sample rays."""
     import torch
     from oracle import nerf_oracle as O
+    spec_c = O.MLPSpec(D=COARSE_D, semantic_num_classes=semK)
+    spec_f = O.MLPSpec(D=FINE_D, semantic_num_classes=semK)
+    pc = {k: v.requires_grad_(True) for k, v in O.init_params(spec_c, 3407 + COARSE_D).items()}
+    pf = {k: v.requires_grad_(True) for k, v in O.init_params(spec_f, 3407 + FINE_D).items()}
+    ro, rd, tgt, dep, n_rgb, n_dep = make_batch(n_sample, seed)
+    rb = O.pack_rays(H, W, FOCAL, ro, rd)
+    tsem = torch.randint(0, semK, (n_rgb,), generator=torch.Generator().manual_seed(seed)) if semK else None
+
+    def step():
+        rng = O.RenderRNG(torch.rand(n_sample, N_SAMPLES), torch.randn(n_sample, N_SAMPLES),
+                          torch.rand(n_sample, N_IMPORTANCE), torch.randn(n_sample, N_SAMPLES + N_IMPORTANCE))
+        out = O.render_rays(rb, pc, spec_c, pf, spec_f, N_SAMPLES, N_IMPORTANCE, rng, raw_noise_std=1.0,
+                            semantic_loss=bool(semK))
+        res = O.train_loss(out, n_rgb, tgt, dep, depth_lambda=DEPTH_LAMBDA, depth_importance=1.0,
+                           target_semantic=tsem, semantic_lambda=SEMANTIC_LAMBDA if semK else 0.0)
+        for p in list(pc.values()) + list(pf.values()):
+            p.grad = None
+        res["loss"].backward()
+        return float(res["loss"].detach())
+    return step, n_rgb, n_dep
+
+
+def _time_steps(step, steps, warmup):
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    return (time.perf_counter() - t0) / max(steps, 1)
+
+
+def run_reference(args):
+    """CPU arm: the oracle port of the reference's render + loss + backward on the box's host cores -- the WHOLE
+    N_rand-ray step when the host has the memory for its fp32 activations (~2.6 MB/ray) and K+W steps of it fit a few
+    minutes, else a bounded ray sample (rays/s on the CPU does not depend on the batch size).  The timed loop runs with
+    anomaly detection off; the as-shipped setting (`torch.autograd.set_detect_anomaly(True)`, run_nerf_helpers.py:6)
+    and the semantic-head variant (fern_dsnerf.txt:55) are timed on 2 steps each and reported beside it."""
+    import torch
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -137,52 +175,74 @@ def run_reference(args):
     except (AttributeError, OSError):
         torch.set_num_threads(os.cpu_count() or 1)
     torch.manual_seed(3407)
+    torch.autograd.set_detect_anomaly(False)
     total = args.steps + args.warmup
-    n_sample = int(max(128, min(1024, (60000 // max(total, 1)) // 64 * 64)))
-    spec_c, spec_f = O.MLPSpec(D=COARSE_D), O.MLPSpec(D=FINE_D)
-    pc = {k: v.requires_grad_(True) for k, v in O.init_params(spec_c, 3407 + COARSE_D).items()}
-    pf = {k: v.requires_grad_(True) for k, v in O.init_params(spec_f, 3407 + FINE_D).items()}
-    ro, rd, tgt, dep, n_rgb, n_dep = make_batch(n_sample, 3407)
-    rb = O.pack_rays(H, W, FOCAL, ro, rd)
-
-    def step():
-        rng = O.RenderRNG(torch.rand(n_sample, N_SAMPLES), torch.randn(n_sample, N_SAMPLES),
-                          torch.rand(n_sample, N_IMPORTANCE), torch.randn(n_sample, N_SAMPLES + N_IMPORTANCE))
-        out = O.render_rays(rb, pc, spec_c, pf, spec_f, N_SAMPLES, N_IMPORTANCE, rng, raw_noise_std=1.0)
-        res = O.train_loss(out, n_rgb, tgt, dep, depth_lambda=DEPTH_LAMBDA, depth_importance=1.0)
-        for p in list(pc.values()) + list(pf.values()):
-            p.grad = None
-        res["loss"].backward()
-        return float(res["loss"].detach())
-
-    for _ in range(args.warmup):
-        step()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step()
-    dt = (time.perf_counter() - t0) / max(args.steps, 1)
+    n_rand = rays_per_gpu(args)
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except Exception:
+        avail = 0
+    # ~1 300 rays/s on 16 cores: the whole step if K+W of them take < ~4 min, else a 64-ray multiple that does
+    budget_rays = int(240.0 * 1300.0 / max(total, 1))
+    n_sample = n_rand if (n_rand <= budget_rays and avail > n_rand * 6.0e6) else int(
+        max(128, min(n_rand, 1024, budget_rays // 64 * 64)))
+    step, n_rgb, n_dep = _ref_step_fn(n_sample)
+    dt = _time_steps(step, args.steps, args.warmup)
     v = n_sample / dt
     cores = torch.get_num_threads()
+    # as shipped: anomaly detection on (2 steps after 1 warm-up, same sample)
+    torch.autograd.set_detect_anomaly(True)
+    try:
+        dt_anom = _time_steps(step, 2, 1)
+    finally:
+        torch.autograd.set_detect_anomaly(False)
+    del step
+    # fern_dsnerf.txt:55-56 as shipped: semantic head on (19 classes), anomaly off
+    n_sem = min(n_sample, 1024)
+    sem_step, _, _ = _ref_step_fn(n_sem, semK=19)
+    dt_sem = _time_steps(sem_step, 2, 1)
     sample = "%d of the %d rays of the step (%d RGB + %d depth), full 64+64 samples, D=%d/%d nets" % (
-        n_sample, args.n_rand, n_rgb, n_dep, COARSE_D, FINE_D)
+        n_sample, n_rand, n_rgb, n_dep, COARSE_D, FINE_D)
     print(json.dumps({
         "impl": "reference", "metric": "training rays/sec (fwd+bwd)", "value": v, "unit": "rays/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, 1),
+        "higher_is_better": True, "scaling": scaling_kind(args), "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args),
         "cpu_baseline": {"value": v, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample,
-                         "os_cpu_count": os.cpu_count(), "anomaly_detection": False},
+                         "os_cpu_count": os.cpu_count(), "anomaly_detection": False,
+                         "anomaly_on": {"value": n_sample / dt_anom, "unit": "rays/s", "ms_per_step": dt_anom * 1e3,
+                                        "what": "torch.autograd.set_detect_anomaly(True) as run_nerf_helpers.py:6 ships it; "
+                                                "2 steps after 1 warm-up on the same sample"}},
+        "variants": {"semantic_head_19_classes": {
+            "value": n_sem / dt_sem, "unit": "rays/s", "ms_per_step": dt_sem * 1e3,
+            "what": "semantic_loss = True (fern_dsnerf.txt:55-56), %d rays, anomaly off, 2 steps after 1 warm-up" % n_sem}},
         "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
-def workload_config(args, world):
+def rays_per_gpu(args):
+    """--global-n-rand G (strong scaling, config E): G rays per step split evenly over the GPUs; else --n-rand each."""
+    if args.global_n_rand:
+        return max(2, args.global_n_rand // max(args.gpus, 1))
+    return args.n_rand
+
+
+def scaling_kind(args):
+    return "strong" if args.global_n_rand else "weak"
+
+
+def workload_config(args):
+    """Identical in both arms (`--impl ours` / `--impl reference`) for the same command line."""
+    world, n_rand = max(args.gpus, 1), rays_per_gpu(args)
     return {"workload": "fern_dsnerf.txt coarse+fine training step with depth loss, synthetic LLFF-shaped rays",
-            "n_rand_per_gpu": args.n_rand, "global_rays_per_step": args.n_rand * world,
-            "rgb_rays": args.n_rand - args.n_rand // 2, "depth_rays": args.n_rand // 2,
+            "n_rand_per_gpu": n_rand, "global_rays_per_step": n_rand * world,
+            "rgb_rays": n_rand - n_rand // 2, "depth_rays": n_rand // 2,
             "N_samples": N_SAMPLES, "N_importance": N_IMPORTANCE, "netdepth": COARSE_D, "netdepth_fine": FINE_D,
             "netwidth": 256, "use_viewdirs": True, "perturb": 1.0, "raw_noise_std": 1.0, "ndc": True,
             "depth_lambda": DEPTH_LAMBDA, "optimizer_step": "excluded (BASELINE.md §3)",
             "parallelism": "ray-sharded dp%d, NCCL all-reduce of MLP grads" % world,
+            "semantic_head": ("off (headline workload: RGB + LiDAR-depth loss; the head-on step is in `variants`)" if not args.semantic else
+                              "on: %d classes, cross-entropy of fine + coarse per-ray logits, lambda %g (fern_dsnerf.txt:55-56)" % (args.semantic, SEMANTIC_LAMBDA)),
             "l2": "per-step working set (activation stashes, ~1.5 MB/ray = 6 GB per 4096-ray step) is far larger than the 126 MB L2; no flush"}
 
 
@@ -213,7 +273,24 @@ def cpu_baseline(seconds_budget=25.0):
             break
     ts = sorted(times[1:])
     med = ts[len(ts) // 2]
-    return {"value": n / med, "unit": "rays/s", "cores": torch.get_num_threads(), "kind": "port",
+    # as shipped (run_nerf_helpers.py:6): anomaly detection on, 2 more steps
+    torch.autograd.set_detect_anomaly(True)
+    try:
+        ta = []
+        for it2 in range(2):
+            rng = O.synth_rng(n, N_SAMPLES, N_IMPORTANCE, seed=100 + it2)
+            t0 = time.perf_counter()
+            out = O.render_rays(rb, pc, spec_c, pf, spec_f, N_SAMPLES, N_IMPORTANCE, rng, raw_noise_std=1.0)
+            res = O.train_loss(out, n_rgb, tgt, dep, depth_lambda=DEPTH_LAMBDA, depth_importance=1.0)
+            for p in list(pc.values()) + list(pf.values()):
+                p.grad = None
+            res["loss"].backward()
+            ta.append(time.perf_counter() - t0)
+    finally:
+        torch.autograd.set_detect_anomaly(False)
+    return {"anomaly_on": {"value": n / min(ta), "unit": "rays/s", "ms_per_step": min(ta) * 1e3,
+                           "what": "torch.autograd.set_detect_anomaly(True) as run_nerf_helpers.py:6 ships it; best of 2"},
+            "value": n / med, "unit": "rays/s", "cores": torch.get_num_threads(), "kind": "port",
             "sample": "config A: 1024 rays (512 RGB + 512 depth), 64+64 samples, D=4/8; median of %d steps after 1 warm-up"
                       % len(ts), "os_cpu_count": os.cpu_count(), "ms_per_step": med * 1e3, "anomaly_detection": False}
 
@@ -228,6 +305,8 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
+    args.gpus = world
+    args.n_rand = rays_per_gpu(args)          # --global-n-rand: the step's rays split evenly over the ranks
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -360,22 +439,29 @@ def run_ours(args):
         if k in flops:
             kern[k]["tflops"] = flops[k] / (kern[k]["ms_per_launch"] * 1e-3) / 1e12
             kern[k]["frac_of_sustained_peak"] = kern[k]["tflops"] / pk["tf_sust"]
+            kern[k]["frac_of_burst_peak"] = kern[k]["tflops"] / pk["tf_burst"]
     mlp_keys = [k for k in kern if k in flops]
     top = max(mlp_keys, key=lambda k: kern[k]["ms_per_step"])
     mlp_ms = sum(kern[k]["ms_per_step"] for k in mlp_keys)
     mlp_tflops = sum(flops[k] for k in mlp_keys) / (mlp_ms * 1e-3) / 1e12
-    traffic = None      # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
-    try:
-        tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_traffic.json")))
-        if tj.get("n_rand") == args.n_rand:
-            traffic = tj["dram_bytes_per_launch"].get(top)
-    except (OSError, ValueError, KeyError):
-        pass
-    roofline = {"kernel": top, "bound": "tensor", "achieved": kern[top]["tflops"], "peak": pk["tf_sust"],
-                "unit": "TFLOP/s", "frac": kern[top]["tflops"] / pk["tf_sust"], "traffic": traffic,
-                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (%s)" % pk["src"],
+    traffic, traffic_from = None, None   # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", name)))
+            if tj.get("n_rand") == args.n_rand and tj["dram_bytes_per_launch"].get(top):
+                traffic, traffic_from = tj["dram_bytes_per_launch"][top], "profiles/" + name
+                break
+        except (OSError, ValueError, KeyError):
+            pass
+    # the timed region is ~60 ms at full clocks: the burst figure is the applicable peak (a kernel timed alone)
+    roofline = {"kernel": top, "bound": "tensor", "achieved": kern[top]["tflops"], "peak": pk["tf_burst"],
+                "unit": "TFLOP/s", "frac": kern[top]["tflops"] / pk["tf_burst"], "traffic": traffic,
+                "traffic_from": traffic_from,
+                "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst, %s); frac_of_sustained uses bf16_tflops_sustained %.1f" % (pk["src"], pk["tf_sust"]),
+                "frac_of_sustained": kern[top]["tflops"] / pk["tf_sust"],
                 "share_of_step": kern[top]["ms_per_step"] / ms_share,
-                "all_mlp_kernels": {"tflops": mlp_tflops, "frac": mlp_tflops / pk["tf_sust"],
+                "all_mlp_kernels": {"tflops": mlp_tflops, "frac": mlp_tflops / pk["tf_burst"],
+                                    "frac_of_sustained": mlp_tflops / pk["tf_sust"],
                                     "ms_per_step": mlp_ms, "share_of_step": mlp_ms / ms_share},
                 "share_basis_ms_per_step": ms_share,
                 "flops_basis": "algorithmic unpadded MACs/point of the reference's layer structure (SURVEY §8d) x points "
@@ -443,11 +529,10 @@ def run_ours(args):
         print(json.dumps({
             "metric": "training rays/sec (fwd+bwd)", "value": value, "unit": "rays/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": dict(workload_config(args, world), semantic_head=(
-                "off (headline workload: RGB + LiDAR-depth loss)" if not semK else
-                "on: %d classes, cross-entropy of fine + coarse per-ray logits, lambda %g (fern_dsnerf.txt:55-56)" % (semK, SEMANTIC_LAMBDA)),
-                value_route={"graph": "dlnerf_b200.GraphedTrainStep (CUDA graph of train_step)", "fused": "dlnerf_b200.train_step", "dropin": "render()+loss.backward()"}[args.path]), "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches,
+            "scaling": scaling_kind(args), "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": workload_config(args),
+            "value_route": {"graph": "dlnerf_b200.GraphedTrainStep (CUDA graph of train_step)", "fused": "dlnerf_b200.train_step", "dropin": "render()+loss.backward()"}[args.path],
+            "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches,
             "roofline": roofline, "cpu_baseline": cb, "variants": variants, "kernels": kern,
             "kernel_times_from": kernel_times_from}))
     if world > 1:
@@ -460,6 +545,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--n-rand", type=int, default=4096, help="rays per step per GPU (config B: 4096)")
+    ap.add_argument("--global-n-rand", type=int, default=0,
+                    help="strong-scaling mode (config E, 16k-256k rays): rays per step of the WHOLE job, split evenly over "
+                         "the GPUs; overrides --n-rand and reports \"scaling\": \"strong\"")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-variants", action="store_true", help="skip the semantic-head variant of the step")

@@ -22,12 +22,20 @@ def _run(args, timeout):
 
 
 def test_reference_arm_prints_one_contract_line():
-    d = _run(["--impl", "reference", "--steps", "1", "--warmup", "0"], timeout=600)
+    d = _run(["--impl", "reference", "--steps", "1", "--warmup", "0", "--n-rand", "512"], timeout=600)
     assert BASE_KEYS <= set(d) and d["impl"] == "reference"
     assert d["metric"] == "training rays/sec (fwd+bwd)" and d["unit"] == "rays/s" and d["higher_is_better"] is True
     assert d["value"] > 0 and d["vs_baseline"] is None and "workload" in d["config"]
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert cb["anomaly_detection"] is False and cb["anomaly_on"]["value"] > 0          # both settings
+    assert d["variants"]["semantic_head_19_classes"]["value"] > 0                       # fern_dsnerf.txt:55 as shipped
+    # the same command line gives the same `config` in both arms (checked key by key on the GPU box)
+    sys.path.insert(0, ROOT)
+    import argparse
+    import bench
+    ns = argparse.Namespace(gpus=1, n_rand=512, global_n_rand=0, semantic=0)
+    assert d["config"] == bench.workload_config(ns)
     assert d["e2e"] == {"value": d["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
