@@ -110,22 +110,48 @@ SIGNATURES = {
 }
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "--expt-relaxed-constexpr", "-shared", "-Xcompiler", "-fPIC"]
+              "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC"]
+OBJ_DIR = os.path.join(_HERE, "build")
 
 
 def build(verbose: bool = False, force: bool = False) -> str:
-    """Compile csrc/*.cu for sm_100a into the in-tree shared library (nvcc cross-compiles without a GPU)."""
+    """Compile csrc/*.cu for sm_100a into the in-tree shared library (nvcc cross-compiles without a GPU).  Every
+    source becomes its own object (compiled in parallel, rebuilt only when it or a header changed) and the objects
+    are linked into libdlnerf_b200.so."""
+    import glob
+    from concurrent.futures import ThreadPoolExecutor
     srcs = [os.path.join(CSRC, s) for s in SOURCES]
-    deps = srcs + [os.path.join(CSRC, "common.cuh"), os.path.join(ROOT, "include", "dlnerf_b200.h")]
-    if not force and os.path.exists(SO_PATH) and all(os.path.getmtime(SO_PATH) >= os.path.getmtime(d) for d in deps):
-        return SO_PATH
+    hdrs = sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + [os.path.join(ROOT, "include", "dlnerf_b200.h")]
+    hdr_time = max(os.path.getmtime(h) for h in hdrs)
+    if not force and os.path.exists(SO_PATH) and os.path.getmtime(SO_PATH) >= max([hdr_time] + [os.path.getmtime(x) for x in srcs]):
+        return SO_PATH          # up to date (the objects do not travel to the GPU box, the library does)
+    os.makedirs(OBJ_DIR, exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO_PATH] + srcs
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    if verbose:
-        print(res.stderr)
+    extra = os.environ.get("DLN_NVCC_EXTRA", "").split()
+    objs, todo = [], []
+    for src in srcs:
+        obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".o")
+        objs.append(obj)
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), hdr_time):
+            todo.append((src, obj))
+
+    def compile_one(job):
+        src, obj = job
+        cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+        return src, subprocess.run(cmd, capture_output=True, text=True)
+
+    if todo:
+        with ThreadPoolExecutor(max_workers=len(todo)) as ex:
+            results = list(ex.map(compile_one, todo))
+        for src, res in results:
+            if res.returncode != 0:
+                raise RuntimeError("nvcc failed on %s:\n%s%s" % (src, res.stdout, res.stderr))
+            if verbose:
+                print(res.stderr)
+    if todo or not os.path.exists(SO_PATH) or any(os.path.getmtime(SO_PATH) < os.path.getmtime(o) for o in objs):
+        res = subprocess.run([nvcc, "-shared", "-o", SO_PATH] + objs, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("link failed:\n" + res.stdout + res.stderr)
     return SO_PATH
 
 
