@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
 CSRC = os.path.join(_HERE, "csrc")
 SO_PATH = os.environ.get("DLN_SO_PATH") or os.path.join(_HERE, "libdlnerf_b200.so")   # override: A/B builds of the kernels
-SOURCES = ["render_kernels.cu", "mlp_kernels.cu", "optim_kernels.cu", "semantic_kernels.cu", "raygen_kernels.cu"]
+SOURCES = ["render_kernels.cu", "mlp_kernels.cu", "mlp_chain2.cu", "optim_kernels.cu", "semantic_kernels.cu", "raygen_kernels.cu"]
 
 MAX_STEPS = 12
 MAX_KSLABS = 6

@@ -134,7 +134,7 @@ __device__ __forceinline__ void add2(float& a0, float& a1, float b0, float b1) {
 // and a 128-wide output keeps all four warpgroups busy.  relu-mask word h of the thread's uint2 covers chunk h.
 //
 // One 32-column chunk of an epilogue: TMEM values -> (+bias | +dsigma*head) -> relu / mask -> 16 packed bf16x2 words.
-template <int EPI>
+template <int EPI, bool kBiasLdg = false>      // kBiasLdg: the bias vector lives in global memory (read-only path) instead of smem
 __device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], const float* __restrict__ bias,
                                           const float* __restrict__ hw, int n_out, int nheads, float dsig,
                                           uint32_t mw_in, uint32_t& mw_out, float (&hacc)[5], uint32_t (&pk)[16],
@@ -147,7 +147,8 @@ __device__ __forceinline__ void epi_chunk(const uint32_t (&v)[32], const float* 
   if (kFwd) {
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-      const float4 b = *reinterpret_cast<const float4*>(bias + cb + 4 * q);   // smem broadcast
+      const float4 b = kBiasLdg ? __ldg(reinterpret_cast<const float4*>(bias + cb + 4 * q))
+                                : *reinterpret_cast<const float4*>(bias + cb + 4 * q);   // smem broadcast
       add2(f[4 * q], f[4 * q + 1], b.x, b.y);
       add2(f[4 * q + 2], f[4 * q + 3], b.z, b.w);
     }

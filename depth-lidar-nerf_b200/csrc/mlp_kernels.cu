@@ -20,6 +20,7 @@
 // lane, warp 3 weight-arrival helper, warps 4..19 epilogue (four warpgroups; warpgroup g owns the columns
 // [128 h + 32 g, +32), h = 0, 1, of every layer output).
 #include "chain_common.cuh"
+#include <stdlib.h>
 
 using namespace dln;
 
@@ -802,6 +803,18 @@ __global__ void pack_kernel(const float* __restrict__ params, const DlnPackJob* 
 // ================================================================================================
 // C ABI
 // ================================================================================================
+int dln_chain2_launch(const DlnChainProgram* prog, const DlnChainArgs* args, int num_sms, long long n_tiles, cudaStream_t stream);
+
+// DLN_CHAIN=1 selects the one-tile-per-CTA kernel of this file, anything else the CTA-pair kernel (mlp_chain2.cu)
+static int chain_variant() {
+  static int v = 0;
+  if (!v) {
+    const char* e = getenv("DLN_CHAIN");
+    v = (e && e[0] == '1') ? 1 : 2;
+  }
+  return v;
+}
+
 extern "C" {
 
 int dln_mlp_chain(const DlnChainProgram* prog, const DlnChainArgs* args, int num_sms, void* stream) {
@@ -833,6 +846,7 @@ int dln_mlp_chain(const DlnChainProgram* prog, const DlnChainArgs* args, int num
   if (args->stash && prog->stash_slots > 0) DLN_CHECK_ARG((reinterpret_cast<uintptr_t>(args->stash) & 15) == 0);
   if (args->P == 0) return DLN_OK;
   const long long n_tiles = (args->P + DLN_TILE_ROWS - 1) / DLN_TILE_ROWS;
+  if (chain_variant() == 2) return dln_chain2_launch(prog, args, num_sms, n_tiles, (cudaStream_t)stream);
   bool& attr_set = dln_device_flag(0);     // the attribute is per device (context), not per process
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemBytes);

@@ -8,6 +8,7 @@ Same names, argument meaning and error behaviour; the arithmetic runs in the sm_
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import List, Optional
 
 import numpy as np
@@ -71,6 +72,38 @@ def get_embedder(multires, i=0):
 # --------------------------------------------------------------------------------------------------
 # Model (run_nerf_helpers.py:77-174)
 # --------------------------------------------------------------------------------------------------
+_BWD_SIDE = {}          # device -> [side stream, "an MLP backward of the running autograd pass is on it"]
+
+
+def _overlapped_backward(net: "NeRF", d_out, saved, run):
+    """The drop-in route's counterpart of train_step's second stream.  Autograd runs the fine network's MLP backward
+    first (it was recorded last) and then the coarse compositing + MLP backward, which do not depend on it: the FIRST MLP
+    backward of an autograd pass is launched on a side stream and joined when the pass ends
+    (``queue_callback``), so the rest of the pass overlaps its ~1.5 ms of dgrad / wgrad kernels.  Only when the gradients
+    are handed over by reference (every ``p.grad`` is None, as after ``optimizer.zero_grad()``): an accumulating
+    ``p.grad += g`` would run on the main stream before the join.  ``DLN_NO_BWD_OVERLAP=1`` switches it off."""
+    dev = d_out.device
+    ent = _BWD_SIDE.get(dev)
+    if ent is None:
+        ent = _BWD_SIDE[dev] = [torch.cuda.Stream(device=dev), False]
+    if (ent[1] or os.environ.get("DLN_NO_BWD_OVERLAP") or torch.cuda.is_current_stream_capturing()
+            or any(p.grad is not None for p in net._ordered_params())):
+        return run()
+    side, main = ent[0], torch.cuda.current_stream(dev)
+    side.wait_stream(main)
+    for t in [d_out] + [x for x in saved if torch.is_tensor(x)]:
+        t.record_stream(side)               # allocated on the main stream, read on the side stream
+    with torch.cuda.stream(side):
+        grads = run()
+    ent[1] = True
+
+    def join():
+        main.wait_stream(side)
+        ent[1] = False
+    torch.autograd.Variable._execution_engine.queue_callback(join)
+    return grads
+
+
 class _MLP(torch.autograd.Function):
     """Fused MLP forward + (dgrad chain, wgrad GEMMs) backward.  Gradients flow to the parameters
     only: on the reference's training path the network inputs never require grad."""
@@ -86,7 +119,8 @@ class _MLP(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_out):
         net: "NeRF" = ctx.net
-        grads = net._run_backward(d_out, ctx.saved, ctx.P)
+        saved, P = ctx.saved, ctx.P
+        grads = _overlapped_backward(net, d_out, saved, lambda: net._run_backward(d_out, saved, P))
         ctx.saved = None
         return (None, None, None, None, None, None) + tuple(grads)
 
@@ -111,7 +145,10 @@ class _MLPSem(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_out, d_sem, _d_pts):
         net: "NeRF" = ctx.net
-        grads = net._run_backward(d_out, ctx.saved, ctx.P, d_sem=d_sem)
+        saved, P = ctx.saved, ctx.P
+        if torch.is_tensor(d_sem):
+            d_sem.record_stream(_BWD_SIDE.setdefault(d_out.device, [torch.cuda.Stream(device=d_out.device), False])[0])
+        grads = _overlapped_backward(net, d_out, saved, lambda: net._run_backward(d_out, saved, P, d_sem=d_sem))
         ctx.saved = None
         return (None,) * 8 + tuple(grads)
 

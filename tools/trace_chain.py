@@ -39,8 +39,29 @@ for it in range(3):
     args.trace = trace.data_ptr() if it == 2 else None
     L.check(L.lib().dln_mlp_chain(C.byref(prog), C.byref(args), st["sms"], dn.ops._stream()), "chain")
 torch.cuda.synchronize()
-t = (trace.cpu()[:128] & 0xFFFF).view(16, 8)
 n_steps = prog.n_steps
+if os.environ.get("DLN_CHAIN", "2") != "1":
+    # CTA-pair kernel: 8 consecutive (round, step) pairs from index 10 on, per slot: MMA first issue / commit issued,
+    # epilogue thread 0: accumulator seen / stores done / hand-off (+ next prologue) done
+    t = (trace.cpu()[:128] & 0xFFFF).view(8, 16)
+    if not any(int(x) for x in t[0]):
+        print("no timeline recorded (build with DLN_NVCC_EXTRA=-DDLN_CHAIN2_TRACE for it)")
+        sys.exit(0)
+    t0 = min(int(x) for x in t[0] if int(x))
+    rel = lambda x: (((int(x) - t0) & 0xFFFF) << 3) if int(x) else -1
+    print("%s D=%d keep=%d: %d steps per tile; (round, step) index 10..17 of CTA 0 (leader of pair 0)" % ("dgrad" if bwd else "fwd", D, keep, n_steps))
+    print("  idx s | X: mma-first mma-commit  acc-seen stores-done handed-off | Y: mma-first mma-commit  acc-seen stores-done handed-off")
+    for i in range(8):
+        r = [rel(x) for x in t[i]]
+        print("%5d %d | %10d %10d %9d %11d %10d | %10d %10d %9d %11d %10d" % (
+            10 + i, (10 + i) % n_steps, r[0], r[1], r[2], r[3], r[4], r[8], r[9], r[10], r[11], r[12]))
+    print("epilogue thread 0, cycles after acc-seen: first tmem load landed / chunk 0 converted / second load landed (chunk 0 stored) / stores done / handed off")
+    for i in range(8):
+        r = [rel(x) for x in t[i]]
+        f = lambda o: " ".join("%6d" % (r[o + k] - r[o + 2]) for k in (5, 6, 7, 3, 4))
+        print("%5d %d | X: %s | Y: %s" % (10 + i, (10 + i) % n_steps, f(0), f(8)))
+    sys.exit(0)
+t = (trace.cpu()[:128] & 0xFFFF).view(16, 8)
 t0 = int(t[0, 0])
 rel = lambda x: (((int(x) - t0) & 0xFFFF) << 3) if int(x) else -1
 print("%s D=%d keep=%d: %d steps per tile; gsteps 8..23 of CTA 0" % ("dgrad" if bwd else "fwd", D, keep, n_steps))
