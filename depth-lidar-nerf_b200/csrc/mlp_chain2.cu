@@ -181,12 +181,14 @@ __device__ __forceinline__ void epi2_chunk(const uint32_t (&v)[32], const float4
 #pragma unroll
     for (int i = 0; i < 32; ++i) f[i] = (mw_in & (1u << i)) ? f[i] : 0.f;
   }
-  if (kFwd && nheads > 0) {
+  // heads: fixed counts for the sigma (1) and rgb (3) steps, run-time count for output_linear (and 0 for plain ReLU)
+  constexpr int kHeads = EPI == DLN_EPI_RELU_SIGMA ? 1 : EPI == DLN_EPI_RELU_RGB ? 3 : EPI == DLN_EPI_RELU_OUT ? 5 : 0;
+  if (kHeads > 0 && (EPI != DLN_EPI_RELU_OUT || nheads > 0)) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
 #pragma unroll
-    for (int h = 0; h < 5; ++h)
-      if (h < nheads) {
+    for (int h = 0; h < kHeads; ++h)
+      if (EPI != DLN_EPI_RELU_OUT || h < nheads) {
         float a = 0.f;
         const float* w = hw + h * n_out + cb;
 #pragma unroll
@@ -556,6 +558,11 @@ __global__ void __launch_bounds__(k2Threads, 1)
       }
     }
     for (long long rnd = 0; rnd < n_rounds; ++rnd) {
+      // per-round invariants of the two slots (kept out of the step loop: the epilogue is instruction-issue bound)
+      const long long tile0 = tile_of(rnd, 0), tile1 = tile0 + 1;
+      const bool ok0 = tile0 < n_tiles, ok1 = tile1 < n_tiles;
+      uint32_t* const mtile0 = reinterpret_cast<uint32_t*>(args.masks) + (size_t)(ok0 ? tile0 : 0) * 1024;
+      uint32_t* const mtile1 = reinterpret_cast<uint32_t*>(args.masks) + (size_t)(ok1 ? tile1 : 0) * 1024;
       for (int s = 0; s < n_steps; ++s, ++nev) {
         const DlnChainStep& st = prog.steps[s];
         const int epi = st.epi, n_out = st.n_out, mask_slot = st.mask_slot;
@@ -571,16 +578,19 @@ __global__ void __launch_bounds__(k2Threads, 1)
         const float* const brow = kBwd ? hw : args.fblob + st.bias_off;
         const bool need_b = !kBwd || epi == DLN_EPI_BWD_MASK_SIGMA;
         const bool use_mi = kBwd && epi >= DLN_EPI_BWD_MASK && mask_slot >= 0;
-        const bool fast = nheads == 0 && n_out == 256 && (kBwd ? (epi == DLN_EPI_BWD_MASK || epi == DLN_EPI_BWD_MASK_SIGMA) && mask_slot >= 0
-                                                               : epi == DLN_EPI_RELU);
+        const size_t mask_step_off = (size_t)(mask_slot < 0 ? 0 : mask_slot) * (size_t)n_tiles * 1024;
+        // steps with a compile-time specialised epilogue: the plans of every shipped configuration consist of these
+        const bool fast = kBwd ? n_out == 256 && (epi == DLN_EPI_BWD_MASK || epi == DLN_EPI_BWD_MASK_SIGMA) && mask_slot >= 0
+                               : (n_out == 256 && ((epi == DLN_EPI_RELU && nheads == 0) || (epi == DLN_EPI_RELU_SIGMA && nheads == 1))) ||
+                                     (n_out == 128 && epi == DLN_EPI_RELU_RGB && nheads == 3 && kFastChunks >= 2);
 #pragma unroll 1
         for (int slot = 0; slot < 2; ++slot) {
-          const long long tile = tile_of(rnd, slot);
+          const long long tile = slot ? tile1 : tile0;
           const long long p = tile * DLN_TILE_ROWS + r;
-          const bool valid = p < args.P, tile_ok = tile < n_tiles;
+          const bool valid = p < args.P, tile_ok = slot ? ok1 : ok0;
           const float dsig = slot ? dsig1 : dsig0;
           const float* semrow = kSem ? (slot ? sem1 : sem0) : nullptr;
-          uint32_t* const mblock = reinterpret_cast<uint32_t*>(args.masks) + ((size_t)(mask_slot < 0 ? 0 : mask_slot) * n_tiles + (tile_ok ? tile : 0)) * 1024;
+          uint32_t* const mblock = (slot ? mtile1 : mtile0) + mask_step_off;
           const bool mask_in = use_mi && tile_ok, mask_out = relu && mask_slot >= 0 && args.masks != nullptr && tile_ok;
           const uint32_t t_acc = tmem_base + slot * 256 + lane_addr + cb;
           float hacc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
@@ -597,11 +607,11 @@ __global__ void __launch_bounds__(k2Threads, 1)
             // accumulator columns and bias are in flight while the current chunk is converted.  (With run-time chunk
             // counts and flags the loop carried ~350 instructions of control flow per thread and step next to its ~300
             // of arithmetic, and the epilogue is instruction-issue bound.)
-            auto fast_path = [&](auto epi_tag) {
+            auto fast_path = [&](auto epi_tag, auto nch_tag) {
               constexpr int E = decltype(epi_tag)::value;
-              constexpr int NCH = kFastChunks;
-              constexpr bool kNeedB = E == DLN_EPI_RELU || E == DLN_EPI_BWD_MASK_SIGMA;
-              constexpr bool kMaskIn = E >= DLN_EPI_BWD_MASK, kMaskOut = E == DLN_EPI_RELU;
+              constexpr int NCH = decltype(nch_tag)::value;
+              constexpr bool kNeedB = E <= DLN_EPI_RELU_OUT || E == DLN_EPI_BWD_MASK_SIGMA;
+              constexpr bool kMaskIn = E >= DLN_EPI_BWD_MASK, kMaskOut = E <= DLN_EPI_RELU_OUT && E != DLN_EPI_LINEAR;
               uint32_t mi[NCH], mo[NCH];
 #pragma unroll
               for (int c = 0; c < NCH; ++c) mi[c] = 0, mo[c] = 0;
@@ -625,7 +635,7 @@ __global__ void __launch_bounds__(k2Threads, 1)
                 uint32_t(&nxt)[32] = (c & 1) ? va : vb;
                 if (c + 1 < NCH) tmem_ld32(t_acc + 32 * (c + 1), nxt);
                 const int c0 = cb + 32 * c;
-                epi2_chunk<E>(cur, bq, hw, 256, 0, dsig, mi[c], mo[c], hacc, pk, c0, semrow);
+                epi2_chunk<E>(cur, bq, hw, NCH * 32 * k2WG, 0, dsig, mi[c], mo[c], hacc, pk, c0, semrow);
                 if (c == 0 && et == 0) trace2(sm, args.trace, nev, slot * 8 + 6);
                 if (c + 1 < NCH && kNeedB) load_b(c + 1);
                 if (write_a) sts_packed32(row_addr_of(slot, c0), (c0 & 63) >> 3, pk);
@@ -646,9 +656,16 @@ __global__ void __launch_bounds__(k2Threads, 1)
                 for (int c = 0; c < NCH; ++c) mblock[mask_idx(cb + 32 * c)] = mo[c];
               }
             };
-            if (!kBwd) fast_path(std::integral_constant<int, DLN_EPI_RELU>{});
-            else if (epi == DLN_EPI_BWD_MASK) fast_path(std::integral_constant<int, DLN_EPI_BWD_MASK>{});
-            else fast_path(std::integral_constant<int, DLN_EPI_BWD_MASK_SIGMA>{});
+            using Wide = std::integral_constant<int, kFastChunks>;
+            using Half = std::integral_constant<int, kFastChunks / 2>;
+            if (!kBwd) {
+              if (epi == DLN_EPI_RELU) fast_path(std::integral_constant<int, DLN_EPI_RELU>{}, Wide{});
+              else if (epi == DLN_EPI_RELU_SIGMA) fast_path(std::integral_constant<int, DLN_EPI_RELU_SIGMA>{}, Wide{});
+              else fast_path(std::integral_constant<int, DLN_EPI_RELU_RGB>{}, Half{});
+            } else {
+              if (epi == DLN_EPI_BWD_MASK) fast_path(std::integral_constant<int, DLN_EPI_BWD_MASK>{}, Wide{});
+              else fast_path(std::integral_constant<int, DLN_EPI_BWD_MASK_SIGMA>{}, Wide{});
+            }
           } else {
             // ---------------------------------------------------------------- head steps (sigma / rgb / output_linear) and the
             // unfolded plan's linear / copy steps: one chunk at a time, every epilogue variant behind one call site
