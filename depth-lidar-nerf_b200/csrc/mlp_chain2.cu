@@ -30,11 +30,16 @@ using namespace dln;
 namespace {
 
 #ifndef DLN_CHAIN2_WG
-#define DLN_CHAIN2_WG 2
+#define DLN_CHAIN2_WG 4
 #endif
-constexpr int k2WG = DLN_CHAIN2_WG;    // epilogue warpgroups: 2 -> 11 warps, 168 registers per thread (4 -> 19 warps, 96 registers:
-                                       // the epilogue spilled and its 480 instructions per thread and step were the bound)
-constexpr int k2EpiWarp0 = 3;
+constexpr int k2WG = DLN_CHAIN2_WG;    // epilogue warpgroups.  4 (default): 20 warps launched with 96 registers, the service warpgroup then
+                                       // hands registers to the 16 epilogue warps (setmaxnreg 24 / 112); 2: 11 warps with 168 registers
+                                       // (measured: forward without stash 0.61 ms against 0.52 ms with four warpgroups)
+// With four epilogue warpgroups the 20 warps get 96 registers each at launch; the four service warps (one warpgroup)
+// then hand registers over with setmaxnreg (24 / 112: 128 x 24 + 512 x 112 = 60 416 of the 61 440 the CTA was launched with) -- issued INSIDE the role branches, so that the register budget
+// of each role's code is the one that dominates it (issued ahead of the branches ptxas holds all code to the minimum).
+constexpr bool k2Rebalance = k2WG == 4;
+constexpr int k2EpiWarp0 = k2WG == 4 ? 4 : 3;
 constexpr int kFastChunks = 256 / 32 / k2WG;     // 32-column chunks per thread in a 256-wide step
 constexpr int k2Threads = (k2EpiWarp0 + 4 * k2WG) * 32;
 constexpr int k2Stages = 4;
@@ -46,7 +51,8 @@ struct Chain2Small {
   uint64_t w_full[k2Stages];            // local: this CTA's half of the stage has landed (transaction bytes)
   uint64_t w_empty[k2Stages];           // local: the pair's MMAs have read the stage (multicast commit)
   uint64_t w_ready[k2Stages];           // leader's copy is the live one: both CTAs' helpers arrive (count 2)
-  uint64_t a_ready[2];                  // leader's copy: operands of the slot's next step written in BOTH CTAs (32 warps)
+  uint64_t a_ready[2][2];               // leader's copy: [slot][0: activation slabs 0, 1 | 1: slabs 2, 3 + aux] of the slot's next
+                                        // step written in BOTH CTAs (one arrival per epilogue warp of the pair)
   uint64_t acc_full[2];                 // local: the slot's accumulator is complete (multicast commit)
   uint64_t s_ready[2][2];               // local: [slot][0 activation slabs | 1 aux slab] staged for the stash lane (16 warps)
   uint64_t s_free[2][2];                // local: the stash copies have read them (1)
@@ -237,7 +243,7 @@ __global__ void __launch_bounds__(k2Threads, 1)
   if (threadIdx.x == 0) {
     for (int i = 0; i < k2Stages; ++i) mbar_init(&sm->w_full[i], 1), mbar_init(&sm->w_empty[i], 1), mbar_init(&sm->w_ready[i], 2);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&sm->a_ready[i], 8 * k2WG);
+      mbar_init(&sm->a_ready[i][0], 8 * k2WG), mbar_init(&sm->a_ready[i][1], 8 * k2WG);
       mbar_init(&sm->acc_full[i], 1);
       for (int k = 0; k < 2; ++k) mbar_init(&sm->s_ready[i][k], 4 * k2WG), mbar_init(&sm->s_free[i][k], 1);
     }
@@ -254,6 +260,28 @@ __global__ void __launch_bounds__(k2Threads, 1)
   tc_fence_after();
   const uint32_t tmem_base = sm->tmem_base;
 
+  // weight-arrival helper: local landing of a stage -> the leader's w_ready.  A lane of its own warp where there is one
+  // (it sits on the critical path of the first pass over a layer's weights: the ring holds exactly one layer, so a
+  // stage is refilled only ~2 k cycles before it is needed again).
+  auto helper_loop = [&]() {
+    uint32_t L = 0;
+    uint32_t remote[k2Stages];
+#pragma unroll
+    for (int i = 0; i < k2Stages; ++i) remote[i] = mapa_u32(smem_u32(&sm->w_ready[i]), 0);
+    for (long long r = 0; r < n_rounds; ++r)
+      for (int s = 0; s < n_steps; ++s) {
+        const int nk = prog.steps[s].nk;
+        const int n = nk <= k2Stages ? nk : 2 * nk;
+        for (int j = 0; j < n; ++j, ++L) {
+          const uint32_t stage = L % k2Stages, ph = (L / k2Stages) & 1;
+          mbar_wait2(&sm->w_full[stage], ph);
+          mbar_arrive_cluster(stage == 0 ? remote[0] : stage == 1 ? remote[1] : stage == 2 ? remote[2] : remote[3]);
+        }
+      }
+  };
+
+  if (warp < k2EpiWarp0) {
+  if (k2Rebalance) asm volatile("setmaxnreg.dec.sync.aligned.u32 24;" ::: "memory");
   if (warp == 0) {
     // ===================================================== weight producer: this CTA's half (n_out/2 rows) of every K slab.
     // Steps with <= k2Stages slabs keep their weights resident for both slots (loaded once per step); longer steps
@@ -275,24 +303,11 @@ __global__ void __launch_bounds__(k2Threads, 1)
                        &sm->w_full[stage]);
             }
         }
-    } else if (lane == 1) {
-      // weight-arrival helper (second lane of the producer warp): local landing -> the leader's w_ready.  Both loops
-      // are spin waits with ~2 k cycles of slack (the ring holds a whole layer), so sharing a warp costs nothing.
-      uint32_t L = 0;
-      uint32_t remote[k2Stages];
-#pragma unroll
-      for (int i = 0; i < k2Stages; ++i) remote[i] = mapa_u32(smem_u32(&sm->w_ready[i]), 0);
-      for (long long r = 0; r < n_rounds; ++r)
-        for (int s = 0; s < n_steps; ++s) {
-          const int nk = prog.steps[s].nk;
-          const int n = nk <= k2Stages ? nk : 2 * nk;
-          for (int j = 0; j < n; ++j, ++L) {
-            const uint32_t stage = L % k2Stages, ph = (L / k2Stages) & 1;
-            mbar_wait2(&sm->w_full[stage], ph);
-            mbar_arrive_cluster(stage == 0 ? remote[0] : stage == 1 ? remote[1] : stage == 2 ? remote[2] : remote[3]);
-          }
-        }
+    } else if (lane == 1 && k2EpiWarp0 == 3) {
+      helper_loop();       // no spare service warp in the 11-warp layout: second lane of the producer warp
     }
+  } else if (warp == 3 && k2EpiWarp0 == 4) {
+    if (lane == 0) helper_loop();
   } else if (warp == 1) {
     // ===================================================== MMA issuer (leader CTA): X(s), Y(s), X(s+1), ...
     if (rank == 0) {
@@ -307,8 +322,9 @@ __global__ void __launch_bounds__(k2Threads, 1)
           const uint32_t idesc = umma_idesc_bf16(256, st.n_out, 0, 0);
 #pragma unroll 1
           for (int slot = 0; slot < 2; ++slot) {
-            mbar_wait_cl(&sm->a_ready[slot], nev & 1);
-            tc_fence_after();
+            // operands arrive in two halves (activation slabs 0, 1 first): the MMAs on K slabs 0, 1 of the next step start
+            // while the epilogue still converts the columns of slabs 2, 3
+            bool seen_lo = false, seen_hi = false;
             const uint32_t d_tmem = tmem_base + slot * 256;
             const uint32_t Lb = (reuse || slot == 0) ? L : L + nk;
             const bool first_use = !(reuse && slot == 1), release = !reuse || slot == 1;
@@ -320,6 +336,15 @@ __global__ void __launch_bounds__(k2Threads, 1)
               }
               if (j == 0) trace2(sm, args.trace, nev, slot * 8 + 0);
               const int slab = st.kslab[j], kc = st.kcnt[j];
+              if (slab < 2 && !seen_lo) {
+                mbar_wait_cl(&sm->a_ready[slot][0], nev & 1);
+                tc_fence_after();
+                seen_lo = true;
+              } else if (slab >= 2 && !seen_hi) {
+                mbar_wait_cl(&sm->a_ready[slot][1], nev & 1);
+                tc_fence_after();
+                seen_hi = true;
+              }
               const uint64_t ad = desc_k | (uint64_t)((slab < 4 ? a_addr0 + (slot * 4 + slab) * kSlab : aux_addr0 + slot * kSlab) >> 4);
               const uint64_t bd = desc_k | (uint64_t)((ring_addr0 + stage * k2StageBytes) >> 4);
               if (elect_one()) {
@@ -333,6 +358,9 @@ __global__ void __launch_bounds__(k2Threads, 1)
             }
             if (elect_one()) umma2_commit_mc(&sm->acc_full[slot]);
             __syncwarp();
+            // both halves complete exactly once per (slot, step): observe the one this step did not read
+            if (!seen_lo) mbar_wait_cl(&sm->a_ready[slot][0], nev & 1);
+            if (!seen_hi) mbar_wait_cl(&sm->a_ready[slot][1], nev & 1);
             trace2(sm, args.trace, nev, slot * 8 + 1);
           }
           L += reuse ? nk : 2 * nk;
@@ -383,14 +411,17 @@ __global__ void __launch_bounds__(k2Threads, 1)
       }
       bulk_wait_all0();
     }
-  } else if (warp >= k2EpiWarp0) {
+  }
+  } else {
+    if (k2Rebalance) asm volatile("setmaxnreg.inc.sync.aligned.u32 112;" ::: "memory");
     // ===================================================== prologue + epilogue warps: k2WG warpgroups, warpgroup g owns
     // the columns [g n_out/k2WG, (g+1) n_out/k2WG) of both slots, thread = row
     const int et = threadIdx.x - k2EpiWarp0 * 32;
     const int g = et >> 7;                          // warpgroup
     const int r = ((warp & 3) << 5) | lane;         // tile row == TMEM lane
     const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
-    const uint32_t ready_remote0 = mapa_u32(smem_u32(&sm->a_ready[0]), 0), ready_remote1 = mapa_u32(smem_u32(&sm->a_ready[1]), 0);
+    const uint32_t ready_remote0 = mapa_u32(smem_u32(&sm->a_ready[0][0]), 0), ready_remote1 = mapa_u32(smem_u32(&sm->a_ready[1][0]), 0);
+    // (the second half's barrier of a slot follows the first: + 8 bytes)
     const uint32_t abuf_addr = smem_u32(abuf);
     const uint32_t row_sw = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((r & 7) << 4));
     uint32_t cntA0 = 0, cntA1 = 0, cntX0 = 0, cntX1 = 0;      // productions of A[slot] / AUX[slot] so far
@@ -411,16 +442,26 @@ __global__ void __launch_bounds__(k2Threads, 1)
         if (lane == 0) mbar_arrive(&sm->s_ready[slot][0]);
       }
     };
-    // end_A + arrive_ready with ONE proxy fence: the activation slabs are complete for the stash lane and for the MMAs
-    auto end_A_and_ready = [&](int slot) {
+    // end_A + hand-off with ONE proxy fence: the activation slabs are complete for the stash lane and for the MMAs
+    // (`lo_too`: the first half has not been handed over yet)
+    auto end_A_and_ready = [&](int slot, bool lo_too) {
       if (slot) ++cntA1; else ++cntA0;
       tc_fence_before();
       fence_async_smem();
       __syncwarp();
       if (lane == 0) {
         if (keep) mbar_arrive(&sm->s_ready[slot][0]);
-        mbar_arrive_cluster(slot ? ready_remote1 : ready_remote0);
+        const uint32_t a = slot ? ready_remote1 : ready_remote0;
+        if (lo_too) mbar_arrive_cluster(a);
+        mbar_arrive_cluster(a + 8);
       }
+    };
+    // first half (slabs 0, 1) of the slot's next operands is in place and ALL accumulator reads of this thread are done
+    auto arrive_lo = [&](int slot) {
+      tc_fence_before();
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(slot ? ready_remote1 : ready_remote0);
     };
     auto begin_X = [&](int slot) {
       const uint32_t c = slot ? cntX1 : cntX0;
@@ -439,7 +480,11 @@ __global__ void __launch_bounds__(k2Threads, 1)
       tc_fence_before();
       fence_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(slot ? ready_remote1 : ready_remote0);
+      if (lane == 0) {
+        const uint32_t a = slot ? ready_remote1 : ready_remote0;
+        mbar_arrive_cluster(a);
+        mbar_arrive_cluster(a + 8);
+      }
     };
     // word of the ReLU-mask block of (mask_slot, tile) that covers columns [col0, col0 + 32) of this thread's row
     auto mask_idx = [&](int col0) -> int { return (((col0 & 127) >> 5) * 128 + r) * 2 + (col0 >> 7); };
@@ -570,9 +615,10 @@ __global__ void __launch_bounds__(k2Threads, 1)
         const float* hw = args.fblob + st.head_off;
         const int nheads = (epi <= DLN_EPI_RELU_OUT) ? st.n_heads : 0;
         const bool relu = (epi == DLN_EPI_RELU || epi == DLN_EPI_RELU_SIGMA || epi == DLN_EPI_RELU_RGB || epi == DLN_EPI_RELU_OUT);
-        const int cpw = n_out / k2WG;                  // columns per warpgroup
-        const int cb = g * cpw;
-        const int nch = cpw >> 5;                      // 32-column chunks per thread: 1, 2 or 4
+        // Columns of a thread: chunk c = [32 k2WG c + 32 g, + 32) -- chunk c of ALL warpgroups together covers 32 k2WG
+        // consecutive columns, so the activation slabs fill up in order (slabs 0, 1 by the first half of the chunks)
+        const int nch = n_out / (32 * k2WG);           // 32-column chunks per thread: 1, 2 or 4
+        auto col_of = [&](int c) -> int { return c * 32 * k2WG + 32 * g; };
         const bool write_a = !last || (keep && st.stash_slot >= 0);
         // bias (forward) or alpha head row (dgrad sigma step): added per column, preloaded ahead of the accumulator
         const float* const brow = kBwd ? hw : args.fblob + st.bias_off;
@@ -592,13 +638,13 @@ __global__ void __launch_bounds__(k2Threads, 1)
           const float* semrow = kSem ? (slot ? sem1 : sem0) : nullptr;
           uint32_t* const mblock = (slot ? mtile1 : mtile0) + mask_step_off;
           const bool mask_in = use_mi && tile_ok, mask_out = relu && mask_slot >= 0 && args.masks != nullptr && tile_ok;
-          const uint32_t t_acc = tmem_base + slot * 256 + lane_addr + cb;
+          const uint32_t t_acc = tmem_base + slot * 256 + lane_addr;
           float hacc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
           bool simple = false;
           float4 bq[8];
           auto load_b = [&](int c) {
 #pragma unroll
-            for (int q = 0; q < 8; ++q) bq[q] = __ldg(reinterpret_cast<const float4*>(brow + cb + 32 * c + 4 * q));
+            for (int q = 0; q < 8; ++q) bq[q] = __ldg(reinterpret_cast<const float4*>(brow + col_of(c) + 4 * q));
           };
 
           if (fast) {
@@ -617,43 +663,49 @@ __global__ void __launch_bounds__(k2Threads, 1)
               for (int c = 0; c < NCH; ++c) mi[c] = 0, mo[c] = 0;
               if (kMaskIn && tile_ok) {
 #pragma unroll
-                for (int c = 0; c < NCH; ++c) mi[c] = mblock[mask_idx(cb + 32 * c)];
+                for (int c = 0; c < NCH; ++c) mi[c] = mblock[mask_idx(col_of(c))];
               }
               if (kNeedB) load_b(0);
               mbar_wait_cl(&sm->acc_full[slot], nev & 1);
               tc_fence_after();
               if (et == 0) trace2(sm, args.trace, nev, slot * 8 + 2);
+              // With two chunks per thread BOTH are loaded up front: once they have landed nothing of this thread reads the
+              // accumulator any more, and the first half of the operands can be handed over after chunk 0.
+              constexpr bool kEarly = NCH == 2;
               uint32_t va[32], vb[32], pk[16];
-              tmem_ld32(t_acc, va);
+              tmem_ld32(t_acc + col_of(0), va);
+              if (kEarly) tmem_ld32(t_acc + col_of(1), vb);
               if (write_a) begin_A(slot);
               tmem_ld_wait();
               tmem_ld_pin32(va);
+              if (kEarly) tmem_ld_pin32(vb);
+              simple = write_a && !last && s != reload_step;
               if (et == 0) trace2(sm, args.trace, nev, slot * 8 + 5);
 #pragma unroll
               for (int c = 0; c < NCH; ++c) {
                 uint32_t(&cur)[32] = (c & 1) ? vb : va;
                 uint32_t(&nxt)[32] = (c & 1) ? va : vb;
-                if (c + 1 < NCH) tmem_ld32(t_acc + 32 * (c + 1), nxt);
-                const int c0 = cb + 32 * c;
+                if (!kEarly && c + 1 < NCH) tmem_ld32(t_acc + col_of(c + 1), nxt);
+                const int c0 = col_of(c);
                 epi2_chunk<E>(cur, bq, hw, NCH * 32 * k2WG, 0, dsig, mi[c], mo[c], hacc, pk, c0, semrow);
                 if (c == 0 && et == 0) trace2(sm, args.trace, nev, slot * 8 + 6);
                 if (c + 1 < NCH && kNeedB) load_b(c + 1);
                 if (write_a) sts_packed32(row_addr_of(slot, c0), (c0 & 63) >> 3, pk);
-                if (c + 1 < NCH) {
+                if (!kEarly && c + 1 < NCH) {
                   tmem_ld_wait();
                   tmem_ld_pin32(nxt);
                 }
+                if (kEarly && c == 0 && simple) arrive_lo(slot);
                 if (c == 0 && et == 0) trace2(sm, args.trace, nev, slot * 8 + 7);
               }
-              // plain step: one fence + one arrival pair hands the slabs to the stash lane and the MMA warp at once
-              simple = write_a && !last && s != reload_step;
-              if (simple) end_A_and_ready(slot);
+              // plain step: one fence + one arrival hands the slabs to the stash lane and the (rest to the) MMA warp
+              if (simple) end_A_and_ready(slot, !kEarly);
               else if (write_a) end_A(slot);
               if (et == 0) trace2(sm, args.trace, nev, slot * 8 + 3);
               // the ReLU masks go out AFTER the hand-off: nothing in this kernel reads them
               if (kMaskOut && mask_out) {
 #pragma unroll
-                for (int c = 0; c < NCH; ++c) mblock[mask_idx(cb + 32 * c)] = mo[c];
+                for (int c = 0; c < NCH; ++c) mblock[mask_idx(col_of(c))] = mo[c];
               }
             };
             using Wide = std::integral_constant<int, kFastChunks>;
@@ -675,9 +727,9 @@ __global__ void __launch_bounds__(k2Threads, 1)
             if (write_a) begin_A(slot);
 #pragma unroll 1
             for (int c = 0; c < nch; ++c) {
-              const int c0 = cb + 32 * c;
+              const int c0 = col_of(c);
               uint32_t v[32], pk[16], mo = 0;
-              tmem_ld32(t_acc + 32 * c, v);
+              tmem_ld32(t_acc + c0, v);
               if (need_b) load_b(c);
               const uint32_t mi = mask_in ? mblock[mask_idx(c0)] : 0u;
               tmem_ld_wait();
