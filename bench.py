@@ -352,18 +352,23 @@ def run_ours(args):
         allreduce_grads()
         return loss
 
+    sched = {}                  # SM partition between the fine net's write-bound kernels and the coarse backward
+    if args.coarse_sms:
+        sched = dict(coarse_sms=args.coarse_sms, fine_sms=args.fine_sms or None)
+
     def fused_step(rays, t_rgb, t_dep, overlap=True):
         """Same step through dlnerf_b200.train_step: loss gradient fused into the compositing backward kernel."""
         out = dn.train_step(H, W, FOCAL, rays, t_rgb, t_dep, n_rgb, net_c, net_f, N_samples=N_SAMPLES,
                             N_importance=N_IMPORTANCE, perturb=1., raw_noise_std=1., depth_lambda=DEPTH_LAMBDA,
-                            depth_importance=1., world_size=world, overlap_coarse_backward=overlap, **sem_kw)
+                            depth_importance=1., world_size=world, overlap_coarse_backward=overlap,
+                            **(sched if overlap else {}), **sem_kw)
         return out["loss"]
 
     graphed = None
     if args.path == "graph":
         graphed = dn.GraphedTrainStep(H, W, FOCAL, args.n_rand, n_rgb, net_c, net_f, world_size=world,
                                       N_samples=N_SAMPLES, N_importance=N_IMPORTANCE, perturb=1., raw_noise_std=1.,
-                                      depth_lambda=DEPTH_LAMBDA, depth_importance=1.,
+                                      depth_lambda=DEPTH_LAMBDA, depth_importance=1., **sched,
                                       **({"semantic_lambda": SEMANTIC_LAMBDA} if semK else {}))
 
     def graph_step(rays, t_rgb, t_dep):
@@ -549,6 +554,9 @@ def main():
                     help="strong-scaling mode (config E, 16k-256k rays): rays per step of the WHOLE job, split evenly over "
                          "the GPUs; overrides --n-rand and reports \"scaling\": \"strong\"")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--coarse-sms", type=int, default=0, help="SMs of the coarse backward when it runs next to the fine "
+                    "forward / dgrad (0: train_step's default schedule)")
+    ap.add_argument("--fine-sms", type=int, default=0, help="SMs of the fine forward / dgrad in that schedule (0: all)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-variants", action="store_true", help="skip the semantic-head variant of the step")
     ap.add_argument("--semantic", type=int, default=0,

@@ -254,7 +254,7 @@ class NeRF(nn.Module):
         """Semantic logits appended to every output row (0: no head, or a head the reference never evaluates)."""
         return self._shape.sem_K
 
-    def _run_forward(self, mode, a, b, P, keep, force_pack=False, sem_group=0, sem_points=False):
+    def _run_forward(self, mode, a, b, P, keep, force_pack=False, sem_group=0, sem_points=False, sms=None):
         """One forward chain launch.  Returns (out, saved) -- and, when the semantic head is asked for through
         ``sem_group`` (points per summed group, run_nerf_helpers.py:589) / ``sem_points`` (per-point logits for
         ``raw``), (out, saved, sem [G,K] | None, point_logits [P,K] | None).  The head reads the kept activations,
@@ -285,7 +285,8 @@ class NeRF(nn.Module):
             masks = torch.empty(pl.mask_slots * n_tiles * 2 * 128 * 4, device=dev, dtype=torch.int32)
             args.masks = masks.data_ptr()
             saved = (stash, masks)
-        L.call("dln_mlp_chain", C.byref(pl.fwd), C.byref(args), st["sms"], ops._stream(), tag="mlp_fwd D=%d" % self.D)
+        L.call("dln_mlp_chain", C.byref(pl.fwd), C.byref(args), min(st["sms"], sms) if sms else st["sms"], ops._stream(),
+               tag="mlp_fwd D=%d" % self.D)
         if not want_sem:
             return out, saved
         K = pl.sem.K
@@ -305,7 +306,7 @@ class NeRF(nn.Module):
             saved = (stash, masks, hsum, int(sem_group))
         return out, saved, sem, pts
 
-    def _run_backward(self, d_out, saved, P, gflat=None, sms=None, d_sem=None):
+    def _run_backward(self, d_out, saved, P, gflat=None, sms=None, d_sem=None, wgrad_sms=None):
         """dgrad chain + wgrad.  ``gflat`` (flat fp32 [n_flat]) accumulates across calls when given (ray-chunked
         steps); otherwise a zeroed buffer is allocated.  ``d_sem`` [G, K]: gradient of the summed semantic logits
         (``sem`` of ``_run_forward``); its input gradient enters the dgrad chain as one fp32 row per group."""
@@ -344,7 +345,7 @@ class NeRF(nn.Module):
         # pace, so slabs two items share (dZ of the skip layer, the last hidden layer, dZ_views) are found in L2 by
         # the second reader and neighbouring slots of a tile are read together; two waves or per-item split counts
         # proportional to the bytes were both measured 10-50 % slower.
-        splits = int(max(1, min(n_tiles, st["sms"] // n_items)))
+        splits = int(max(1, min(n_tiles, (min(st["sms"], wgrad_sms) if wgrad_sms else st["sms"]) // n_items)))
         L.call("dln_mlp_wgrad", st["items"].data_ptr(), n_items, splits, stash_f.data_ptr(), pl.fwd_slots,
                                   stash_b.data_ptr(), pl.bwd_slots, n_tiles, gflat.data_ptr(), s, tag="mlp_wgrad D=%d" % self.D)
         if pl.fold:

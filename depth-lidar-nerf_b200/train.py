@@ -180,7 +180,7 @@ def train_step(H, W, focal, batch_rays: Tensor, target_s: Tensor, target_depth: 
                ndc: bool = True, near: float = 0., far: float = 1., depth_lambda: float = 0.,
                depth_importance: float = 1., ray_weights: Optional[Tensor] = None, depth_mode: str = "mse",
                coarse_loss: bool = True, world_size: int = 1, group=None, ray_chunk: Optional[int] = None,
-               overlap_coarse_backward: bool = True, coarse_sms: Optional[int] = None,
+               overlap_coarse_backward: bool = True, coarse_sms: Optional[int] = None, fine_sms: Optional[int] = None,
                target_semantic: Optional[Tensor] = None, semantic_lambda: float = 0.,
                rng_state: Optional["ops.RngState"] = None, global_counts=None,
                _rng: Optional[Dict[str, Tensor]] = None, _force_pack: bool = False,
@@ -282,36 +282,54 @@ def train_step(H, W, focal, batch_rays: Tensor, target_s: Tensor, target_depth: 
                                                       bool(white_bkgd), rng=g_n0)
         u, g_u = draw("u", 2) if perturb != 0. else (None, None)
         z_samples, z1 = ops.importance_resample(z0, w0, N_importance, u, rng=g_u)
+        side = None
+        grads_c = None
+
+        def coarse_backward():
+            # coarse pass: colour loss only (run_nerf.py:1759-1761); depth_map0 is unsupervised
+            d_raw0 = ops.composite_bwd_fused_loss(raw0, z0, rays_d, noise0, raw_noise_std, white_bkgd, tgt_c,
+                                                  None, None, nr_c, 0., 0., 0, 1., sums[2:4], rng=g_n0,
+                                                  coefs_dev=coefs[4:7])
+            # the coarse logits are supervised too (run_nerf.py:1545-1546), whatever no_coarse says
+            d_sem0 = ops.semantic_ce(sem0[0], tsem_c, nr_c, coef_sem, sums[5:6]) if use_sem else None
+            cap = coarse_sms if side is not main else None
+            g = network_fn._run_backward(d_raw0, saved0, Nc * N_samples, gflat=gacc[0], sms=cap, wgrad_sms=cap, d_sem=d_sem0)
+            if world_size > 1 and c == n_chunks - 1:
+                # the coarse network's gradients are complete: reduce them from the side stream, under the fine
+                # network's kernels still running on the main stream
+                _assign_grads(network_fn, g)
+                allreduce_gradients(list(network_fn.parameters()), world_size, group, average=False)
+            return g
+
+        early = bool(coarse_loss or use_sem) and overlap_coarse_backward and coarse_sms is not None
+        if early:
+            # SM-partitioned schedule: the coarse backward depends on the coarse forward alone, and the fine network's
+            # forward and dgrad kernels are bound by their stash WRITES (3.9 TB/s for a pure write stream), not by the
+            # SMs.  So they run on `fine_sms` SMs, and the coarse backward -- its wgrad a pure READ stream, which the
+            # memory system overlaps with writes almost for free -- runs next to them on the remaining `coarse_sms`.
+            side = _side_stream(dev)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                grads_c = coarse_backward()
         raw1, saved1, *sem1 = network_fine._run_forward("rays", rb_c, z1, Nc * S1, keep=True,
-                                                        force_pack=_force_pack and c == 0, **sem_kw(S1))
+                                                        force_pack=_force_pack and c == 0, sms=fine_sms if early else None,
+                                                        **sem_kw(S1))
         raw1 = raw1.view(Nc, S1, -1)
         noise1, g_n1 = draw("noise1", 3) if raw_noise_std > 0. else (None, None)
         # fine pass: colour loss on the RGB rays, depth loss on the depth rays (run_nerf.py:1461, :1500-1524)
         d_raw1 = ops.composite_bwd_fused_loss(raw1, z1, rays_d, noise1, raw_noise_std, white_bkgd, tgt_c, tdep_c,
                                               rw_c, nr_c, 0., 0., mode, 1., sums[0:2], rng=g_n1, coefs_dev=coefs[0:3])
         d_sem1 = ops.semantic_ce(sem1[0], tsem_c, nr_c, coef_sem, sums[4:5]) if use_sem else None
-        side = None
-        if coarse_loss or use_sem:
-            # coarse pass: colour loss only (run_nerf.py:1759-1761); depth_map0 is unsupervised.  It depends on the
-            # coarse forward alone, so it runs on a second stream next to the fine backward: its CTAs fill the SMs
-            # the persistent fine-net kernels leave idle at their tails and under the HBM-bound wgrad.
+        if (coarse_loss or use_sem) and not early:
+            # default schedule: the coarse backward on a second stream next to the fine backward -- its CTAs fill the
+            # SMs the persistent fine-net kernels leave idle at their tails and under the HBM-bound wgrad
             side = _side_stream(dev) if overlap_coarse_backward else main
             if side is not main:
                 side.wait_stream(main)
             with torch.cuda.stream(side):
-                d_raw0 = ops.composite_bwd_fused_loss(raw0, z0, rays_d, noise0, raw_noise_std, white_bkgd, tgt_c,
-                                                      None, None, nr_c, 0., 0., 0, 1., sums[2:4], rng=g_n0,
-                                                      coefs_dev=coefs[4:7])
-                # the coarse logits are supervised too (run_nerf.py:1545-1546), whatever no_coarse says
-                d_sem0 = ops.semantic_ce(sem0[0], tsem_c, nr_c, coef_sem, sums[5:6]) if use_sem else None
-                grads_c = network_fn._run_backward(d_raw0, saved0, Nc * N_samples, gflat=gacc[0],
-                                                   sms=coarse_sms if side is not main else None, d_sem=d_sem0)
-                if world_size > 1 and c == n_chunks - 1:
-                    # the coarse network's gradients are complete: reduce them from the side stream, under the
-                    # fine backward still running on the main stream
-                    _assign_grads(network_fn, grads_c)
-                    allreduce_gradients(list(network_fn.parameters()), world_size, group, average=False)
-        grads_f = network_fine._run_backward(d_raw1, saved1, Nc * S1, gflat=gacc[1], d_sem=d_sem1)
+                grads_c = coarse_backward()
+        grads_f = network_fine._run_backward(d_raw1, saved1, Nc * S1, gflat=gacc[1], d_sem=d_sem1,
+                                             sms=fine_sms if early else None)
         if world_size > 1 and c == n_chunks - 1:
             _assign_grads(network_fine, grads_f)
             allreduce_gradients(list(network_fine.parameters()), world_size, group, average=False)
