@@ -541,6 +541,8 @@ def run_ours(args):
             "roofline": roofline, "cpu_baseline": cb, "variants": variants, "kernels": kern,
             "kernel_times_from": kernel_times_from}))
     if world > 1:
+        if graphed is not None:
+            graphed.close()          # the graph holds NCCL kernels: release it before the process group
         dist.destroy_process_group()
 
 

@@ -443,6 +443,15 @@ class GraphedTrainStep:
             self.out = train_step(*args, **kw)
         self._grads = [(p, p.grad) for net in self.nets for p in net.parameters()]
 
+    def close(self) -> None:
+        """Drop the captured graph.  With ``world_size`` > 1 the graph holds NCCL kernels: destroy it BEFORE
+        ``dist.destroy_process_group()`` (a process group torn down under a live graph that references its communicator
+        hung at exit on the 2-GPU box)."""
+        if getattr(self, "graph", None) is not None:
+            torch.cuda.synchronize()
+            self.graph.reset()
+            self.graph = None
+
     def set_depth_importance(self, depth_importance: float) -> None:
         """run_nerf.py:1527-1532: the decayed weight of the depth term, for the following replays (two scalar
         fills on the stream, no host sync)."""

@@ -59,6 +59,7 @@ def _worker(rank, world, port, out):
     step(r.to(dev), t.to(dev), dp.to(dev))
     step(r.to(dev), t.to(dev), dp.to(dev))
     res["graph"] = [p.grad.detach().cpu().clone() for p in list(net_c.parameters()) + list(net_f.parameters())]
+    step.close()                  # the graph holds NCCL kernels: release it before the process group goes away
     # the no-grad part of a patch render, split over the ranks and all-gathered
     q = d.FusedQuery(d.get_embedder(10, 0)[0], d.get_embedder(4, 0)[0], 1 << 16, 10, 4, 0)
     rk = dict(network_query_fn=q, perturb=0., N_importance=64, network_fine=net_f, N_samples=64, network_fn=net_c,
