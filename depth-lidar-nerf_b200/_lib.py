@@ -30,14 +30,15 @@ class ChainStep(C.Structure):
                 ("head_bias_off", C.c_uint32), ("n_out", C.c_uint16), ("nk", C.c_uint8), ("epi", C.c_uint8),
                 ("kslab", C.c_uint8 * MAX_KSLABS), ("kcnt", C.c_uint8 * MAX_KSLABS),
                 ("stash_slot", C.c_int16), ("mask_slot", C.c_int16), ("n_heads", C.c_uint8),
-                ("pad_", C.c_uint8 * 3)]
+                ("n_valid32", C.c_uint8), ("pad_", C.c_uint8 * 2)]
 
 
 class ChainProgram(C.Structure):
     _fields_ = [("n_steps", C.c_int32), ("backward", C.c_int32), ("use_viewdirs", C.c_int32),
                 ("out_ch", C.c_int32), ("L_pts", C.c_int32), ("L_dir", C.c_int32), ("stash_slots", C.c_int32),
                 ("mask_slots", C.c_int32), ("pro_head_off", C.c_int32), ("pro_mask_slot", C.c_int32),
-                ("pro_slot", C.c_int32), ("reload_step", C.c_int32), ("steps", ChainStep * MAX_STEPS)]
+                ("pro_slot", C.c_int32), ("reload_step", C.c_int32), ("pro_valid", C.c_int32),
+                ("steps", ChainStep * MAX_STEPS)]
 
 
 class ChainArgs(C.Structure):

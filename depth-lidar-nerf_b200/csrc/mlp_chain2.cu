@@ -218,7 +218,9 @@ __device__ __forceinline__ void sts_packed32(uint32_t row_addr, int ch0, const u
 }
 
 // ---------------------------------------------------------------------------------------------
-template <bool kBwd, bool kSem>
+// kNarrow: the plan has zero-padded layers (netwidth < 256).  A separate instantiation, so that the register allocation
+// of the full-width kernels is exactly what it was without that code (at 112 registers the epilogue is on the edge).
+template <bool kBwd, bool kSem, bool kNarrow = false>
 __global__ void __launch_bounds__(k2Threads, 1)
     chain2_kernel(const __grid_constant__ DlnChainProgram prog, const __grid_constant__ DlnChainArgs args,
                   const long long n_tiles) {
@@ -547,6 +549,7 @@ __global__ void __launch_bounds__(k2Threads, 1)
         if (slot) dsig1 = dr[3]; else dsig0 = dr[3];
         const int nh = prog.use_viewdirs ? 3 : prog.out_ch;
         const int width = prog.use_viewdirs ? 128 : 256;
+        const int pvalid = (kNarrow && prog.pro_valid > 0) ? prog.pro_valid : width;     // head rows are pvalid wide; the rest is padding
         const int cpw = width / k2WG;
         if (kSem) {
           const float* sp = valid ? args.sem_g + (size_t)((unsigned)p / (unsigned)args.sem_g_div) * 256 : nullptr;
@@ -561,16 +564,16 @@ __global__ void __launch_bounds__(k2Threads, 1)
 #pragma unroll 1
         for (int c = 0; c < (cpw >> 5); ++c) {
           const int col0 = g * cpw + 32 * c;
-          const uint32_t mk = tile < n_tiles ? mp[mask_idx(col0)] : 0u;
+          const uint32_t mk = (tile < n_tiles && col0 < pvalid) ? mp[mask_idx(col0)] : 0u;
           float f[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) f[i] = 0.f;
 #pragma unroll
           for (int j = 0; j < 5; ++j)
-            if (j < nh) {
+            if (j < nh && col0 < pvalid) {
 #pragma unroll
               for (int q = 0; q < 8; ++q) {
-                const float4 w4 = __ldg(reinterpret_cast<const float4*>(ph + j * width + col0 + 4 * q));
+                const float4 w4 = __ldg(reinterpret_cast<const float4*>(ph + j * pvalid + col0 + 4 * q));
                 f[4 * q] += dr[j] * w4.x, f[4 * q + 1] += dr[j] * w4.y, f[4 * q + 2] += dr[j] * w4.z, f[4 * q + 3] += dr[j] * w4.w;
               }
             }
@@ -611,6 +614,7 @@ __global__ void __launch_bounds__(k2Threads, 1)
       for (int s = 0; s < n_steps; ++s, ++nev) {
         const DlnChainStep& st = prog.steps[s];
         const int epi = st.epi, n_out = st.n_out, mask_slot = st.mask_slot;
+        const int n_valid = (kNarrow && st.n_valid32) ? 32 * st.n_valid32 : n_out;     // netwidth < 256: the columns beyond are padding
         const bool last = s == n_steps - 1;
         const float* hw = args.fblob + st.head_off;
         const int nheads = (epi <= DLN_EPI_RELU_OUT) ? st.n_heads : 0;
@@ -626,7 +630,7 @@ __global__ void __launch_bounds__(k2Threads, 1)
         const bool use_mi = kBwd && epi >= DLN_EPI_BWD_MASK && mask_slot >= 0;
         const size_t mask_step_off = (size_t)(mask_slot < 0 ? 0 : mask_slot) * (size_t)n_tiles * 1024;
         // steps with a compile-time specialised epilogue: the plans of every shipped configuration consist of these
-        const bool fast = kBwd ? n_out == 256 && (epi == DLN_EPI_BWD_MASK || epi == DLN_EPI_BWD_MASK_SIGMA) && mask_slot >= 0
+        const bool fast = (kNarrow && n_valid != n_out) ? false : kBwd ? n_out == 256 && (epi == DLN_EPI_BWD_MASK || epi == DLN_EPI_BWD_MASK_SIGMA) && mask_slot >= 0
                                : (n_out == 256 && ((epi == DLN_EPI_RELU && nheads == 0) || (epi == DLN_EPI_RELU_SIGMA && nheads == 1))) ||
                                      (n_out == 128 && epi == DLN_EPI_RELU_RGB && nheads == 3 && kFastChunks >= 2);
 #pragma unroll 1
@@ -729,18 +733,25 @@ __global__ void __launch_bounds__(k2Threads, 1)
             for (int c = 0; c < nch; ++c) {
               const int c0 = col_of(c);
               uint32_t v[32], pk[16], mo = 0;
+              if (kNarrow && c0 >= n_valid) {      // padding columns of a narrow layer: zeros, no bias, no head, mask 0
+#pragma unroll
+                for (int i = 0; i < 16; ++i) pk[i] = 0u;
+                if (write_a) sts_packed32(row_addr_of(slot, c0), (c0 & 63) >> 3, pk);
+                if (mask_out) mblock[mask_idx(c0)] = 0u;
+                continue;
+              }
               tmem_ld32(t_acc + c0, v);
               if (need_b) load_b(c);
               const uint32_t mi = mask_in ? mblock[mask_idx(c0)] : 0u;
               tmem_ld_wait();
               tmem_ld_pin32(v);
               if (!kBwd) {
-                if (epi == DLN_EPI_LINEAR) epi2_chunk<DLN_EPI_LINEAR>(v, bq, hw, n_out, nheads, dsig, mi, mo, hacc, pk, c0, semrow);
-                else epi2_chunk<DLN_EPI_RELU_OUT>(v, bq, hw, n_out, nheads, dsig, mi, mo, hacc, pk, c0, semrow);
+                if (epi == DLN_EPI_LINEAR) epi2_chunk<DLN_EPI_LINEAR>(v, bq, hw, n_valid, nheads, dsig, mi, mo, hacc, pk, c0, semrow);
+                else epi2_chunk<DLN_EPI_RELU_OUT>(v, bq, hw, n_valid, nheads, dsig, mi, mo, hacc, pk, c0, semrow);
               } else {
-                if (epi == DLN_EPI_BWD_COPY) epi2_chunk<DLN_EPI_BWD_COPY>(v, bq, hw, n_out, nheads, dsig, mi, mo, hacc, pk, c0, semrow);
-                else if (epi == DLN_EPI_BWD_MASK) epi2_chunk<DLN_EPI_BWD_MASK>(v, bq, hw, n_out, nheads, dsig, mi, mo, hacc, pk, c0, semrow);
-                else epi2_chunk<DLN_EPI_BWD_MASK_SIGMA>(v, bq, hw, n_out, nheads, dsig, mi, mo, hacc, pk, c0, semrow);
+                if (epi == DLN_EPI_BWD_COPY) epi2_chunk<DLN_EPI_BWD_COPY>(v, bq, hw, n_valid, nheads, dsig, mi, mo, hacc, pk, c0, semrow);
+                else if (epi == DLN_EPI_BWD_MASK) epi2_chunk<DLN_EPI_BWD_MASK>(v, bq, hw, n_valid, nheads, dsig, mi, mo, hacc, pk, c0, semrow);
+                else epi2_chunk<DLN_EPI_BWD_MASK_SIGMA>(v, bq, hw, n_valid, nheads, dsig, mi, mo, hacc, pk, c0, semrow);
               }
               if (write_a) sts_packed32(row_addr_of(slot, c0), (c0 & 63) >> 3, pk);
               if (mask_out) mblock[mask_idx(c0)] = mo;
@@ -825,14 +836,19 @@ __global__ void __launch_bounds__(k2Threads, 1)
 int dln_chain2_launch(const DlnChainProgram* prog, const DlnChainArgs* args, int num_sms, long long n_tiles, cudaStream_t stream) {
   bool& attr_set = dln_device_flag(3);
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(chain2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChain2SmemBytes);
-    if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(chain2_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChain2SmemBytes);
-    if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(chain2_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChain2SmemBytes);
-    if (e != cudaSuccess) return (int)e;
+    const void* fns[5] = {(const void*)chain2_kernel<false, false>, (const void*)chain2_kernel<true, false>,
+                          (const void*)chain2_kernel<true, true>, (const void*)chain2_kernel<false, false, true>,
+                          (const void*)chain2_kernel<true, false, true>};
+    for (const void* f : fns) {
+      cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChain2SmemBytes);
+      if (e != cudaSuccess) return (int)e;
+    }
     attr_set = true;
   }
+  bool narrow = prog->pro_valid != 0;
+  for (int s = 0; s < prog->n_steps; ++s)
+    narrow = narrow || (prog->steps[s].n_valid32 != 0 && prog->steps[s].n_valid32 * 32 != prog->steps[s].n_out);
+  if (narrow && prog->backward && args->sem_g) return DLN_EINVAL;      // the semantic head is built for netwidth 256
   const long long want_pairs = (n_tiles + 3) / 4;
   long long pairs = num_sms / 2;
   if (pairs < 1) pairs = 1;
@@ -845,7 +861,9 @@ int dln_chain2_launch(const DlnChainProgram* prog, const DlnChainArgs* args, int
   at[0].val.clusterDim.x = 2, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
   cfg.attrs = at, cfg.numAttrs = 1;
   cudaError_t e;
-  if (prog->backward && args->sem_g) e = cudaLaunchKernelEx(&cfg, chain2_kernel<true, true>, *prog, *args, n_tiles);
+  if (narrow && prog->backward) e = cudaLaunchKernelEx(&cfg, chain2_kernel<true, false, true>, *prog, *args, n_tiles);
+  else if (narrow) e = cudaLaunchKernelEx(&cfg, chain2_kernel<false, false, true>, *prog, *args, n_tiles);
+  else if (prog->backward && args->sem_g) e = cudaLaunchKernelEx(&cfg, chain2_kernel<true, true>, *prog, *args, n_tiles);
   else if (prog->backward) e = cudaLaunchKernelEx(&cfg, chain2_kernel<true, false>, *prog, *args, n_tiles);
   else e = cudaLaunchKernelEx(&cfg, chain2_kernel<false, false>, *prog, *args, n_tiles);
   if (e != cudaSuccess) return (int)e;

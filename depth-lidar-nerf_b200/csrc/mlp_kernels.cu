@@ -846,7 +846,13 @@ int dln_mlp_chain(const DlnChainProgram* prog, const DlnChainArgs* args, int num
   if (args->stash && prog->stash_slots > 0) DLN_CHECK_ARG((reinterpret_cast<uintptr_t>(args->stash) & 15) == 0);
   if (args->P == 0) return DLN_OK;
   const long long n_tiles = (args->P + DLN_TILE_ROWS - 1) / DLN_TILE_ROWS;
-  if (chain_variant() == 2) return dln_chain2_launch(prog, args, num_sms, n_tiles, (cudaStream_t)stream);
+  bool narrow = prog->pro_valid != 0;
+  for (int s = 0; s < prog->n_steps; ++s) {
+    const int nv = prog->steps[s].n_valid32;
+    DLN_CHECK_ARG(nv * 32 <= prog->steps[s].n_out);
+    narrow = narrow || (nv != 0 && nv * 32 != prog->steps[s].n_out);
+  }
+  if (chain_variant() == 2 || narrow) return dln_chain2_launch(prog, args, num_sms, n_tiles, (cudaStream_t)stream);
   bool& attr_set = dln_device_flag(0);     // the attribute is per device (context), not per process
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmemBytes);

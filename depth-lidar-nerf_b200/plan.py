@@ -32,8 +32,11 @@ class NetShape:
     semantic_num_classes: int = 0      # K > 0: semantic_linear = Linear(W, W/2) -> Linear(W/2, K) (helpers:107-111)
 
     def validate(self) -> None:
-        if self.W != 256:
-            raise NotImplementedError("the sm_100a MLP kernels are built for netwidth W=256 (got %d)" % self.W)
+        if self.W % 64 or not 64 <= self.W <= 256:
+            raise NotImplementedError("netwidth must be 64, 128, 192 or 256 (got %d): the sm_100a MLP kernels compute 256 "
+                                      "output columns per layer, narrower layers are zero-padded up to that" % self.W)
+        if self.W != 256 and self.semantic_num_classes:
+            raise NotImplementedError("the semantic-head kernels are built for netwidth 256")
         if self.D < 1 or self.D > (8 if self.use_viewdirs else 9):
             raise NotImplementedError("netdepth must be in [1, %d] (bias staging in shared memory)"
                                       % (8 if self.use_viewdirs else 9))
@@ -141,6 +144,17 @@ def build_plan(shape: NetShape, fold_feature: bool = True) -> Plan:
     by ``dln_mlp_unfold_grads`` -- identical in exact arithmetic, one bf16 rounding fewer in practice."""
     shape.validate()
     D, W = shape.D, shape.W
+    # netwidth < 256: every layer still runs as a 256- (views: 128-) column step of the kernels with the missing weight
+    # rows / K columns packed as zeros; `n_valid32` tells the epilogues which columns are real.  The folded feature
+    # layer's kernels are 256-wide, so narrow nets run the unfolded plan.
+    fold_feature = fold_feature and W == 256
+    NV, NVH = W // 32, W // 64            # valid output columns / 32 of a hidden (W) and of the views (W/2) layer
+
+    def k_slabs(width, first=0):
+        """(slab list, K=16-step counts) covering `width` input features held in slabs first, first+1, ..."""
+        n = _ceil_div(width, 64)
+        return [first + j for j in range(n)], [min(4, _ceil_div(width - 64 * j, 16)) for j in range(n)]
+
     pl = Plan(shape=shape)
     off = 0
     for name, shp in shape.param_shapes():
@@ -188,18 +202,20 @@ def build_plan(shape: NetShape, fold_feature: bool = True) -> Plan:
         st = fwd.steps[steps]
         wname = "pts_linears.%d.weight" % i
         ld = shape.fan_in(i)
-        st.w_off, st.bias_off, st.n_out = blob, O["pts_linears.%d.bias" % i], 256
+        st.w_off, st.bias_off, st.n_out, st.n_valid32 = blob, O["pts_linears.%d.bias" % i], 256, NV
+        hs, hc = k_slabs(W)
+        hcols = [(64 * j, min(64, W - 64 * j)) for j in range(len(hs))]
         if i == 0:
             slabs, cnts, cols = [4], [kc_pts], [(0, shape.input_ch)]
         elif (i - 1) in shape.skips:
-            slabs = [4, 0, 1, 2, 3]
-            cnts = [kc_pts, 4, 4, 4, 4]
-            cols = [(0, shape.input_ch)] + [(shape.input_ch + 64 * j, 64) for j in range(4)]
+            slabs = [4] + hs
+            cnts = [kc_pts] + hc
+            cols = [(0, shape.input_ch)] + [(shape.input_ch + c, kv) for c, kv in hcols]
         else:
-            slabs, cnts, cols = [0, 1, 2, 3], [4, 4, 4, 4], [(64 * j, 64) for j in range(4)]
+            slabs, cnts, cols = hs, hc, hcols
         _set_k(st, slabs, cnts)
         for (c0, kv) in cols:
-            add_job(pl.fwd_jobs, wname, ld, 0, c0, 256, kv, 0, 256, blob)
+            add_job(pl.fwd_jobs, wname, ld, 0, c0, W, kv, 0, 256, blob)
             blob += 256 * 128
         st.stash_slot, st.mask_slot = H_slot(i), i
         st.epi = L.EPI_RELU
@@ -217,25 +233,27 @@ def build_plan(shape: NetShape, fold_feature: bool = True) -> Plan:
     if shape.use_viewdirs:
         if not pl.fold:
             st = fwd.steps[steps]
-            st.w_off, st.bias_off, st.n_out, st.epi = blob, O["feature_linear.bias"], 256, L.EPI_LINEAR
-            _set_k(st, [0, 1, 2, 3], [4, 4, 4, 4])
-            for j in range(4):
-                add_job(pl.fwd_jobs, "feature_linear.weight", W, 0, 64 * j, 256, 64, 0, 256, blob)
+            st.w_off, st.bias_off, st.n_out, st.epi, st.n_valid32 = blob, O["feature_linear.bias"], 256, L.EPI_LINEAR, NV
+            hs, hc = k_slabs(W)
+            _set_k(st, hs, hc)
+            for j in hs:
+                add_job(pl.fwd_jobs, "feature_linear.weight", W, 0, 64 * j, W, min(64, W - 64 * j), 0, 256, blob)
                 blob += 256 * 128
             st.stash_slot, st.mask_slot = feat_slot, -1
             steps += 1
         st = fwd.steps[steps]
-        st.w_off, st.n_out, st.epi = blob, 128, L.EPI_RELU_RGB
+        st.w_off, st.n_out, st.epi, st.n_valid32 = blob, 128, L.EPI_RELU_RGB, NVH
         st.bias_off = pl.off_bM if pl.fold else O["views_linears.0.bias"]
-        _set_k(st, [0, 1, 2, 3, 4], [4, 4, 4, 4, kc_dir])     # slab 4 holds the encoded direction by now
+        hs, hc = k_slabs(W)
+        _set_k(st, hs + [4], hc + [kc_dir])     # slab 4 holds the encoded direction by now
         ldv = W + shape.input_ch_views
-        for j in range(4):
+        for j in hs:
             if pl.fold:      # K slabs of M = W_v1 W_f act directly on the last hidden layer
                 add_job(pl.fwd_jobs, pl.off_M, W, 0, 64 * j, 128, 64, 0, 128, blob)
             else:
-                add_job(pl.fwd_jobs, "views_linears.0.weight", ldv, 0, 64 * j, 128, 64, 0, 128, blob)
+                add_job(pl.fwd_jobs, "views_linears.0.weight", ldv, 0, 64 * j, W // 2, min(64, W - 64 * j), 0, 128, blob)
             blob += 128 * 128
-        add_job(pl.fwd_jobs, "views_linears.0.weight", ldv, 0, W, 128, shape.input_ch_views, 0, 128, blob)
+        add_job(pl.fwd_jobs, "views_linears.0.weight", ldv, 0, W, W // 2, shape.input_ch_views, 0, 128, blob)
         blob += 128 * 128
         st.n_heads, st.head_off, st.head_bias_off = 3, O["rgb_linear.weight"], O["rgb_linear.bias"]
         st.stash_slot, st.mask_slot = hv_slot, D
@@ -258,6 +276,7 @@ def build_plan(shape: NetShape, fold_feature: bool = True) -> Plan:
     steps = 0
     bwd.pro_slot = 1
     bwd.reload_step = -1
+    bwd.pro_valid = (W // 2 if shape.use_viewdirs else W) if W != 256 else 0
     if shape.use_viewdirs:
         bwd.pro_head_off, bwd.pro_mask_slot = O["rgb_linear.weight"], D
         dzv_slot, dzf_slot = 1, 3
@@ -276,18 +295,20 @@ def build_plan(shape: NetShape, fold_feature: bool = True) -> Plan:
             steps += 1
         else:
             st = bwd.steps[steps]            # d feature = dZ_v * W_views[:, :W]
-            st.w_off, st.n_out, st.epi = blob, 256, L.EPI_BWD_COPY
-            _set_k(st, [0, 1], [4, 4])
-            for j in range(2):
-                add_job(pl.bwd_jobs, "views_linears.0.weight", ldv, 64 * j, 0, 256, 64, 1, 256, blob)
+            st.w_off, st.n_out, st.epi, st.n_valid32 = blob, 256, L.EPI_BWD_COPY, NV
+            vs, vc = k_slabs(W // 2)
+            _set_k(st, vs, vc)
+            for j in vs:
+                add_job(pl.bwd_jobs, "views_linears.0.weight", ldv, 64 * j, 0, W, min(64, W // 2 - 64 * j), 1, 256, blob)
                 blob += 256 * 128
             st.stash_slot, st.mask_slot = dzf_slot, -1
             steps += 1
             st = bwd.steps[steps]            # dH_{D-1} = d feature * W_feature + d sigma * w_alpha ; mask
-            st.w_off, st.n_out, st.epi = blob, 256, L.EPI_BWD_MASK_SIGMA
-            _set_k(st, [0, 1, 2, 3], [4, 4, 4, 4])
-            for j in range(4):
-                add_job(pl.bwd_jobs, "feature_linear.weight", W, 64 * j, 0, 256, 64, 1, 256, blob)
+            st.w_off, st.n_out, st.epi, st.n_valid32 = blob, 256, L.EPI_BWD_MASK_SIGMA, NV
+            hs, hc = k_slabs(W)
+            _set_k(st, hs, hc)
+            for j in hs:
+                add_job(pl.bwd_jobs, "feature_linear.weight", W, 64 * j, 0, W, min(64, W - 64 * j), 1, 256, blob)
                 blob += 256 * 128
             st.n_heads, st.head_off = 1, O["alpha_linear.weight"]
             st.stash_slot, st.mask_slot = dz_slot(D - 1), D - 1
@@ -297,11 +318,12 @@ def build_plan(shape: NetShape, fold_feature: bool = True) -> Plan:
         dz_slot = lambda l: 1 + 4 * (D - 1 - l)
     for l in range(D - 1, 0, -1):        # dH_{l-1} = dZ_l * W_l[:, h-part] ; mask_{l-1}
         st = bwd.steps[steps]
-        st.w_off, st.n_out, st.epi = blob, 256, L.EPI_BWD_MASK
-        _set_k(st, [0, 1, 2, 3], [4, 4, 4, 4])
+        st.w_off, st.n_out, st.epi, st.n_valid32 = blob, 256, L.EPI_BWD_MASK, NV
+        hs, hc = k_slabs(W)
+        _set_k(st, hs, hc)
         c0 = shape.input_ch if (l - 1) in shape.skips else 0
-        for j in range(4):
-            add_job(pl.bwd_jobs, "pts_linears.%d.weight" % l, shape.fan_in(l), 64 * j, c0, 256, 64, 1, 256, blob)
+        for j in hs:
+            add_job(pl.bwd_jobs, "pts_linears.%d.weight" % l, shape.fan_in(l), 64 * j, c0, W, min(64, W - 64 * j), 1, 256, blob)
             blob += 256 * 128
         st.stash_slot, st.mask_slot = dz_slot(l - 1), l - 1
         steps += 1
@@ -322,27 +344,28 @@ def build_plan(shape: NetShape, fold_feature: bool = True) -> Plan:
         it.db_col_off, it.db_n = db_col, db_n
         pl.wgrad.append(it)
 
+    # (the slab counts stay 4 / 2: the padded slabs of a narrow net hold zeros; rows / columns are limited to W)
     for l in range(D):
         wn, bn, ld = "pts_linears.%d.weight" % l, "pts_linears.%d.bias" % l, shape.fan_in(l)
         if l == 0:
-            item(dz_slot(0), 4, 0, 1, wn, ld, 0, shape.input_ch, 0, 256, bn, 0, 256)
+            item(dz_slot(0), 4, 0, 1, wn, ld, 0, shape.input_ch, 0, W, bn, 0, W)
         elif (l - 1) in shape.skips:
-            item(dz_slot(l), 4, 0, 1, wn, ld, 0, shape.input_ch, 0, 256, bn, 0, 256)
-            item(dz_slot(l), 4, H_slot(l - 1), 4, wn, ld, shape.input_ch, 256, 0, 256)
+            item(dz_slot(l), 4, 0, 1, wn, ld, 0, shape.input_ch, 0, W, bn, 0, W)
+            item(dz_slot(l), 4, H_slot(l - 1), 4, wn, ld, shape.input_ch, W, 0, W)
         else:
-            item(dz_slot(l), 4, H_slot(l - 1), 4, wn, ld, 0, 256, 0, 256, bn, 0, 256)
+            item(dz_slot(l), 4, H_slot(l - 1), 4, wn, ld, 0, W, 0, W, bn, 0, W)
     if shape.use_viewdirs:
         if not pl.fold:
-            item(dzf_slot, 4, H_slot(D - 1), 4, "feature_linear.weight", W, 0, 256, 0, 256, "feature_linear.bias", 0, 256)
-        item(0, 1, H_slot(D - 1), 4, "alpha_linear.weight", W, 0, 256, 3, 1, "alpha_linear.bias", 3, 1)
+            item(dzf_slot, 4, H_slot(D - 1), 4, "feature_linear.weight", W, 0, W, 0, W, "feature_linear.bias", 0, W)
+        item(0, 1, H_slot(D - 1), 4, "alpha_linear.weight", W, 0, W, 3, 1, "alpha_linear.bias", 3, 1)
         ldv = W + shape.input_ch_views
         if pl.fold:      # dM = dZ_v^T H_{D-1} and db' = colsum(dZ_v) into the scratch tail of the gradient buffer
             item(dzv_slot, 2, H_slot(D - 1), 4, pl.off_M, W, 0, 256, 0, 128, pl.off_bM, 0, 128)
         else:
-            item(dzv_slot, 2, feat_slot, 4, "views_linears.0.weight", ldv, 0, 256, 0, 128, "views_linears.0.bias", 0, 128)
-        item(dzv_slot, 2, 1, 1, "views_linears.0.weight", ldv, W, shape.input_ch_views, 0, 128)
-        item(0, 1, hv_slot, 2, "rgb_linear.weight", W // 2, 0, 128, 0, 3, "rgb_linear.bias", 0, 3)
+            item(dzv_slot, 2, feat_slot, 4, "views_linears.0.weight", ldv, 0, W, 0, W // 2, "views_linears.0.bias", 0, W // 2)
+        item(dzv_slot, 2, 1, 1, "views_linears.0.weight", ldv, W, shape.input_ch_views, 0, W // 2)
+        item(0, 1, hv_slot, 2, "rgb_linear.weight", W // 2, 0, W // 2, 0, 3, "rgb_linear.bias", 0, 3)
     else:
-        item(0, 1, H_slot(D - 1), 4, "output_linear.weight", W, 0, 256, 0, shape.output_ch,
+        item(0, 1, H_slot(D - 1), 4, "output_linear.weight", W, 0, W, 0, shape.output_ch,
              "output_linear.bias", 0, shape.output_ch)
     return pl

@@ -159,7 +159,7 @@ typedef struct {
   uint32_t bias_off;  /* float offset of the bias vector in the fp32 blob                              */
   uint32_t head_off;  /* float offset of head weights [n_heads][n_out] (or the rank-1 vector)          */
   uint32_t head_bias_off; /* float offset of the head biases                                           */
-  uint16_t n_out;     /* 256 or 128                                                                    */
+  uint16_t n_out;     /* 256 or 128: output columns the step computes (a narrower layer is zero-padded up)   */
   uint8_t nk;         /* number of K slab entries                                                      */
   uint8_t epi;        /* DLN_EPI_*                                                                     */
   uint8_t kslab[DLN_MAX_KSLABS]; /* 0..3 activation slabs, 4 encoded position / direction / d_raw     */
@@ -167,7 +167,9 @@ typedef struct {
   int16_t stash_slot; /* first stash slot of the output slabs, -1 = not kept                           */
   int16_t mask_slot;  /* relu bit-mask slot written (fwd) / read (bwd), -1 = none                      */
   uint8_t n_heads;
-  uint8_t pad_[3];
+  uint8_t n_valid32;  /* valid output columns / 32 (netwidth < 256: columns beyond are written as zeros, take no
+                         bias and feed no head; head rows are n_valid wide); 0 = all n_out columns              */
+  uint8_t pad_[2];
 } DlnChainStep;
 
 typedef struct {
@@ -183,6 +185,8 @@ typedef struct {
   int32_t pro_mask_slot;   /* relu mask of that layer's forward output                                  */
   int32_t pro_slot;        /* first stash slot of the prologue's activation slabs                       */
   int32_t reload_step;     /* forward: after this step slab 4 is rewritten with the encoded direction   */
+  int32_t pro_valid;       /* backward prologue: valid columns of that first dZ (= row pitch of the head
+                              weights at pro_head_off); 0 = 128 with view directions, 256 without         */
   DlnChainStep steps[DLN_MAX_STEPS];
 } DlnChainProgram;
 

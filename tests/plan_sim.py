@@ -98,15 +98,17 @@ def run_forward(plan, flat, enc_pts, enc_dir):
             Wst = stages[st.w_off + j * st.n_out * 128]
             k = 16 * st.kcnt[j]
             acc += slabs[st.kslab[j]][:, :k] @ Wst[:, :k].T
-        x = acc + flat[st.bias_off: st.bias_off + st.n_out]
+        nv = 32 * st.n_valid32 if st.n_valid32 else st.n_out      # columns beyond are padding: zeros, no bias, no head
+        x = np.zeros((P, st.n_out))
+        x[:, :nv] = acc[:, :nv] + flat[st.bias_off: st.bias_off + nv]
         if st.epi in (L.EPI_RELU, L.EPI_RELU_SIGMA, L.EPI_RELU_RGB, L.EPI_RELU_OUT):
             if st.mask_slot >= 0:
                 masks[st.mask_slot] = x > 0
             x = np.maximum(x, 0)
         heads = None
         if st.n_heads:
-            Hw = flat[st.head_off: st.head_off + st.n_heads * st.n_out].reshape(st.n_heads, st.n_out)
-            heads = x @ Hw.T + flat[st.head_bias_off: st.head_bias_off + st.n_heads]
+            Hw = flat[st.head_off: st.head_off + st.n_heads * nv].reshape(st.n_heads, nv)
+            heads = x[:, :nv] @ Hw.T + flat[st.head_bias_off: st.head_bias_off + st.n_heads]
         for i in range(st.n_out // 64):
             slabs[i] = x[:, 64 * i: 64 * i + 64].copy()
             if st.stash_slot >= 0:
@@ -132,8 +134,10 @@ def run_backward(plan, flat, d_out, masks):
     stash = {}
     nh = 3 if prog.use_viewdirs else prog.out_ch
     width = 128 if prog.use_viewdirs else 256
-    Hw = flat[prog.pro_head_off: prog.pro_head_off + nh * width].reshape(nh, width)
-    dz = (d_out[:, :nh] @ Hw) * masks[prog.pro_mask_slot][:, :width]
+    pv = prog.pro_valid if prog.pro_valid > 0 else width
+    Hw = flat[prog.pro_head_off: prog.pro_head_off + nh * pv].reshape(nh, pv)
+    dz = np.zeros((P, width))
+    dz[:, :pv] = (d_out[:, :nh] @ Hw) * masks[prog.pro_mask_slot][:, :pv]
     for i in range(width // 64):
         slabs[i] = dz[:, 64 * i: 64 * i + 64].copy()
         stash[prog.pro_slot + i] = slabs[i].copy()
@@ -148,9 +152,11 @@ def run_backward(plan, flat, d_out, masks):
             Wst = stages[st.w_off + j * st.n_out * 128]
             k = 16 * st.kcnt[j]
             acc += slabs[st.kslab[j]][:, :k] @ Wst[:, :k].T
-        x = acc
+        nv = 32 * st.n_valid32 if st.n_valid32 else st.n_out
+        x = np.zeros((P, st.n_out))
+        x[:, :nv] = acc[:, :nv]
         if st.epi == L.EPI_BWD_MASK_SIGMA:
-            x = x + dsig[:, None] * flat[st.head_off: st.head_off + st.n_out][None, :]
+            x[:, :nv] += dsig[:, None] * flat[st.head_off: st.head_off + nv][None, :]
         if st.epi in (L.EPI_BWD_MASK, L.EPI_BWD_MASK_SIGMA):
             x = x * masks[st.mask_slot]
         for i in range(st.n_out // 64):

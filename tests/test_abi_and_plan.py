@@ -96,14 +96,18 @@ def _flat_from(params, plan):
     return flat
 
 
-@pytest.mark.parametrize("D,vd,fold", [(8, True, True), (4, True, True), (6, True, True), (8, True, False),
-                                       (4, True, False), (8, False, True), (3, False, True)])
-def test_plan_reproduces_oracle_forward_and_gradients(D, vd, fold):
-    spec = O.MLPSpec(D=D, use_viewdirs=vd)
+@pytest.mark.parametrize("D,vd,fold,W", [(8, True, True, 256), (4, True, True, 256), (6, True, True, 256),
+                                         (8, True, False, 256), (4, True, False, 256), (8, False, True, 256),
+                                         (3, False, True, 256),
+                                         # netwidth < 256 (run_nerf.py:693-700 takes any): zero-padded 256-column steps
+                                         (8, True, True, 64), (8, True, True, 128), (4, True, True, 192),
+                                         (8, False, True, 64), (6, False, True, 128)])
+def test_plan_reproduces_oracle_forward_and_gradients(D, vd, fold, W):
+    spec = O.MLPSpec(D=D, W=W, use_viewdirs=vd)
     params = {k: v.double() for k, v in O.init_params(spec, seed=D).items()}
-    shape = plan_mod.NetShape(D=D, input_ch=63, input_ch_views=27, output_ch=5, use_viewdirs=vd)
+    shape = plan_mod.NetShape(D=D, W=W, input_ch=63, input_ch_views=27, output_ch=5, use_viewdirs=vd)
     plan = plan_mod.build_plan(shape, fold_feature=fold)
-    assert plan.fold == (fold and vd)
+    assert plan.fold == (fold and vd and W == 256)
     flat = plan_sim.extend_flat(plan, _flat_from(params, plan))      # what dln_mlp_fold appends (M, b')
     g = torch.Generator().manual_seed(D)
     P = 37
@@ -131,8 +135,10 @@ def test_plan_reproduces_oracle_forward_and_gradients(D, vd, fold):
 
 
 def test_plan_rejects_what_the_kernels_cannot_do():
+    with pytest.raises(NotImplementedError):      # widths are 64, 128, 192, 256 (zero-padded to the kernels' 256 columns)
+        plan_mod.build_plan(plan_mod.NetShape(D=8, W=96, input_ch=63, input_ch_views=27))
     with pytest.raises(NotImplementedError):
-        plan_mod.build_plan(plan_mod.NetShape(D=8, W=128, input_ch=63, input_ch_views=27))
+        plan_mod.build_plan(plan_mod.NetShape(D=8, W=512, input_ch=63, input_ch_views=27))
     with pytest.raises(ValueError):
         plan_mod.build_plan(plan_mod.NetShape(D=5, input_ch=63, input_ch_views=27))   # skip after last layer
     with pytest.raises(NotImplementedError):     # the semantic kernels hold one class per register / lane: K <= 32

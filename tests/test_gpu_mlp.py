@@ -202,7 +202,7 @@ def test_weights_are_repacked_after_an_optimizer_step():
 
 def test_unsupported_shapes_fail_loudly():
     with pytest.raises(NotImplementedError):
-        dn().NeRF(D=8, W=128, input_ch=63, input_ch_views=27, use_viewdirs=True).to(DEV)(torch.zeros(4, 90, device=DEV))
+        dn().NeRF(D=8, W=96, input_ch=63, input_ch_views=27, use_viewdirs=True).to(DEV)(torch.zeros(4, 90, device=DEV))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         dn().NeRF(D=8, W=256, input_ch=63, input_ch_views=27, use_viewdirs=True)(torch.zeros(4, 90))
 
@@ -266,3 +266,75 @@ def test_reference_generated_w256_case(golden_dir):
     agg = (num / den) ** 0.5
     print("  worst cosine %.5f, worst rel-L2 %.3e, aggregate rel-L2 %.3e" % (worst_cos, worst_l2, agg))
     assert worst_cos >= 0.99 and worst_l2 <= 0.16 and agg <= 2.6e-2      # measured 0.9925 / 0.127 / 1.3e-2
+
+
+@pytest.mark.parametrize("tag,D,vd", [("d8", 8, True), ("d4", 4, True), ("d8nv", 8, False)])
+def test_reference_generated_w64_cases(golden_dir, tag, D, vd):
+    """tests/golden/mlp_small.npz: the UNMODIFIED reference NeRF at netwidth 64 (forward + every parameter gradient on 96
+    points), through the CUDA MLP -- narrow layers run as zero-padded 256-column steps of the same kernels
+    (run_nerf.py:693-700 passes any netwidth)."""
+    g = np.load(os.path.join(golden_dir, "mlp_small.npz"))
+    params = {k[len(tag) + 3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith(tag + "_p_")}
+    net = dn().NeRF(D=D, W=64, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=vd)
+    net.load_state_dict(params)
+    net = net.to(DEV)
+    y = net(torch.from_numpy(g[tag + "_x"]).to(DEV))
+    ref = torch.from_numpy(g[tag + "_y"])
+    report("NeRF(W=64, D=%d) forward vs the reference module" % D, y, ref, atol=3e-2 * ref.abs().max().item())
+    (y * torch.from_numpy(g[tag + "_cot"]).to(DEV)).sum().backward()
+    worst_cos, worst_l2, num, den = 1.0, 0.0, 0.0, 0.0
+    for k, p in net.named_parameters():
+        if tag + "_g_" + k not in g.files:          # views_linears is unused without view directions
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
+            continue
+        r = torch.from_numpy(g[tag + "_g_" + k])
+        c, l = cosine(p.grad, r), rel_l2(p.grad, r)
+        print("  %-26s cos %.5f relL2 %.3e |ref| %.3e" % (k, c, l, r.norm()))
+        worst_cos, worst_l2 = min(worst_cos, c), max(worst_l2, l)
+        num += float((p.grad.detach().cpu().double() - r.double()).pow(2).sum())
+        den += float(r.double().pow(2).sum())
+    agg = (num / den) ** 0.5
+    print("  worst cosine %.5f, worst rel-L2 %.3e, aggregate rel-L2 %.3e" % (worst_cos, worst_l2, agg))
+    assert worst_cos >= 0.99 and worst_l2 <= 0.16 and agg <= 8e-2
+
+
+def test_narrow_net_renders_and_trains():
+    """netwidth 128 through the fused render route: render() + loss + backward against the fp32 oracle."""
+    n_rgb, n_dep = 96, 64
+    spec_c, spec_f = O.MLPSpec(D=4, W=128), O.MLPSpec(D=8, W=128)
+    pc = O.trained_like(O.init_params(spec_c, 3407 + 4), 1.0)
+    pf = O.trained_like(O.init_params(spec_f, 3407 + 8), 1.0)
+    ro, rd = O.synth_rays(n_rgb + n_dep, seed=9)
+    rng = O.synth_rng(n_rgb + n_dep, 64, 64, seed=9)
+    tgt, dep = O.synth_targets(n_rgb, n_dep, seed=9)
+    rb = O.pack_rays(378, 504, 407.6, ro, rd)
+    pcg = {k: v.clone().requires_grad_(True) for k, v in pc.items()}
+    pfg = {k: v.clone().requires_grad_(True) for k, v in pf.items()}
+    ref = O.render_rays(rb, pcg, spec_c, pfg, spec_f, 64, 64, rng, raw_noise_std=1.0)
+    res = O.train_loss(ref, n_rgb, tgt, dep, depth_lambda=0.01, depth_importance=1.0)
+    res["loss"].backward()
+    d = dn()
+    net_c = d.NeRF(D=4, W=128, input_ch=63, input_ch_views=27, use_viewdirs=True)
+    net_f = d.NeRF(D=8, W=128, input_ch=63, input_ch_views=27, use_viewdirs=True)
+    net_c.load_state_dict(pc), net_f.load_state_dict(pf)
+    net_c, net_f = net_c.to(DEV), net_f.to(DEV)
+    q = d.FusedQuery(d.get_embedder(10, 0)[0], d.get_embedder(4, 0)[0], 65536, 10, 4, 0)
+    inj = {k: getattr(rng, k).to(DEV) for k in ("t_rand", "noise0", "u", "noise1")}
+    rgb, disp, acc, depth, extras = d.render(378, 504, 407.6, chunk=32768, rays=torch.stack([ro, rd], 0).to(DEV),
+                                             retraw=True, near=0., far=1., network_query_fn=q, perturb=1.0, N_importance=64,
+                                             network_fine=net_f, N_samples=64, network_fn=net_c, use_viewdirs=True,
+                                             white_bkgd=False, raw_noise_std=1.0, ndc=True, _rng=inj)
+    loss = d.img2mse(rgb[:n_rgb], tgt.to(DEV)) + 0.01 * d.img2mse(depth[n_rgb:], dep.to(DEV)) \
+        + d.img2mse(extras["rgb0"][:n_rgb], tgt.to(DEV))
+    loss.backward()
+    report("rgb_map (W=128)", rgb, ref["rgb_map"], atol=2e-2)
+    report("depth_map (W=128)", depth, ref["depth_map"], atol=2e-2)
+    assert abs(loss.item() - res["loss"].item()) <= 2e-2 * abs(res["loss"].item())
+    num = den = 0.0
+    for net, pg in ((net_c, pcg), (net_f, pfg)):
+        for k, p in net.named_parameters():
+            num += float((p.grad.detach().cpu().double() - pg[k].grad.double()).pow(2).sum())
+            den += float(pg[k].grad.double().pow(2).sum())
+    agg = (num / den) ** 0.5
+    print("  aggregate gradient rel-L2 vs the fp32 oracle (W=128): %.3e" % agg)
+    assert agg <= 3e-2
