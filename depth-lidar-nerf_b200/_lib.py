@@ -20,6 +20,7 @@ MAX_KSLABS = 6
 SLAB_BYTES = 16384
 TILE_ROWS = 128
 SEM_MAX_CLASSES = 32
+WGRAD_PARTIAL_FLOATS = 256 * 256 + 256
 
 EPI_RELU, EPI_RELU_SIGMA, EPI_LINEAR, EPI_RELU_RGB, EPI_RELU_OUT = 0, 1, 2, 3, 4
 EPI_BWD_COPY, EPI_BWD_MASK, EPI_BWD_MASK_SIGMA = 8, 9, 10
@@ -90,7 +91,7 @@ SIGNATURES = {
     "dln_sample_pdf": [_P, _I, _I, _P, _I, _I, _P, _I, _P, _P, _I, _P, _P, _P, _I, _P],
     "dln_searchsorted": [_P, _I, _I, _P, _I, _I, _P, _I, _P],
     "dln_mlp_chain": [C.POINTER(ChainProgram), C.POINTER(ChainArgs), _I, _P],
-    "dln_mlp_wgrad": [_P, _I, _I, _P, _I, _P, _I, _LL, _P, _P],
+    "dln_mlp_wgrad": [_P, _I, _I, _P, _I, _P, _I, _LL, _P, _P, _P],
     "dln_mlp_pack_weights": [_P, _P, _I, _P, _P],
     "dln_inv_depth_smooth_fwd": [_P, _P, _I, _I, _I, _P, _P],
     "dln_inv_depth_smooth_bwd": [_P, _P, _I, _I, _I, _P, _P, _P, _P],

@@ -634,6 +634,7 @@ constexpr int kWgThreads = 256;       // warp 0 producer, warp 1 MMA, warps 4..7
 constexpr int kWgStages = 3;
 constexpr int kHalfSlab = kSlab / 2;  // 64 points x 64 features
 constexpr int kWgStageBytes = 8 * kHalfSlab;  // 4 A + 4 B half-slabs = 64 KB
+constexpr int kWgPartialFloats = 256 * 256 + 256;   // per-CTA block of the deterministic reduction: dW accumulator + bias sums
 
 struct WgradSmall {
   uint64_t full[kWgStages], empty[kWgStages];
@@ -645,7 +646,7 @@ constexpr size_t kWgradSmemBytes = (size_t)kWgStages * kWgStageBytes + sizeof(Wg
 __global__ void __launch_bounds__(kWgThreads, 1)
     wgrad_kernel(const DlnWgradItem* __restrict__ items, int splits, const uint8_t* __restrict__ stash_fwd,
                  int fwd_slots, const uint8_t* __restrict__ stash_bwd, int bwd_slots, long long n_tiles,
-                 float* __restrict__ grads) {
+                 float* __restrict__ grads, float* __restrict__ partial) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   WgradSmall* sm = reinterpret_cast<WgradSmall*>(smem + kWgStages * kWgStageBytes);
@@ -741,12 +742,18 @@ __global__ void __launch_bounds__(kWgThreads, 1)
       mbar_arrive(&sm->empty[stage]);
       if (++stage == kWgStages) stage = 0, phase ^= 1;
     }
-    if (do_bias) {
+    // Deterministic mode (partial != null): this CTA's share of dW / db goes to its own block of `partial` with plain
+    // stores -- [256 accumulator rows][256 columns] then [256 bias sums] -- and wgrad_reduce_kernel adds the blocks of
+    // an item in split order.  Otherwise fp32 atomics straight into the gradient buffer (run-to-run order varies).
+    float* const pblk = partial ? partial + (size_t)blockIdx.x * kWgPartialFloats : nullptr;
+    if (pblk) {
+      *reinterpret_cast<float2*>(pblk + 65536 + feat) = make_float2(do_bias ? b0 : 0.f, do_bias ? b1 : 0.f);
+    } else if (do_bias) {
       float* db = grads + it.db_off;
       if (feat >= it.db_col_off && feat < it.db_col_off + it.db_n) atomicAdd(db + feat - it.db_col_off, b0);
       if (feat + 1 >= it.db_col_off && feat + 1 < it.db_col_off + it.db_n) atomicAdd(db + feat + 1 - it.db_col_off, b1);
     }
-    // ---- dW: TMEM -> global (fp32 atomics; several CTAs own the same item)
+    // ---- dW: TMEM -> global
     mbar_wait(&sm->acc_full, 0);
     tc_fence_after();
     float* dw = grads + it.dw_off;
@@ -758,7 +765,13 @@ __global__ void __launch_bounds__(kWgThreads, 1)
         uint32_t v[32];
         tmem_ld32(tmem_base + h * 256 + c * 32 + lane_addr, v);
         tmem_ld_wait();
-        if (row_ok) {
+        if (pblk) {
+          float4* dst = reinterpret_cast<float4*>(pblk + (size_t)(h * 128 + r) * 256 + c * 32);
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            dst[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                                 __uint_as_float(v[4 * q + 3]));
+        } else if (row_ok) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const int col = c * 32 + i;
@@ -772,6 +785,30 @@ __global__ void __launch_bounds__(kWgThreads, 1)
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// Second pass of the deterministic reduction: grid (16-row groups, items); thread = column.  The blocks of the splits
+// of an item are added in split order (fixed summation order -> bit-reproducible gradients), skipping the splits that
+// had no tiles, and the sum is ADDED to the gradient buffer (it accumulates across ray chunks; items never overlap).
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const DlnWgradItem* __restrict__ items, int splits, long long n_tiles,
+                                                            const float* __restrict__ partial, float* __restrict__ grads) {
+  const DlnWgradItem it = items[blockIdx.y];
+  const long long per = (n_tiles + splits - 1) / splits;
+  const int live = (int)((n_tiles + per - 1) / per);                 // splits [0, live) had work
+  const float* blk = partial + (size_t)blockIdx.y * splits * kWgPartialFloats;
+  const int col = threadIdx.x;
+  for (int i = 0; i < 16; ++i) {
+    const int row = blockIdx.x * 16 + i;
+    if (row >= it.n_rows || col >= it.n_cols) continue;
+    float acc = 0.f;
+    for (int s = 0; s < live; ++s) acc += blk[(size_t)s * kWgPartialFloats + (size_t)(it.row_off + row) * 256 + col];
+    grads[it.dw_off + (size_t)row * it.ld + it.col_off + col] += acc;
+  }
+  if (blockIdx.x == 0 && it.db_off >= 0 && col < it.db_n) {
+    float acc = 0.f;
+    for (int s = 0; s < live; ++s) acc += blk[(size_t)s * kWgPartialFloats + 65536 + it.db_col_off + col];
+    grads[it.db_off + col] += acc;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -874,8 +911,10 @@ int dln_mlp_chain(const DlnChainProgram* prog, const DlnChainArgs* args, int num
 }
 
 int dln_mlp_wgrad(const DlnWgradItem* items_dev, int n_items, int splits, const void* stash_fwd, int fwd_slots,
-                  const void* stash_bwd, int bwd_slots, long long n_tiles, float* grads_flat, void* stream) {
+                  const void* stash_bwd, int bwd_slots, long long n_tiles, float* grads_flat, float* partial,
+                  void* stream) {
   DLN_CHECK_ARG(items_dev && n_items >= 1 && splits >= 1 && stash_fwd && stash_bwd && grads_flat && n_tiles >= 0);
+  DLN_CHECK_ARG(!partial || (reinterpret_cast<uintptr_t>(partial) & 15) == 0);
   if (n_tiles == 0) return DLN_OK;
   bool& attr_set = dln_device_flag(1);
   if (!attr_set) {
@@ -885,7 +924,13 @@ int dln_mlp_wgrad(const DlnWgradItem* items_dev, int n_items, int splits, const 
   }
   wgrad_kernel<<<(unsigned)(n_items * splits), kWgThreads, kWgradSmemBytes, (cudaStream_t)stream>>>(
       items_dev, splits, reinterpret_cast<const uint8_t*>(stash_fwd), fwd_slots,
-      reinterpret_cast<const uint8_t*>(stash_bwd), bwd_slots, n_tiles, grads_flat);
+      reinterpret_cast<const uint8_t*>(stash_bwd), bwd_slots, n_tiles, grads_flat, partial);
+  if (partial) {
+    int st = dln_launch_status();
+    if (st != DLN_OK) return st;
+    wgrad_reduce_kernel<<<dim3(16, (unsigned)n_items), 256, 0, (cudaStream_t)stream>>>(items_dev, splits, n_tiles, partial,
+                                                                                        grads_flat);
+  }
   return dln_launch_status();
 }
 

@@ -346,8 +346,13 @@ class NeRF(nn.Module):
         # the second reader and neighbouring slots of a tile are read together; two waves or per-item split counts
         # proportional to the bytes were both measured 10-50 % slower.
         splits = int(max(1, min(n_tiles, (min(st["sms"], wgrad_sms) if wgrad_sms else st["sms"]) // n_items)))
+        # deterministic reduction (default): per-CTA shares in a scratch, added in split order by a second kernel;
+        # DLN_WGRAD_ATOMICS=1 selects fp32 atomics straight into the gradient buffer instead
+        partial = None
+        if not os.environ.get("DLN_WGRAD_ATOMICS"):
+            partial = torch.empty(n_items * splits * L.WGRAD_PARTIAL_FLOATS, device=dev, dtype=torch.float32)
         L.call("dln_mlp_wgrad", st["items"].data_ptr(), n_items, splits, stash_f.data_ptr(), pl.fwd_slots,
-                                  stash_b.data_ptr(), pl.bwd_slots, n_tiles, gflat.data_ptr(), s, tag="mlp_wgrad D=%d" % self.D)
+               stash_b.data_ptr(), pl.bwd_slots, n_tiles, gflat.data_ptr(), _ptr(partial), s, tag="mlp_wgrad D=%d" % self.D)
         if pl.fold:
             L.call("dln_mlp_unfold_grads", st["flat"].data_ptr(), gflat.data_ptr(), *self._fold_args(), s,
                    tag="unfold_grads")

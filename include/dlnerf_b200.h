@@ -236,10 +236,14 @@ typedef struct {
   int32_t db_n;            /* features summed                                                          */
 } DlnWgradItem;
 
-/* items_dev: DEVICE array of n_items; each item is split over `splits` CTAs along the points. */
+/* items_dev: DEVICE array of n_items; each item is split over `splits` CTAs along the points.
+ * `partial`: null -> the CTAs add their shares to grads_flat with fp32 atomics (summation order varies from run to
+ * run); else a scratch of n_items * splits * DLN_WGRAD_PARTIAL_FLOATS floats (16-byte aligned) -> every CTA stores its
+ * share there and a second kernel adds the shares of an item in split order: bit-reproducible gradients. */
+#define DLN_WGRAD_PARTIAL_FLOATS (256 * 256 + 256)
 int dln_mlp_wgrad(const DlnWgradItem* items_dev, int n_items, int splits, const void* stash_fwd,
                   int fwd_slots, const void* stash_bwd, int bwd_slots, long long n_tiles, float* grads_flat,
-                  void* stream);
+                  float* partial, void* stream);
 
 /* fp32 master parameters -> bf16 SWIZZLE_128B weight stages. */
 typedef struct {

@@ -210,8 +210,9 @@ def test_unsupported_shapes_fail_loudly():
 def test_full_size_backward_is_additive_over_points():
     """BASELINE config B size (4096 rays x 128 fine samples = 524 288 points, 4096 tiles, 28 per persistent CTA):
     size-independent property instead of an oracle run -- the parameter gradient of the whole batch equals the sum
-    of the gradients of its two halves (wgrad is a sum over points), and a second run reproduces the first up to
-    fp32 atomics ordering."""
+    of the gradients of its two halves (wgrad is a sum over points), and a second run reproduces the first BIT FOR BIT
+    (wgrad's shares are added in a fixed order by the second reduction pass; the fp32-atomics variant,
+    DLN_WGRAD_ATOMICS=1, is reproducible to ~1e-7 only)."""
     net, params, spec = make_net(8)
     N, S = 4096, 128
     g = torch.Generator().manual_seed(0)
@@ -236,7 +237,11 @@ def test_full_size_backward_is_additive_over_points():
     worst_rep = max(rel_l2(x, y) for x, y in zip(again, full))
     worst_add = max(rel_l2(x + y, f) for x, y, f in zip(a, b, full))
     print("  run-to-run rel-L2 %.2e, halves-vs-whole rel-L2 %.2e" % (worst_rep, worst_add))
-    assert worst_rep <= 1e-4 and worst_add <= 1e-4
+    assert worst_add <= 1e-4
+    if os.environ.get("DLN_WGRAD_ATOMICS"):
+        assert worst_rep <= 1e-4
+    else:
+        assert all(torch.equal(x, y) for x, y in zip(again, full)), "gradients must be bit-reproducible run to run"
     assert all(torch.isfinite(x).all() for x in full)
 
 

@@ -63,8 +63,9 @@ gflat = torch.zeros(plan.n_params, device=DEV)
 n_items = len(plan.wgrad)
 for splits in (max(1, min(n_tiles, (2 * st["sms"]) // n_items)), n_tiles):
     gflat.zero_()
+    PARTIAL = None
     L.check(L.lib().dln_mlp_wgrad(st["items"].data_ptr(), n_items, splits, saved[0].data_ptr(), plan.fwd_slots,
-                                  stash_b.data_ptr(), plan.bwd_slots, n_tiles, gflat.data_ptr(), dn.ops._stream()), "wgrad")
+                                  stash_b.data_ptr(), plan.bwd_slots, n_tiles, gflat.data_ptr(), PARTIAL, dn.ops._stream()), "wgrad")
     torch.cuda.synchronize()
     print("wgrad with splits=%d (tiles per CTA %.1f)" % (splits, n_tiles / splits))
     for name, shp in plan.shape.param_shapes():

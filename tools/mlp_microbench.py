@@ -41,8 +41,10 @@ for D in (8, 4):
     t_dg_nostash = timeit(lambda: dgrad(False))
     gflat = torch.zeros(plan.n_params, device=DEV)
     res = {}
+    _part = torch.empty(len(plan.wgrad) * 64 * L.WGRAD_PARTIAL_FLOATS, device=DEV) if not os.environ.get("DLN_WGRAD_ATOMICS") else None
+    PARTIAL = _part.data_ptr() if _part is not None else None
     for splits in [int(x) for x in os.environ.get("SPLITS", "10,21,32,42").split(",")]:
-        res[splits] = timeit(lambda: L.check(L.lib().dln_mlp_wgrad(st["items"].data_ptr(), len(plan.wgrad), splits, saved[0].data_ptr(), plan.fwd_slots, stash_b.data_ptr(), plan.bwd_slots, n_tiles, gflat.data_ptr(), dn.ops._stream()), "wgrad"))
+        res[splits] = timeit(lambda: L.check(L.lib().dln_mlp_wgrad(st["items"].data_ptr(), len(plan.wgrad), splits, saved[0].data_ptr(), plan.fwd_slots, stash_b.data_ptr(), plan.bwd_slots, n_tiles, gflat.data_ptr(), PARTIAL, dn.ops._stream()), "wgrad"))
     print("D=%d P=%d  fwd(infer) %.3f ms %.0f TF/s | fwd(train) %.3f ms %.0f TF/s | dgrad %.3f ms %.0f TF/s (no stash %.3f) | wgrad %s" % (
         D, P, t_inf, fl_f / t_inf / 1e9, t_trn, fl_f / t_trn / 1e9, t_dg, fl_d / t_dg / 1e9, t_dg_nostash,
         {k: "%.3f" % v for k, v in res.items()}))
