@@ -47,7 +47,8 @@ class ChainArgs(C.Structure):
                 ("z", C.c_void_p), ("S", C.c_int32), ("x", C.c_void_p), ("x_ld", C.c_int32),
                 ("wblob", C.c_void_p), ("fblob", C.c_void_p), ("out", C.c_void_p), ("d_out", C.c_void_p),
                 ("stash", C.c_void_p), ("masks", C.c_void_p), ("trace", C.c_void_p),
-                ("sem_g", C.c_void_p), ("sem_g_div", C.c_int32), ("pad_", C.c_int32)]
+                ("sem_g", C.c_void_p), ("sem_g_div", C.c_int32), ("z_lindisp", C.c_int32),
+                ("z_gen", C.c_void_p), ("z_rng_state", C.c_void_p), ("z_rng_offset", C.c_ulonglong)]
 
 
 class WgradItem(C.Structure):

@@ -129,6 +129,26 @@ __device__ __forceinline__ void rng_fill(const RngKey& key, unsigned long long e
   }
 }
 
+// ------------------------------------------------------------------ stratified depths (run_nerf.py:571-593)
+// z_i before the jitter: near (1 - t_i) + far t_i, or the lindisp form; t = linspace(0, 1, S)
+__device__ __forceinline__ float base_z(float nr, float fr, int i, int S, int lindisp) {
+  const float t = linspace01(i, S);
+  if (!lindisp) return __fadd_rn(__fmul_rn(nr, __fsub_rn(1.f, t)), __fmul_rn(fr, t));
+  return __fdiv_rn(1.f, __fadd_rn(__fmul_rn(__fdiv_rn(1.f, nr), __fsub_rn(1.f, t)), __fmul_rn(__fdiv_rn(1.f, fr), t)));
+}
+// Sample i of a ray with bounds (nr, fr): bin centre (jitter == false) or lower + (upper - lower) * t_rand with
+// mids / upper / lower as the reference forms them.  One definition for the stand-alone kernel (render_kernels.cu) and for
+// the MLP chain's tile prologue (mlp_chain2.cu), so the two routes give the same bits.
+__device__ __forceinline__ float stratified_z_point(float nr, float fr, int i, int S, int lindisp, bool jitter, float t_rand) {
+  const float zi = base_z(nr, fr, i, S, lindisp);
+  if (!jitter) return zi;
+  const float zl = i > 0 ? base_z(nr, fr, i - 1, S, lindisp) : zi;
+  const float zr = i < S - 1 ? base_z(nr, fr, i + 1, S, lindisp) : zi;
+  const float lower = i > 0 ? __fmul_rn(0.5f, __fadd_rn(zi, zl)) : zi;
+  const float upper = i < S - 1 ? __fmul_rn(0.5f, __fadd_rn(zr, zi)) : zi;
+  return __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), t_rand));
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
 }

@@ -501,7 +501,19 @@ __global__ void __launch_bounds__(k2Threads, 1)
           const long long ray = (unsigned)p / (unsigned)args.S;      // P < 2^31 (checked by the host side)
           const float* rp = args.rays + (size_t)ray * args.ray_stride;
           if (which == 0) {
-            const float zz = args.z[p];
+            float zz;
+            if (args.z_gen != nullptr) {
+              // fused stratified sampling (run_nerf.py:571-593): the depth of this point is computed here -- every
+              // warpgroup of the row gets the same bits -- and the owner of the first quarter writes it out
+              const int i = (int)((unsigned)p - (unsigned)ray * (unsigned)args.S);
+              float tr[1] = {0.f};
+              if (args.z_rng_state != nullptr)
+                rng_fill<1, false>(rng_key(RngRef{args.z_rng_state, args.z_rng_offset}), (unsigned long long)p, tr);
+              zz = stratified_z_point(rp[6], rp[7], i, args.S, args.z_lindisp, args.z_rng_state != nullptr, tr[0]);
+              if (q == 0) args.z_gen[p] = zz;
+            } else {
+              zz = args.z[p];
+            }
             vx = rp[0] + rp[3] * zz, vy = rp[1] + rp[4] * zz, vz = rp[2] + rp[5] * zz;
           } else {
             vx = rp[args.vd_col], vy = rp[args.vd_col + 1], vz = rp[args.vd_col + 2];

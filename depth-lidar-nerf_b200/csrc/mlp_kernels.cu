@@ -878,7 +878,8 @@ int dln_mlp_chain(const DlnChainProgram* prog, const DlnChainArgs* args, int num
     DLN_CHECK_ARG(!args->sem_g || (args->sem_g_div >= 1 && (reinterpret_cast<uintptr_t>(args->sem_g) & 15) == 0));
   } else {
     DLN_CHECK_ARG(args->out);
-    DLN_CHECK_ARG(args->x || (args->rays && args->z && args->S >= 1 && args->ray_stride >= 6));
+    DLN_CHECK_ARG(args->x || (args->rays && (args->z || args->z_gen) && args->S >= 1 && args->ray_stride >= 6));
+    DLN_CHECK_ARG(!args->z_gen || (!args->x && args->ray_stride >= 8 && chain_variant() == 2));   // CTA-pair kernel only
   }
   if (args->stash && prog->stash_slots > 0) DLN_CHECK_ARG((reinterpret_cast<uintptr_t>(args->stash) & 15) == 0);
   if (args->P == 0) return DLN_OK;

@@ -217,7 +217,7 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
             return rng[name], None
         return None, (gen, off + k)
 
-    def query(net, z):
+    def query(net, z, strat=None):
         """(raw for compositing, per-ray semantic logits | None, raw as the reference returns it).  Fused route: the
         logits come from the kept activations of the last trunk layer (one sum per ray, csrc/semantic_kernels.cu);
         compositing runs on the 4-channel raw and the per-sample logits are appended only to the returned copy.
@@ -227,9 +227,9 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
             if semantic_loss and not K:
                 raise RuntimeError("semantic_loss=True needs networks built with semantic_num_classes")
             if not (semantic_loss or (retraw and K)):
-                raw = net.forward_rays(rb, z)
+                raw = net.forward_rays(rb, z, strat=strat)
                 return raw, None, raw
-            raw, sem, pts = net.forward_rays(rb, z, semantic=bool(semantic_loss), point_logits=bool(retraw))
+            raw, sem, pts = net.forward_rays(rb, z, semantic=bool(semantic_loss), point_logits=bool(retraw), strat=strat)
             return raw, sem, (torch.cat([raw, pts], -1) if retraw else raw)
         pts = rays_o[..., None, :] + rays_d[..., None, :] * z[..., :, None]
         raw = network_query_fn(pts, viewdirs, net)
@@ -240,8 +240,14 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
         return ops.composite(raw, z, rays_d, noise, float(raw_noise_std), bool(white_bkgd), rng=g)
 
     t_rand, g = draw("t_rand", 0) if perturb > 0. else (None, None)
-    z_vals = ops.stratified_z(rb, N_samples, t_rand, lindisp, rng=g)
-    raw, sem, raw_ret = query(network_fn, z_vals)
+    if (t_rand is None and isinstance(network_query_fn, FusedQuery) and network_query_fn.fused_ok(network_fn, rb)
+            and network_fn.fused_sampling_available()):
+        # stratified sampling fused into the coarse network's kernel: it computes the depths it encodes and fills z_vals
+        z_vals = torch.empty(N, N_samples, device=dev, dtype=torch.float32)
+        raw, sem, raw_ret = query(network_fn, z_vals, strat=dict(rng=g, lindisp=lindisp))
+    else:
+        z_vals = ops.stratified_z(rb, N_samples, t_rand, lindisp, rng=g)
+        raw, sem, raw_ret = query(network_fn, z_vals)
     rgb_map, disp_map, acc_map, weights, depth_map = composite(raw, z_vals, "noise0", 1)
 
     ret = {}

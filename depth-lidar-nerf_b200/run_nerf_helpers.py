@@ -271,9 +271,19 @@ class NeRF(nn.Module):
         out = torch.empty(P, self._shape.out_ch, device=dev, dtype=torch.float32)
         args = L.ChainArgs()
         args.P = P
+        strat = None
+        if isinstance(mode, tuple):              # ("rays", strat): the kernel computes the stratified depths itself
+            mode, strat = mode
         if mode == "rays":                       # a = ray_batch [N, C], b = z_vals [N, S]
             args.rays, args.ray_stride, args.vd_col = a.data_ptr(), a.stride(0), a.shape[1] - 3
-            args.z, args.S = b.data_ptr(), b.shape[1]
+            args.S = b.shape[1]
+            if strat is None:
+                args.z = b.data_ptr()
+            else:
+                # fused stratified sampling (run_nerf.py:571-593): b is an OUTPUT, filled by the tile prologues
+                args.z_gen, args.z_lindisp = b.data_ptr(), int(bool(strat.get("lindisp")))
+                if strat.get("rng") is not None:
+                    args.z_rng_state, args.z_rng_offset = strat["rng"][0].ptr(), int(strat["rng"][1])
         else:                                    # a = x [P, in]
             args.x, args.x_ld = a.data_ptr(), a.stride(0)
         args.wblob, args.fblob, args.out = st["wf"].data_ptr(), st["flat"].data_ptr(), out.data_ptr()
@@ -390,27 +400,38 @@ class NeRF(nn.Module):
             out = _MLP.apply(self, "x", xs, None, P, self._keep(), *self._ordered_params())
         return out.reshape(*x.shape[:-1], out.shape[-1])
 
+    @staticmethod
+    def fused_sampling_available() -> bool:
+        """The CTA-pair chain kernel (default) can compute the stratified depths in its tile prologue."""
+        return os.environ.get("DLN_CHAIN", "2")[:1] != "1"
+
     @ops.on_device_of(1)
-    def forward_rays(self, ray_batch: Tensor, z_vals: Tensor, semantic: bool = False, point_logits: bool = False):
+    def forward_rays(self, ray_batch: Tensor, z_vals: Tensor, semantic: bool = False, point_logits: bool = False,
+                     strat: Optional[dict] = None):
         """Fused path of run_nerf.py:595 + run_network (:60-74) + forward: points o + d*z are formed,
         encoded (positions per sample, the unit view direction once per ray) and pushed through the MLP
         inside one kernel.  ray_batch is the packed [N, 8|11] batch of render(); returns raw[N, S, 4].
 
         With the semantic head, ``semantic`` / ``point_logits`` make it return (raw[N, S, 4], sem_preds[N, K] | None,
         logits[N, S, K] | None): the per-ray logits of raw2outputs (helpers:589: the UNWEIGHTED sum of the per-sample
-        logits; differentiable) and the per-sample logits that fill raw[..., 4:] in the reference (values only)."""
+        logits; differentiable) and the per-sample logits that fill raw[..., 4:] in the reference (values only).
+
+        ``strat`` = dict(rng=(RngState, offset) | None, lindisp=bool): fused stratified sampling (run_nerf.py:571-593) --
+        ``z_vals`` is then an uninitialised [N, S] tensor the kernel FILLS (same bits as ``ops.stratified_z``) while it
+        encodes the points; the coarse pass of render_rays / train_step uses it."""
         rb, z = ops._f32(ray_batch, "forward_rays"), ops._f32(z_vals, "forward_rays")
         if self.use_viewdirs and rb.shape[1] < 11:
             raise RuntimeError("use_viewdirs=True needs the unit view direction in the last 3 ray columns")
         N, S = z.shape
         if (semantic or point_logits) and not self.sem_K:
             raise RuntimeError("this NeRF has no semantic head (semantic_num_classes / use_viewdirs)")
+        mode = "rays" if strat is None else ("rays", strat)
         if semantic or point_logits:
-            out, sem, pts = _MLPSem.apply(self, "rays", rb, z, N * S, S if semantic else 0, bool(point_logits),
+            out, sem, pts = _MLPSem.apply(self, mode, rb, z, N * S, S if semantic else 0, bool(point_logits),
                                           self._keep(), *self._ordered_params())
             return (out.reshape(N, S, 4), sem if semantic else None,
                     pts.reshape(N, S, -1) if point_logits else None)
-        out = _MLP.apply(self, "rays", rb, z, N * S, self._keep(), *self._ordered_params())
+        out = _MLP.apply(self, mode, rb, z, N * S, self._keep(), *self._ordered_params())
         return out.reshape(N, S, out.shape[-1])
 
     def load_weights_from_keras(self, weights):

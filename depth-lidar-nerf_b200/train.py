@@ -272,9 +272,16 @@ def train_step(H, W, focal, batch_rays: Tensor, target_s: Tensor, target_depth: 
             return None, (gen, 4 * c + k)
 
         t_rand, g_t = draw("t_rand", 0) if perturb > 0. else (None, None)
-        z0 = ops.stratified_z(rb_c, N_samples, t_rand, lindisp, rng=g_t)
         sem_kw = lambda S: dict(sem_group=S) if use_sem else {}          # noqa: E731
-        raw0, saved0, *sem0 = network_fn._run_forward("rays", rb_c, z0, Nc * N_samples, keep=True,
+        if t_rand is None and network_fn.fused_sampling_available():
+            # stratified sampling fused into the coarse chain's tile prologue (north_star part 1): the kernel computes
+            # the depths it encodes and writes z0 for the compositing kernels -- no separate launch, no z round trip
+            z0 = torch.empty(Nc, N_samples, device=dev, dtype=torch.float32)
+            mode0 = ("rays", dict(rng=g_t, lindisp=lindisp))
+        else:
+            z0 = ops.stratified_z(rb_c, N_samples, t_rand, lindisp, rng=g_t)
+            mode0 = "rays"
+        raw0, saved0, *sem0 = network_fn._run_forward(mode0, rb_c, z0, Nc * N_samples, keep=True,
                                                       force_pack=_force_pack and c == 0, **sem_kw(N_samples))
         raw0 = raw0.view(Nc, N_samples, -1)
         noise0, g_n0 = draw("noise0", 1) if raw_noise_std > 0. else (None, None)

@@ -211,7 +211,14 @@ typedef struct {
   const float* sem_g;      /* bwd, optional: G[ceil(P / sem_g_div), 256] added to dH of the last trunk layer
                               (DLN_EPI_BWD_MASK_SIGMA step) -- the semantic head's input gradient, dln_sem_head_bwd */
   int32_t sem_g_div;       /* points per row of sem_g (samples per ray; 1 = one row per point)                  */
-  int32_t pad_;
+  int32_t z_lindisp;       /* fused stratified sampling: sample linearly in inverse depth (run_nerf.py:575-578)  */
+  /* Fused stratified sampling (forward, fused mode, CTA-pair kernel): when z_gen is set the tile prologue COMPUTES the
+   * depths of its points (run_nerf.py:571-593: t_vals, near/far from rays columns 6/7, mids / upper / lower, jitter drawn
+   * in-kernel as in dln_stratified_z_rng when z_rng_state is set, bin centres otherwise), uses them for the encoding and
+   * writes them to z_gen[N,S] for the compositing kernels; `z` is then not read.  Same bits as dln_stratified_z(_rng). */
+  float* z_gen;
+  const unsigned long long* z_rng_state;
+  unsigned long long z_rng_offset;
 } DlnChainArgs;
 
 /* Fused MLP chain (forward or dgrad).  prog_host / args_host are HOST structs passed by value to the

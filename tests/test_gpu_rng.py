@@ -234,3 +234,25 @@ def test_no_grad_forward_writes_no_stash():
     stash = N * S * 4608                             # 36 slabs x 16 KB per 128 points
     print("  peak bytes: no_grad %.1f MB, grad %.1f MB (stash %.1f MB)" % (p_inf / 1e6, p_train / 1e6, stash / 1e6))
     assert p_inf < 0.05 * stash and p_train >= stash
+
+
+@pytest.mark.parametrize("perturb,lindisp", [(True, False), (False, False), (True, True)])
+def test_fused_stratified_sampling_gives_the_stand_alone_kernels_bits(perturb, lindisp):
+    """north_star part 1: the coarse chain's tile prologue computes the stratified depths it encodes (run_nerf.py:571-593)
+    and writes z_vals; they must equal dln_stratified_z(_rng) bit for bit (same draws, same arithmetic), and so must the
+    network output that was computed from them."""
+    d = dn()
+    net, _, _ = make_net(4, seed=5)
+    N, S = 300, 64                       # 150 tiles: several per CTA pair, the last one partial
+    ro, rd = O.synth_rays(N, seed=12)
+    rb = d.pack_ray_batch(378, 504, 407.6, torch.stack([ro, rd], 0).to(DEV), ndc=not lindisp, near=0.5 if lindisp else 0.,
+                          far=6. if lindisp else 1.)
+    st = d.ops.RngState(torch.device(DEV), 1234)
+    rng = (st, 7) if perturb else None
+    z_ref = d.ops.stratified_z(rb, S, None, lindisp, rng=rng)
+    with torch.no_grad():
+        raw_ref = net.forward_rays(rb, z_ref)
+        z = torch.full((N, S), float("nan"), device=DEV)
+        raw = net.forward_rays(rb, z, strat=dict(rng=rng, lindisp=lindisp))
+    assert torch.equal(z, z_ref), "fused stratified depths differ from the stand-alone kernel"
+    assert torch.equal(raw, raw_ref)
