@@ -14,6 +14,7 @@
 from __future__ import annotations
 
 import math
+import os as _os
 from typing import Dict, Optional, Sequence
 
 import torch
@@ -246,6 +247,7 @@ def train_step(H, W, focal, batch_rays: Tensor, target_s: Tensor, target_depth: 
     gacc = [torch.zeros(net._plan.n_flat, device=dev, dtype=torch.float32) for net in (network_fn, network_fine)]
     gen = rng_state if rng_state is not None else ops.default_rng(dev, 1)
     main = torch.cuda.current_stream(dev)
+    advanced = []
 
     for c in range(n_chunks):
         if n_chunks == 1:
@@ -273,6 +275,16 @@ def train_step(H, W, focal, batch_rays: Tensor, target_s: Tensor, target_depth: 
 
         t_rand, g_t = draw("t_rand", 0) if perturb > 0. else (None, None)
         sem_kw = lambda S: dict(sem_group=S) if use_sem else {}          # noqa: E731
+        pack_ev = None
+        if c == 0 and overlap_coarse_backward and not _os.environ.get("DLN_NO_PACK_OVERLAP"):
+            # the fine network's fp32 -> bf16 weight re-pack (fold + two pack launches, ~40 us) does not depend on
+            # anything of this step: it runs on the side stream under the coarse forward
+            s0 = _side_stream(dev)
+            s0.wait_stream(main)
+            with torch.cuda.stream(s0):
+                network_fine._pack(network_fine._state(), force=_force_pack)
+                pack_ev = torch.cuda.Event()
+                pack_ev.record(s0)
         if t_rand is None and network_fn.fused_sampling_available():
             # stratified sampling fused into the coarse chain's tile prologue (north_star part 1): the kernel computes
             # the depths it encodes and writes z0 for the compositing kernels -- no separate launch, no z round trip
@@ -306,6 +318,11 @@ def train_step(H, W, focal, batch_rays: Tensor, target_s: Tensor, target_depth: 
                 # network's kernels still running on the main stream
                 _assign_grads(network_fn, g)
                 allreduce_gradients(list(network_fn.parameters()), world_size, group, average=False)
+            if c == n_chunks - 1 and side is not main and not _rng and not early:
+                # every kernel that draws from the generator's current base has been enqueued (the main stream's before
+                # this stream forked): the counter bump rides on the side stream, off the step's critical path
+                gen.advance(4 * n_chunks)
+                advanced.append(True)
             return g
 
         early = bool(coarse_loss or use_sem) and overlap_coarse_backward and coarse_sms is not None
@@ -318,9 +335,11 @@ def train_step(H, W, focal, batch_rays: Tensor, target_s: Tensor, target_depth: 
             side.wait_stream(main)
             with torch.cuda.stream(side):
                 grads_c = coarse_backward()
+        if pack_ev is not None:
+            main.wait_event(pack_ev)
         raw1, saved1, *sem1 = network_fine._run_forward("rays", rb_c, z1, Nc * S1, keep=True,
-                                                        force_pack=_force_pack and c == 0, sms=fine_sms if early else None,
-                                                        **sem_kw(S1))
+                                                        force_pack=_force_pack and c == 0 and pack_ev is None,
+                                                        sms=fine_sms if early else None, **sem_kw(S1))
         raw1 = raw1.view(Nc, S1, -1)
         noise1, g_n1 = draw("noise1", 3) if raw_noise_std > 0. else (None, None)
         # fine pass: colour loss on the RGB rays, depth loss on the depth rays (run_nerf.py:1461, :1500-1524)
@@ -343,7 +362,7 @@ def train_step(H, W, focal, batch_rays: Tensor, target_s: Tensor, target_depth: 
         if side is not None and side is not main:
             main.wait_stream(side)
         del saved1, d_raw1, raw1, saved0
-    if not _rng:
+    if not _rng and not advanced:
         gen.advance(4 * n_chunks)             # the next step (or graph replay) names fresh tensors
     _assign_grads(network_fine, grads_f)
     if coarse_loss or use_sem:
