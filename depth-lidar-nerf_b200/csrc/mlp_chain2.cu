@@ -11,15 +11,22 @@
 //     per slot = the A operand of the next layer AND the staging buffer of the stash copy -- one st.shared serves both),
 //     one 256-column fp32 accumulator per slot in tensor memory (2 x 256 = all 512 columns);
 //   * the MMA warp of the leader CTA alternates X(l), Y(l), X(l+1), ... : the epilogue of X(l) runs under the MMAs of
-//     Y(l).  Every hand-off is one mbarrier phase per (slot, step).
+//     Y(l).  Operands are handed over per (slot, step) in two halves (activation slabs 0, 1 first), one mbarrier phase
+//     each; remote arrivals use the default CTA-scope semantics behind fence.proxy.async (the cluster-scope forms cost
+//     a MEMBAR + ERRBAR per arrival and an L1 invalidation per wait, see mbar_arrive_cluster).
+//
+// Bound: without the activation stash the epilogue's instruction issue, ~0.72 of the burst bf16
+// peak for the D=8 forward; with it (training) the HBM write-only rate -- the kernel is a pure write stream.
 //
 // Per-CTA shared memory: A[2][4] slabs 128 KB | AUX[2] 32 KB (encoded position -> encoded direction, or d_raw; scratch
 // of the head sums at the end of a tile) | weight ring 4 x 16 KB | barriers.  Biases and head weights are read through
 // the read-only path (no room to stage them).
 //
-// Warp roles (608 threads, both CTAs): warp 0 lane 0 weight producer (its half of every K slab) and lane 1 weight-arrival
-// helper (tells the leader that this CTA's half has landed), warp 1 MMA issuer (leader CTA only) + TMEM owner, warp 2
-// stash lane, warps 3..18 epilogue: warpgroup g owns the columns [g n_out/4, (g+1) n_out/4) of both slots, thread = row.
+// Warp roles (640 threads, both CTAs): warp 0 weight producer (its half of every K slab), warp 1 MMA issuer (leader CTA
+// only) + TMEM owner, warp 2 stash lane, warp 3 weight-arrival helper (tells the leader that this CTA's half has
+// landed), warps 4..19 epilogue: thread = row, chunk c of warpgroup g = columns [128 c + 32 g, + 32) of both slots, so the
+// slabs fill in order.  The service warpgroup hands registers to the epilogue warps (setmaxnreg 24 / 112).
+// Fused into the tile prologue: stratified sampling (coarse pass), o + d z, positional encoding.
 //
 // Same program / argument structs, stash images and ReLU-mask layout as the one-tile kernel, so wgrad_kernel, the host
 // plans and every test are shared (dln_mlp_chain picks the kernel).
@@ -32,12 +39,12 @@ namespace {
 #ifndef DLN_CHAIN2_WG
 #define DLN_CHAIN2_WG 4
 #endif
-constexpr int k2WG = DLN_CHAIN2_WG;    // epilogue warpgroups.  4 (default): 20 warps launched with 96 registers, the service warpgroup then
-                                       // hands registers to the 16 epilogue warps (setmaxnreg 24 / 112); 2: 11 warps with 168 registers
-                                       // (measured: forward without stash 0.61 ms against 0.52 ms with four warpgroups)
-// With four epilogue warpgroups the 20 warps get 96 registers each at launch; the four service warps (one warpgroup)
-// then hand registers over with setmaxnreg (24 / 112: 128 x 24 + 512 x 112 = 60 416 of the 61 440 the CTA was launched with) -- issued INSIDE the role branches, so that the register budget
-// of each role's code is the one that dominates it (issued ahead of the branches ptxas holds all code to the minimum).
+// Epilogue warpgroups.  4 (default): 20 warps launched with 96 registers each; the four service warps (one warpgroup)
+// then hand registers over with setmaxnreg (24 / 112: 128 x 24 + 512 x 112 = 60 416 of the 61 440 the CTA was launched
+// with -- the pool is the CTA's launch allocation, 40 / 120 hangs at the inc), issued INSIDE the role branches so that
+// the register budget of each role's code is the one that dominates it (issued ahead of the branches ptxas holds all
+// code to the minimum).  2: 11 warps with 168 registers (measured: forward without stash 0.61 ms against 0.52 ms).
+constexpr int k2WG = DLN_CHAIN2_WG;
 constexpr bool k2Rebalance = k2WG == 4;
 constexpr int k2EpiWarp0 = k2WG == 4 ? 4 : 3;
 constexpr int kFastChunks = 256 / 32 / k2WG;     // 32-column chunks per thread in a 256-wide step
