@@ -17,7 +17,9 @@ Tensor = torch.Tensor
 
 
 def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+    """Raw handle of the current stream of the current device.  (torch.cuda.current_stream() builds a Stream object and
+    resolves the device index in Python: ~19 us per call, 12 calls per drop-in step; the C accessor takes ~1 us.)"""
+    return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())
 
 
 def on_device_of(argpos: int = 0, kw: Optional[str] = None):

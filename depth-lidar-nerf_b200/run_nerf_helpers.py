@@ -209,9 +209,12 @@ class NeRF(nn.Module):
         if dev.type != "cuda":
             raise RuntimeError("dlnerf_b200.NeRF: parameters are on %s; the B200 path has no CPU fallback" % dev)
         st = self._dev_state
-        names = [n for n, _ in self._shape.param_shapes()]
-        stale = st is None or st["device"] != dev or any(
-            p.data_ptr() != st["flat"].data_ptr() + 4 * pl.offsets[n] for p, n in zip(params, names))
+        names = self.__dict__.get("_param_names")
+        if names is None:
+            names = self.__dict__["_param_names"] = [n for n, _ in self._shape.param_shapes()]
+        # every parameter must still be the view of the flat buffer it was made (one list comparison: the per-parameter
+        # Python loop cost ~40 us per call, 4 calls per drop-in step)
+        stale = st is None or st["device"] != dev or [p.data_ptr() for p in params] != st["ptrs"]
         if stale:
             flat = torch.zeros(pl.n_flat, device=dev, dtype=torch.float32)     # parameters (+ folded operands M, b')
             for p, n in zip(params, names):
@@ -227,6 +230,7 @@ class NeRF(nn.Module):
                       wb=torch.zeros(pl.bwd_blob_bytes, device=dev, dtype=torch.uint8),
                       fwd_jobs=upload(pl.fwd_jobs), bwd_jobs=upload(pl.bwd_jobs), items=upload(pl.wgrad),
                       version=None, sms=torch.cuda.get_device_properties(dev).multi_processor_count)
+            st["ptrs"] = [p.data_ptr() for p in params]
             self._dev_state = st
         return st
 
@@ -374,7 +378,10 @@ class NeRF(nn.Module):
             L.call("dln_sem_unfold_grads", st["flat"].data_ptr(), gflat.data_ptr(), C.byref(pl.sem), s,
                    tag="unfold_semantic")
         grads = []
-        for (name, shp), p in zip(self._shape.param_shapes(), self._ordered_params()):
+        shapes = self.__dict__.get("_param_shapes")
+        if shapes is None:
+            shapes = self.__dict__["_param_shapes"] = self._shape.param_shapes()
+        for (name, shp), p in zip(shapes, self._ordered_params()):
             o = pl.offsets[name]
             grads.append(gflat[o: o + p.numel()].view(p.shape) if p.requires_grad else None)
         return grads
