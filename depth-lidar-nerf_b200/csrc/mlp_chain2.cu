@@ -502,6 +502,13 @@ __global__ void __launch_bounds__(k2Threads, 1)
     // quarter q (columns [16q, 16q+16)) of one encoded row (which = 0 position / 1 direction) of point p
     auto encoded_quarter = [&](long long p, bool valid, int which, int q, uint32_t (&pk)[8]) {
       float e[16];
+      if (16 * q >= 3 + 6 * (which == 0 ? prog.L_pts : prog.L_dir)) {
+        // quarter beyond the encoding's width (the direction encoding has 27 columns: quarters 2, 3 are padding): no
+        // loads, no sincosf -- these warps share their schedulers with the warps that do encode
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pk[i] = 0u;
+        return;
+      }
       if (args.x == nullptr) {
         float vx = 0.f, vy = 0.f, vz = 0.f;
         if (valid) {
@@ -664,6 +671,16 @@ __global__ void __launch_bounds__(k2Threads, 1)
           const uint32_t t_acc = tmem_base + slot * 256 + lane_addr;
           float hacc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
           bool simple = false;
+          // Early prologue (forward): the next tile's positions are encoded into registers BEFORE this (last) step's
+          // accumulator is waited for -- the coarse network's epilogue warps are idle there (its per-slot MMA -> epilogue
+          // chain is the bound), so the ~4 k cycles of sincosf per tile leave the critical path.  Stored after the heads.
+          uint32_t epk[4 / k2WG][8];
+          const bool pre = !kBwd && last && rnd + 1 < n_rounds;
+          if (pre) {
+            const long long pn = (tile + 4 * n_pairs) * DLN_TILE_ROWS + r;
+#pragma unroll
+            for (int qq = 0; qq < 4 / k2WG; ++qq) encoded_quarter(pn, pn < args.P, 0, g * (4 / k2WG) + qq, epk[qq]);
+          }
           float4 bq[8];
           auto load_b = [&](int c) {
 #pragma unroll
@@ -830,7 +847,14 @@ __global__ void __launch_bounds__(k2Threads, 1)
           if (!last) {
             if (!simple) arrive_ready(slot);
           } else if (rnd + 1 < n_rounds) {
-            prologue(slot, tile_of(rnd + 1, slot));
+            if (pre) {
+              begin_X(slot);
+#pragma unroll
+              for (int qq = 0; qq < 4 / k2WG; ++qq) store_quarter(aux + (size_t)slot * kSlab, r, g * (4 / k2WG) + qq, epk[qq]);
+              end_X(slot);
+            } else {
+              prologue(slot, tile_of(rnd + 1, slot));
+            }
             arrive_ready(slot);
           }
           if (et == 0) trace2(sm, args.trace, nev, slot * 8 + 4);
