@@ -153,7 +153,8 @@ __device__ __forceinline__ void trace2(Chain2Small* sm, const long long* trace, 
 template <int EPI>
 __device__ __forceinline__ void epi2_chunk(const uint32_t (&v)[32], const float4 (&b)[8], const float* __restrict__ hw,
                                            int n_out, int nheads, float dsig, uint32_t mw_in, uint32_t& mw_out,
-                                           float (&hacc)[5], uint32_t (&pk)[16], int cb, const float* __restrict__ semrow) {
+                                           float (&hacc)[5], uint32_t (&pk)[16], int cb, const float* __restrict__ semrow,
+                                           bool want_mask = true) {
   constexpr bool kFwd = EPI <= DLN_EPI_RELU_OUT;
   constexpr bool kRelu = EPI == DLN_EPI_RELU || EPI == DLN_EPI_RELU_SIGMA || EPI == DLN_EPI_RELU_RGB || EPI == DLN_EPI_RELU_OUT;
   float f[32];
@@ -179,7 +180,7 @@ __device__ __forceinline__ void epi2_chunk(const uint32_t (&v)[32], const float4
       }
     }
   }
-  if (kRelu) {
+  if (kRelu && want_mask) {     // (an inference pass keeps no masks: ~40 of a chunk's ~90 instructions)
     uint32_t n0 = 0, n1 = 0, n2 = 0, n3 = 0;      // sign bits -> mask word, one funnel shift per element
 #pragma unroll
     for (int i = 7; i >= 0; --i) {
@@ -727,7 +728,7 @@ __global__ void __launch_bounds__(k2Threads, 1)
                 uint32_t(&nxt)[32] = (c & 1) ? va : vb;
                 if (!kEarly && c + 1 < NCH) tmem_ld32(t_acc + col_of(c + 1), nxt);
                 const int c0 = col_of(c);
-                epi2_chunk<E>(cur, bq, hw, NCH * 32 * k2WG, 0, dsig, mi[c], mo[c], hacc, pk, c0, semrow);
+                epi2_chunk<E>(cur, bq, hw, NCH * 32 * k2WG, 0, dsig, mi[c], mo[c], hacc, pk, c0, semrow, mask_out);
                 if (c == 0 && et == 0) trace2(sm, args.trace, nev, slot * 8 + 6);
                 if (c + 1 < NCH && kNeedB) load_b(c + 1);
                 if (write_a) sts_packed32(row_addr_of(slot, c0), (c0 & 63) >> 3, pk);
