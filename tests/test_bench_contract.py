@@ -55,3 +55,17 @@ def test_b200_arm_prints_one_contract_line():
     assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and 0.05 < r["frac"] < 1.0 and "traffic" in r
     c = d["clocks"]
     assert c["sm_mhz"] > 0 and c["sm_max_mhz"] >= c["sm_mhz"] and isinstance(c["reasons"], list)
+
+
+def test_strong_scaling_mode_splits_the_global_batch():
+    """`--global-n-rand G` (config E): G rays per step over the GPUs, reported as strong scaling, same config in both arms."""
+    sys.path.insert(0, ROOT)
+    import argparse
+    import bench
+    ns = argparse.Namespace(gpus=8, n_rand=4096, global_n_rand=262144, semantic=0)
+    assert bench.rays_per_gpu(ns) == 32768 and bench.scaling_kind(ns) == "strong"
+    cfg = bench.workload_config(ns)
+    assert cfg["n_rand_per_gpu"] == 32768 and cfg["global_rays_per_step"] == 262144 and "dp8" in cfg["parallelism"]
+    ns = argparse.Namespace(gpus=2, n_rand=4096, global_n_rand=0, semantic=19)
+    assert bench.rays_per_gpu(ns) == 4096 and bench.scaling_kind(ns) == "weak"
+    assert bench.workload_config(ns)["global_rays_per_step"] == 8192 and "19 classes" in bench.workload_config(ns)["semantic_head"]

@@ -119,3 +119,24 @@ def test_full_size_banks_match_the_oracle():
     bank_d, max_depth = dn().build_depth_ray_bank(H, W, focal, poses, depth_gts, i_train, shuffle=False)
     np.testing.assert_array_equal(bank_d.cpu().numpy(), ref_d)
     assert float(max_depth) == float(ref_d[:, 3, 0].max())
+
+
+def test_bank_with_labels_feeds_the_device_loader():
+    """run_nerf.py:1153-1158 + :1195-1206: per-pixel labels follow the shuffle of the bank, and the device loader hands out
+    (rays, labels) batches of it."""
+    H, W, focal = 24, 40, 31.5
+    rs = np.random.RandomState(1)
+    poses = np.stack([np.concatenate([np.linalg.qr(rs.randn(3, 3))[0], rs.randn(3, 1)], 1) for _ in range(3)]).astype(np.float32)
+    images = rs.rand(3, H, W, 3).astype(np.float32)
+    seg = rs.randint(0, 19, (3, H, W))
+    bank, labels = dn().build_ray_bank(H, W, focal, poses, images, [0, 2], shuffle=True, segmentation_gt=seg,
+                                       generator=torch.Generator(device="cuda").manual_seed(0))
+    assert bank.shape == (2 * H * W, 3, 3) and labels.shape == (2 * H * W,)
+    # a row's colour identifies its pixel: the label of that pixel must have travelled with it
+    flat_img = torch.from_numpy(images[[0, 2]].reshape(-1, 3)).to(DEV)
+    flat_seg = torch.from_numpy(seg[[0, 2]].reshape(-1)).to(DEV)
+    idx = (bank[:, 2][:, None, :] == flat_img[None, :64, :]).all(-1).float().argmax(0)      # rows holding the first 64 pixels
+    assert torch.equal(labels[idx], flat_seg[:64])
+    loader = dn().DeviceRayLoader(bank, batch_size=500, semantic_data=labels, device=DEV)
+    rays, lab = next(iter(loader))
+    assert rays.shape == (500, 3, 3) and lab.shape == (500,) and rays.is_cuda
