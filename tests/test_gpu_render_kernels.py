@@ -220,6 +220,44 @@ def test_importance_resample(N, S, Ni):
     assert (zm_det[:, 1:] >= zm_det[:, :-1]).all()
 
 
+@pytest.mark.parametrize("N", [1, 97, 4096 + 17])
+def test_importance_resample_thread_per_ray_kernel(N, monkeypatch):
+    """The 64 + 64 shape has two kernels (render_kernels.cu: warp per ray below 32 768 rays, thread per ray above):
+    same bits from both, for injected u, the deterministic u and the in-kernel Philox draws, with the rays of a
+    partial last warp included; and the thread-per-ray kernel alone against the reference arithmetic."""
+    S = Ni = 64
+    g = torch.Generator().manual_seed(1000 + N)
+    z = torch.sort(torch.rand(N, S, generator=g), dim=-1)[0]
+    w = torch.rand(N, S, generator=g) ** 6
+    w[0] = 0.0
+    w[N // 2, 5:] = 0.0                                            # a cdf that saturates early: denom < 1e-5 -> 1
+    u = torch.rand(N, Ni, generator=g)
+    u[0, :4] = torch.tensor([0.0, 1.0 - 2.0 ** -24, 0.5, 1e-38])   # ends of the range, a numerator div.rn's fast path rejects
+    zd, wd, ud = z.to(DEV), w.to(DEV), u.to(DEV)
+    st = dn().ops.RngState(DEV, 1234)
+    out = {}
+    for mode in ("warp", "thread"):
+        monkeypatch.setenv("DLN_RESAMPLE", mode)
+        out[mode] = (dn().ops.importance_resample(zd, wd, Ni, ud, return_debug=True),
+                     dn().ops.importance_resample(zd, wd, Ni, None, return_debug=True),
+                     None,
+                     dn().ops.importance_resample(zd, wd, Ni, rng=(st, 7)))
+    for case in (0, 1, 3):
+        for a, b in zip(out["warp"][case], out["thread"][case]):
+            assert torch.equal(a, b), "warp-per-ray and thread-per-ray kernels differ (case %d)" % case
+    zs, zm, cdf, inds = out["thread"][0]
+    mids = 0.5 * (z[:, 1:] + z[:, :-1])
+    report("cdf (thread per ray)", cdf, O.pdf_to_cdf(w[:, 1:-1]), atol=5e-7)
+    assert torch.equal(inds.cpu(), torch.searchsorted(cdf.cpu(), u, right=True))
+    assert torch.equal(zs.cpu(), O.invert_cdf(mids, cdf.cpu(), u)[0]), "inversion must be bit exact on identical cdf"
+    assert torch.equal(zm.cpu(), torch.sort(torch.cat([z, zs.cpu()], -1), -1)[0])
+    # a weights view that is not 4 bytes past a 16-byte boundary takes the scalar-load instantiation
+    w_off = torch.zeros(N * S + 3, device=DEV)[3:].view(N, S)
+    w_off.copy_(wd)
+    zs2, zm2 = dn().ops.importance_resample(zd, w_off, Ni, ud)
+    assert torch.equal(zs2, zs) and torch.equal(zm2, zm)
+
+
 # ---------------------------------------------------------------------------------------- searchsorted
 def test_searchsorted_grid_golden(golden_dir):
     g = np.load(os.path.join(golden_dir, "searchsorted.npz"))
