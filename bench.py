@@ -10,8 +10,9 @@ step excluded as in BASELINE.md §3.  For N>1 every rank renders its own N_rand 
 MLP gradients are all-reduced over NCCL inside the step.
 
 Prints ONE JSON line (see the task contract): `value` = rays/s with the ray batch resident in HBM;
-`e2e` = the same step through the drop-in API from pinned HOST buffers (H2D of the ray batch + targets,
-D2H of the loss, every step); `roofline` for the dominant kernel from CUDA events recorded around every
+`e2e` = the same step through the drop-in API from pinned HOST buffers (H2D of the ray batch + targets and a
+non-blocking D2H of the loss every step, one synchronize behind the K steps; `e2e.sync_every_step` = the same with
+`loss.item()` after every step); `roofline` for the dominant kernel from CUDA events recorded around every
 launch of the timed region; `cpu_baseline` = the oracle port of the reference on the host cores.
 
 `--impl reference` times the reference's own CPU implementation (the oracle port: the reference is Python
@@ -525,27 +526,60 @@ def run_ours(args):
     e2e_api = ("dlnerf_b200.train_step(...) (ray-chunked; the drop-in autograd route cannot hold %d rays)" % args.n_rand
                if big else "dlnerf_b200.render(...) + img2mse + loss.backward() (drop-in path)")
 
-    def e2e_step(fn=None):
+    # The loss of every step is read back to the host.  Headline: a non-blocking 4-byte copy into pinned memory per step
+    # and one synchronize behind the K steps -- the reference's loop reads its loss every i_print = 100 iterations
+    # (run_nerf.py:1943-1959) and otherwise never waits for the device, so the host runs ahead of the GPU there too.
+    # `sync_every_step` is the same loop with `.item()` after every step (the host then starts each step with an idle GPU).
+    loss_ring = torch.zeros(64, dtype=torch.float32).pin_memory()
+    ring_i = [0]
+
+    def read_back(loss):
+        loss_ring[ring_i[0] & 63].copy_(loss.detach().reshape(()), non_blocking=True)
+        ring_i[0] += 1
+
+    def e2e_step(fn=None, wait=False):
         r = host_rays.to(dev, non_blocking=True)
         t1 = host_tgt.to(dev, non_blocking=True)
         t2 = host_dep.to(dev, non_blocking=True)
-        return float((fn or e2e_fn)(r, t1, t2).item())
+        loss = (fn or e2e_fn)(r, t1, t2)
+        if wait:
+            return float(loss.item())
+        read_back(loss)
 
     h2d = int(host_rays.numel() + host_tgt.numel() + host_dep.numel()) * 4
     for _ in range(3):
+        e2e_step(wait=True)
+    ms_sync = timed(lambda: e2e_step(wait=True), args.steps)
+    for _ in range(max(args.warmup, 3)):          # the host runs several steps ahead here: let the allocator grow first
         e2e_step()
     ms_e2e = timed(e2e_step, args.steps)
+    torch.cuda.synchronize()
+    seen = loss_ring[:min(ring_i[0], 64)]
+    assert bool(torch.isfinite(seen).all()) and bool((seen > 0).all()), "read-back losses must be finite: %s" % seen
     e2e = {"value": args.n_rand * world / (ms_e2e * 1e-3), "unit": "rays/s", "ms_per_step": ms_e2e,
-           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "api": e2e_api}
+           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "api": e2e_api,
+           "loss_read": "non-blocking D2H copy of the loss into pinned memory every step, one synchronize behind the K "
+                        "steps (the reference reads its loss every i_print = 100 iterations, run_nerf.py:1943-1959)",
+           "sync_every_step": {"value": args.n_rand * world / (ms_sync * 1e-3), "unit": "rays/s", "ms_per_step": ms_sync,
+                               "loss_read": "loss.item() after every step"}}
     if graphed is not None:
         # same host-buffer protocol through the CUDA-graph step (pinned host tensors are copied straight into the
-        # graph's static inputs, loss read back with .item())
-        def e2e_graph_step():
-            return float(graphed(host_rays, host_tgt, host_dep, target_semantic=d_sem)["loss"].item())
+        # graph's static inputs)
+        def e2e_graph_step(wait=False):
+            loss = graphed(host_rays, host_tgt, host_dep, target_semantic=d_sem)["loss"]
+            if wait:
+                return float(loss.item())
+            read_back(loss)
+        for _ in range(3):
+            e2e_graph_step(wait=True)
+        ms_gs = timed(lambda: e2e_graph_step(wait=True), args.steps)
         for _ in range(3):
             e2e_graph_step()
         ms_g = timed(e2e_graph_step, args.steps)
+        torch.cuda.synchronize()
         e2e["graph_route"] = {"value": args.n_rand * world / (ms_g * 1e-3), "unit": "rays/s", "ms_per_step": ms_g,
+                              "sync_every_step": {"value": args.n_rand * world / (ms_gs * 1e-3), "unit": "rays/s",
+                                                  "ms_per_step": ms_gs},
                               "api": "dlnerf_b200.GraphedTrainStep(...)(host_rays, host_target_s, host_target_depth)"}
 
     # ---- the same step with the semantic head on, reported next to the headline (one GPU only) ---------------

@@ -50,6 +50,8 @@ def test_b200_arm_prints_one_contract_line():
     e = d["e2e"]
     assert e["value"] > 0 and e["unit"] == "rays/s" and e["h2d_bytes_per_step"] == (2 * 4096 * 3 + 2048 * 3 + 2048) * 4
     assert e["d2h_bytes_per_step"] == 4 and e["value"] <= 1.05 * d["value"]
+    # the loss is read back every step either way; waiting for it after every step can only be slower
+    assert 0 < e["sync_every_step"]["value"] <= 1.02 * e["value"] and "loss_read" in e
     r = d["roofline"]
     assert r["bound"] in ("tensor", "hbm") and r["unit"] in ("TFLOP/s", "GB/s")
     assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and 0.05 < r["frac"] < 1.0 and "traffic" in r
