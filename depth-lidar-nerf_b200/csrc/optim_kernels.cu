@@ -66,35 +66,17 @@ __global__ void __launch_bounds__(256) fold_kernel(float* __restrict__ flat, Fol
   }
 }
 
+// 32 x 32 output tiles, 256 threads, 2 x 2 outputs per thread, K in steps of 32 through shared memory (the first
+// version gave every CTA a whole row and re-read all of W_f / dM from L2 per row: 64 MB of L2 reads, 23 us).
+//   blocks [0, 32)    : dW_v1[i][k] += sum_j dM[i][j] W_f[k][j] + db'_i b_f[k]      (128 x 256, K = 256, "NT")
+//   blocks [32, 96)   : dW_f[k][j]  += sum_i W_v1[i][k] dM[i][j]                    (256 x 256, K = 128, "TN")
+//   block 96          : db_f[k] += sum_i W_v1[i][k] db'_i ;  db_v[i] += db'_i
 __global__ void __launch_bounds__(256) unfold_kernel(const float* __restrict__ flat, float* __restrict__ g, FoldOffsets o) {
-  __shared__ float sh[256];
-  __shared__ float out[256];
-  const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  if (b < 128) {                 // row i of dW_v1: (W_f dM_i)[k] + db'_i b_f[k]; a warp per k, lanes over j
-    const int i = b;
-    sh[t] = g[o.M + i * 256 + t];
-    __syncthreads();
-    const float dbi = g[o.bM + i];
-#pragma unroll 4
-    for (int k = warp; k < 256; k += 8) {      // 4 rows of W_f in flight per warp
-      const float* wf = flat + o.wf + k * 256;
-      float acc = 0.f;
-#pragma unroll
-      for (int q = 0; q < 8; ++q) acc = fmaf(sh[q * 32 + lane], __ldg(wf + q * 32 + lane), acc);
-      acc = dln::warp_sum(acc);
-      if (lane == 0) out[k] = acc;
-    }
-    __syncthreads();           // one coalesced read-modify-write of the gradient row instead of 256 dependent ones
-    g[o.wv + (long long)i * o.ldv + t] += out[t] + dbi * __ldg(flat + o.bf + t);
-  } else if (b < 384) {          // row k of dW_f: sum_i Wv[i][k] dM[i][:]
-    const int k = b - 128;
-    if (t < 128) sh[t] = flat[o.wv + (long long)t * o.ldv + k];
-    __syncthreads();
-    float acc = 0.f;
-#pragma unroll 16
-    for (int i = 0; i < 128; ++i) acc = fmaf(sh[i], g[o.M + i * 256 + t], acc);
-    g[o.wf + k * 256 + t] += acc;
-  } else {                       // biases
+  __shared__ float As[32][33];     // [m][k]
+  __shared__ float Bs[32][33];     // [n][k]
+  const int b = blockIdx.x, t = threadIdx.x;
+  if (b == 96) {
+    float* sh = &As[0][0];
     if (t < 128) sh[t] = g[o.bM + t];
     __syncthreads();
     float acc = 0.f;
@@ -102,7 +84,46 @@ __global__ void __launch_bounds__(256) unfold_kernel(const float* __restrict__ f
     for (int i = 0; i < 128; ++i) acc = fmaf(__ldg(flat + o.wv + (long long)i * o.ldv + t), sh[i], acc);
     g[o.bf + t] += acc;
     if (t < 128) g[o.bv + t] += sh[t];
+    return;
   }
+  const bool nt = b < 32;
+  const int tile = nt ? b : b - 32;
+  const int m0 = (tile >> 3) * 32, n0 = (tile & 7) * 32;          // 8 tiles across the 256 output columns
+  const int K = nt ? 256 : 128;
+  const int lr = t >> 5, lc = t & 31;                              // loader: row lr + 8 p, column lc
+  const int ty = t >> 4, tx = t & 15;                              // outputs (2 ty + {0,1}, 2 tx + {0,1})
+  float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  for (int k0 = 0; k0 < K; k0 += 32) {
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const int r = lr + 8 * p;
+      if (nt) {
+        As[r][lc] = g[o.M + (m0 + r) * 256 + k0 + lc];                              // dM[i][j]
+        Bs[r][lc] = __ldg(flat + o.wf + (n0 + r) * 256 + k0 + lc);                   // W_f[k][j]
+      } else {
+        As[lc][r] = __ldg(flat + o.wv + (long long)(k0 + r) * o.ldv + m0 + lc);      // W_v1[i][k] -> [k][i]
+        Bs[lc][r] = g[o.M + (k0 + r) * 256 + n0 + lc];                               // dM[i][j]   -> [j][i]
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      const float a0 = As[2 * ty][k], a1 = As[2 * ty + 1][k], b0 = Bs[2 * tx][k], b1 = Bs[2 * tx + 1][k];
+      acc[0][0] = fmaf(a0, b0, acc[0][0]), acc[0][1] = fmaf(a0, b1, acc[0][1]);
+      acc[1][0] = fmaf(a1, b0, acc[1][0]), acc[1][1] = fmaf(a1, b1, acc[1][1]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int y = 0; y < 2; ++y)
+#pragma unroll
+    for (int x = 0; x < 2; ++x) {
+      const int m = m0 + 2 * ty + y, n = n0 + 2 * tx + x;
+      if (nt)
+        g[o.wv + (long long)m * o.ldv + n] += acc[y][x] + g[o.bM + m] * __ldg(flat + o.bf + n);
+      else
+        g[o.wf + m * 256 + n] += acc[y][x];
+    }
 }
 
 }  // namespace
@@ -123,7 +144,7 @@ extern "C" int dln_mlp_unfold_grads(const float* params_flat, float* grads_flat,
   DLN_CHECK_ARG(params_flat && grads_flat && ld_views >= 256 && off_views_w >= 0 && off_feature_w >= 0 &&
                 off_feature_b >= 0 && off_views_b >= 0 && off_M >= 0 && off_bM >= 0);
   const FoldOffsets o{off_views_w, off_feature_w, off_feature_b, off_views_b, off_M, off_bM, ld_views};
-  unfold_kernel<<<385, 256, 0, (cudaStream_t)stream>>>(params_flat, grads_flat, o);
+  unfold_kernel<<<97, 256, 0, (cudaStream_t)stream>>>(params_flat, grads_flat, o);
   return dln_launch_status();
 }
 
