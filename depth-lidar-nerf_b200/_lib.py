@@ -85,6 +85,8 @@ SIGNATURES = {
     "dln_composite_bwd_rng": [_P, _I, _P, _P, _P, _U64, _F, _I, _P, _P, _P, _P, _P, _P, _I, _I, _P],
     "dln_composite_bwd_fused_loss_dev": [_P, _I, _P, _P, _P, _P, _U64, _F, _I, _P, _P, _P, _I, _P, _I, _P, _P, _I, _I, _P],
     "dln_sample_pdf_rng": [_P, _I, _I, _P, _I, _I, _P, _U64, _I, _P, _P, _I, _P, _P, _P, _I, _P],
+    "dln_composite_resample_fwd": [_P, _I, _P, _P, _P, _P, _U64, _F, _I, _P, _P, _P, _P, _P, _P, _P, _U64, _I, _P, _P, _I,
+                                   _I, _P],
     "dln_posenc": [_P, _P, _LL, _I, _P],
     "dln_composite_fwd": [_P, _I, _P, _P, _P, _F, _I, _P, _P, _P, _P, _P, _I, _I, _P],
     "dln_composite_bwd": [_P, _I, _P, _P, _P, _F, _I, _P, _P, _P, _P, _P, _P, _I, _I, _P],

@@ -436,6 +436,34 @@ def importance_resample(z_vals: Tensor, weights: Tensor, n_importance: int, u: O
     return zs, zm
 
 
+def composite_resample(raw: Tensor, z_vals: Tensor, rays_d: Tensor, noise: Optional[Tensor], noise_std: float,
+                       white_bkgd: bool, n_importance: int, u: Optional[Tensor] = None, rng_noise: Rng = None,
+                       rng_u: Rng = None):
+    """``composite`` (values only, no autograd node) + ``importance_resample`` of its weights in one launch
+    (run_nerf.py:600-636) for 64 coarse and <= 64 new samples; the same bits as the two calls.  Returns
+    (rgb_map, disp_map, acc_map, weights, depth_map, z_samples, z_merged)."""
+    raw_c, z, d = _f32(raw, "composite_resample"), _f32(z_vals, "composite_resample"), _f32(rays_d, "composite_resample")
+    N, S, Cc = raw_c.shape
+    if S != 64 or not 1 <= n_importance <= 64:
+        raise ValueError("composite_resample: 64 coarse and at most 64 new samples (got %d + %d)" % (S, n_importance))
+    nz = None if noise is None else _f32(noise, "composite_resample")
+    uu = None if u is None else _f32(u, "composite_resample")
+    rn = None if nz is not None else rng_noise
+    ru = None if uu is not None else rng_u
+    dev = raw_c.device
+    rgb = torch.empty(N, 3, device=dev)
+    disp, acc, depth = torch.empty(N, device=dev), torch.empty(N, device=dev), torch.empty(N, device=dev)
+    w = torch.empty(N, S, device=dev)
+    zs = torch.empty(N, n_importance, device=dev)
+    zm = torch.empty(N, S + n_importance, device=dev)
+    L.call("dln_composite_resample_fwd", raw_c.data_ptr(), Cc, z.data_ptr(), d.data_ptr(), _ptr(nz),
+           rn[0].ptr() if rn else None, int(rn[1]) if rn else 0, float(noise_std), int(white_bkgd), rgb.data_ptr(),
+           disp.data_ptr(), acc.data_ptr(), w.data_ptr(), depth.data_ptr(), _ptr(uu), ru[0].ptr() if ru else None,
+           int(ru[1]) if ru else 0, int(n_importance), zs.data_ptr(), zm.data_ptr(), N, S, _stream(),
+           tag="composite_resample")
+    return rgb, disp, acc, w, depth, zs, zm
+
+
 def searchsorted(a: Tensor, v: Tensor, side: str = "left") -> Tensor:
     """Contract of the vendored torchsearchsorted extension (searchsorted.py:20-53)."""
     if side not in ("left", "right"):

@@ -297,10 +297,17 @@ def train_step(H, W, focal, batch_rays: Tensor, target_s: Tensor, target_depth: 
                                                       force_pack=_force_pack and c == 0, **sem_kw(N_samples))
         raw0 = raw0.view(Nc, N_samples, -1)
         noise0, g_n0 = draw("noise0", 1) if raw_noise_std > 0. else (None, None)
-        rgb0, disp0, acc0, w0, depth0 = ops.composite(raw0, z0, rays_d, noise0, float(raw_noise_std),
-                                                      bool(white_bkgd), rng=g_n0)
         u, g_u = draw("u", 2) if perturb != 0. else (None, None)
-        z_samples, z1 = ops.importance_resample(z0, w0, N_importance, u, rng=g_u)
+        if N_samples == 64 and 1 <= N_importance <= 64 and not _os.environ.get("DLN_NO_FUSED_RESAMPLE"):
+            # raw2outputs of the coarse pass and the resampling of its weights in one launch (both are launch-latency
+            # class at 4096 rays; same bits as the two calls below)
+            rgb0, disp0, acc0, w0, depth0, z_samples, z1 = ops.composite_resample(
+                raw0, z0, rays_d, noise0, float(raw_noise_std), bool(white_bkgd),
+                N_importance, u, rng_noise=g_n0, rng_u=g_u)
+        else:
+            rgb0, disp0, acc0, w0, depth0 = ops.composite(raw0, z0, rays_d, noise0, float(raw_noise_std),
+                                                          bool(white_bkgd), rng=g_n0)
+            z_samples, z1 = ops.importance_resample(z0, w0, N_importance, u, rng=g_u)
         side = None
         grads_c = None
 

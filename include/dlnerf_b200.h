@@ -127,6 +127,17 @@ int dln_sample_pdf_rng(const float* bins, int bins_stride, int mid_from_z, const
                        float* samples, const float* z_coarse, int S, float* z_merged, float* cdf_out,
                        long long* inds_out, int N, void* stream);
 
+/* raw2outputs of the coarse pass (dln_composite_fwd / _rng) followed by the hierarchical resampling of its weights
+ * (dln_sample_pdf / _rng with the merge; run_nerf.py:600-636) in ONE launch, for S = 64 coarse and n_samples <= 64
+ * new samples -- the same bits as the two calls.  noise / noise_rng_state and u / u_rng_state are alternatives
+ * (both null: no density noise / deterministic linspace u); weights may be null. */
+int dln_composite_resample_fwd(const float* raw, int raw_ch, const float* z_vals, const float* rays_d, const float* noise,
+                               const unsigned long long* noise_rng_state, unsigned long long noise_rng_offset,
+                               float noise_std, int white_bkgd, float* rgb_map, float* disp_map, float* acc_map,
+                               float* weights, float* depth_map, const float* u, const unsigned long long* u_rng_state,
+                               unsigned long long u_rng_offset, int n_samples, float* samples, float* z_merged, int N,
+                               int S, void* stream);
+
 /* Batched row-wise search with row broadcast: the contract of the vendored extension
  * torchsearchsorted/src/cuda/searchsorted_cuda_kernel.cu:110-142 (searchsorted.py:20-53). */
 int dln_searchsorted(const float* a, int rows_a, int A, const float* v, int rows_v, int V, long long* out,

@@ -258,6 +258,28 @@ def test_importance_resample_thread_per_ray_kernel(N, monkeypatch):
     assert torch.equal(zs2, zs) and torch.equal(zm2, zm)
 
 
+@pytest.mark.parametrize("N,Ni,C", [(1, 64, 4), (301, 64, 4), (77, 40, 4), (130, 64, 7)])
+def test_composite_resample_fused_launch(N, Ni, C):
+    """dln_composite_resample_fwd (coarse raw2outputs + hierarchical resampling in one launch, what train_step calls)
+    returns the bits of the two separate calls -- injected draws, in-kernel draws, and neither."""
+    S = 64
+    g = torch.Generator().manual_seed(5 * N + Ni)
+    raw = (torch.randn(N, S, C, generator=g) * 2).to(DEV)
+    z = torch.sort(torch.rand(N, S, generator=g), -1)[0].to(DEV)
+    rd = torch.randn(N, 3, generator=g).to(DEV)
+    noise = torch.randn(N, S, generator=g).to(DEV)
+    u = torch.rand(N, Ni, generator=g).to(DEV)
+    st = dn().ops.RngState(DEV, 99)
+    for nz, uu, rn, ru, std in ((noise, u, None, None, 1.0), (None, None, (st, 3), (st, 5), 1.0), (None, None, None, None, 0.0)):
+        sep = dn().ops.composite(raw, z, rd, nz, std, False, rng=rn)
+        zs, zm = dn().ops.importance_resample(z, sep[3], Ni, uu, rng=ru)
+        fused = dn().ops.composite_resample(raw, z, rd, nz, std, False, Ni, uu, rng_noise=rn, rng_u=ru)
+        for name, a, b in zip(("rgb", "disp", "acc", "weights", "depth", "z_samples", "z_merged"), fused, list(sep) + [zs, zm]):
+            assert torch.equal(a, b) or (torch.isnan(a) == torch.isnan(b)).all() and torch.equal(a.nan_to_num(), b.nan_to_num()), name
+    with pytest.raises(ValueError):
+        dn().ops.composite_resample(raw[:, :32], z[:, :32], rd, None, 0.0, False, Ni)
+
+
 # ---------------------------------------------------------------------------------------- searchsorted
 def test_searchsorted_grid_golden(golden_dir):
     g = np.load(os.path.join(golden_dir, "searchsorted.npz"))
