@@ -258,6 +258,28 @@ def test_importance_resample_thread_per_ray_kernel(N, monkeypatch):
     assert torch.equal(zs2, zs) and torch.equal(zm2, zm)
 
 
+def test_importance_resample_default_dispatch_at_config_e_size(monkeypatch):
+    """32 768 + 50 rays (a config-E chunk): the default dispatch takes the thread-per-ray kernel there; its output equals
+    the warp-per-ray kernel's and sort(cat(z_vals, z_samples)), with live Philox draws and with injected u."""
+    N, S, Ni = 32768 + 50, 64, 64
+    g = torch.Generator().manual_seed(77)
+    z = torch.sort(torch.rand(N, S, generator=g), dim=-1)[0].to(DEV)
+    w = (torch.rand(N, S, generator=g) ** 8).to(DEV)
+    u = torch.rand(N, Ni, generator=g).to(DEV)
+    st = dn().ops.RngState(DEV, 4321)
+    monkeypatch.delenv("DLN_RESAMPLE", raising=False)
+    zs_d, zm_d = dn().ops.importance_resample(z, w, Ni, u)
+    zs_r, zm_r = dn().ops.importance_resample(z, w, Ni, rng=(st, 2))
+    monkeypatch.setenv("DLN_RESAMPLE", "warp")
+    zs_w, zm_w = dn().ops.importance_resample(z, w, Ni, u)
+    zs_rw, zm_rw = dn().ops.importance_resample(z, w, Ni, rng=(st, 2))
+    assert torch.equal(zs_d, zs_w) and torch.equal(zm_d, zm_w) and torch.equal(zs_r, zs_rw) and torch.equal(zm_r, zm_rw)
+    assert torch.equal(zm_d, torch.sort(torch.cat([z, zs_d], -1), -1)[0])
+    assert torch.equal(zm_r, torch.sort(torch.cat([z, zs_r], -1), -1)[0])
+    mids = 0.5 * (z[:, 1:] + z[:, :-1])
+    assert (zs_r >= mids[:, :1] - 1e-6).all() and (zs_r <= mids[:, -1:] + 1e-6).all()
+
+
 @pytest.mark.parametrize("N,Ni,C", [(1, 64, 4), (301, 64, 4), (77, 40, 4), (130, 64, 7)])
 def test_composite_resample_fused_launch(N, Ni, C):
     """dln_composite_resample_fwd (coarse raw2outputs + hierarchical resampling in one launch, what train_step calls)
