@@ -15,6 +15,7 @@ Usage:  python oracle/make_golden.py                    (re-writes tests/golden/
         python oracle/make_golden.py --only-semantic    (re-writes tests/golden/semantic.npz only)
         python oracle/make_golden.py --only-raygen      (re-writes tests/golden/raygen.npz only)
         python oracle/make_golden.py --only-w256        (re-writes tests/golden/mlp_w256.npz only)
+        python oracle/make_golden.py --only-w256-d4     (re-writes tests/golden/mlp_w256_d4.npz only)
 """
 from __future__ import annotations
 
@@ -287,16 +288,17 @@ def raygen_section(H, R, out_dir):
     np.savez_compressed(os.path.join(out_dir, "raygen.npz"), **fix)
 
 
-def mlp_w256_section(H, R, out_dir):
-    """A full-width (W = 256, D = 8, view directions) case the CUDA MLP can evaluate directly: the UNMODIFIED reference
-    module's forward and parameter gradients on 160 points (one full 128-point tile + a partial one).  Parameters are
-    regenerated from the seed (tests/golden/param_guard.npz pins the generator); big gradient tensors are kept as every
-    16th row."""
-    print("mlp W=256")
-    g = torch.Generator().manual_seed(77)
-    spec = O.MLPSpec(D=8)
-    params = O.trained_like(O.init_params(spec, seed=3407 + 8), 1.0)
-    net = H.NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True)
+def mlp_w256_section(H, R, out_dir, D=8, fname="mlp_w256.npz"):
+    """A full-width (W = 256, view directions) case the CUDA MLP can evaluate directly: the UNMODIFIED reference
+    module's forward and parameter gradients on 160 points (one full 128-point tile + a partial one), for the fine
+    network (D = 8, mlp_w256.npz) and the coarse network of every shipped config (D = 4: the skip never fires,
+    mlp_w256_d4.npz).  Parameters are regenerated from the seed (tests/golden/param_guard.npz pins the generator); big
+    gradient tensors are kept as every 16th row."""
+    print("mlp W=256 D=%d" % D)
+    g = torch.Generator().manual_seed(77 if D == 8 else 77 + D)
+    spec = O.MLPSpec(D=D)
+    params = O.trained_like(O.init_params(spec, seed=3407 + D), 1.0)
+    net = H.NeRF(D=D, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True)
     net.load_state_dict(params)
     pts = (torch.rand(160, 3, generator=g) * 2 - 1) * 1.2
     dirs = torch.nn.functional.normalize(torch.randn(160, 3, generator=g), dim=-1)
@@ -308,13 +310,13 @@ def mlp_w256_section(H, R, out_dir):
     (y_ref * cot).sum().backward()
     pl = {k: v.clone().requires_grad_(True) for k, v in params.items()}
     (O.mlp_forward(pl, xin, spec) * cot).sum().backward()
-    fix = {"x": np_(xin), "y": np_(y_ref), "cot": np_(cot), "seed": np.array([3407 + 8]), "sigma_bias": np.array([1.0])}
+    fix = {"x": np_(xin), "y": np_(y_ref), "cot": np_(cot), "seed": np.array([3407 + D]), "sigma_bias": np.array([1.0])}
     for k, v in net.named_parameters():
         close(pl[k].grad, v.grad, 1e-4, "  grad " + k)
         gr = np_(v.grad)
         fix["g_" + k] = gr[::16] if gr.ndim == 2 and gr.shape[0] >= 128 else gr
         fix["gn_" + k] = np.array([float(v.grad.double().norm())])
-    np.savez_compressed(os.path.join(out_dir, "mlp_w256.npz"), **fix)
+    np.savez_compressed(os.path.join(out_dir, fname), **fix)
 
 
 def main():
@@ -329,6 +331,9 @@ def main():
         return
     if "--only-w256" in sys.argv:
         mlp_w256_section(H, R, out_dir)
+        return
+    if "--only-w256-d4" in sys.argv:
+        mlp_w256_section(H, R, out_dir, D=4, fname="mlp_w256_d4.npz")
         return
     torch.manual_seed(3407)
     g = torch.Generator().manual_seed(3407)
@@ -546,6 +551,7 @@ def main():
     semantic_section(H, R, out_dir)
     raygen_section(H, R, out_dir)
     mlp_w256_section(H, R, out_dir)
+    mlp_w256_section(H, R, out_dir, D=4, fname="mlp_w256_d4.npz")
     print("golden vectors written to", out_dir)
 
 

@@ -245,18 +245,21 @@ def test_full_size_backward_is_additive_over_points():
     assert all(torch.isfinite(x).all() for x in full)
 
 
-def test_reference_generated_w256_case(golden_dir):
-    """tests/golden/mlp_w256.npz: forward and parameter gradients of the UNMODIFIED reference NeRF(D=8, W=256) on 160
-    points, pushed through the CUDA MLP directly (no test-side twin in between).  Tolerances as in the header."""
-    g = np.load(os.path.join(golden_dir, "mlp_w256.npz"))
-    spec = O.MLPSpec(D=8)
+@pytest.mark.parametrize("D,fname", [(8, "mlp_w256.npz"), (4, "mlp_w256_d4.npz")])
+def test_reference_generated_w256_case(golden_dir, D, fname):
+    """tests/golden/mlp_w256.npz, mlp_w256_d4.npz: forward and parameter gradients of the UNMODIFIED reference
+    NeRF(W=256) -- the fine network (D=8) and the coarse network of every shipped config (D=4, the skip never fires) --
+    on 160 points, pushed through the CUDA MLP directly (no test-side twin in between).  Tolerances as in the header."""
+    g = np.load(os.path.join(golden_dir, fname))
+    spec = O.MLPSpec(D=D)
     params = O.trained_like(O.init_params(spec, seed=int(g["seed"][0])), float(g["sigma_bias"][0]))
-    net = dn().NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True)
+    net = dn().NeRF(D=D, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True)
     net.load_state_dict(params)
     net = net.to(DEV)
     y = net(torch.from_numpy(g["x"]).to(DEV))
     ref = torch.from_numpy(g["y"])
-    report("NeRF(W=256) forward vs the reference module", y, ref, atol=3e-2 * ref.abs().max().item())
+    # measured 3.8e-4 (D=8) / 3.3e-4 (D=4) with max|ref| ~ 1.05: bf16 rounding of ~10 layers; bound = 2x
+    report("NeRF(W=256, D=%d) forward vs the reference module" % D, y, ref, atol=8e-4 * ref.abs().max().item())
     (y * torch.from_numpy(g["cot"]).to(DEV)).sum().backward()
     worst_cos, worst_l2, num, den = 1.0, 0.0, 0.0, 0.0
     for k, p in net.named_parameters():

@@ -163,10 +163,11 @@ def test_ray_generators(golden_dir):
         assert grad[0].shape == (gH * gW, 3) and nograd[0].shape == (nH * nW - gH * gW, 3)
 
 
-def test_mlp_w256_reference_case(golden_dir):
-    """The full-width case generated by the unmodified reference module (forward + every parameter gradient)."""
-    g = load(golden_dir, "mlp_w256.npz")
-    spec = O.MLPSpec(D=8)
+@pytest.mark.parametrize("D,fname", [(8, "mlp_w256.npz"), (4, "mlp_w256_d4.npz")])
+def test_mlp_w256_reference_case(golden_dir, D, fname):
+    """The full-width cases generated by the unmodified reference module (forward + every parameter gradient)."""
+    g = load(golden_dir, fname)
+    spec = O.MLPSpec(D=D)
     params = O.trained_like(O.init_params(spec, seed=int(g["seed"][0])), float(g["sigma_bias"][0]))
     pl = {k: v.clone().requires_grad_(True) for k, v in params.items()}
     y = O.mlp_forward(pl, T(g["x"]), spec)
